@@ -1,0 +1,116 @@
+/*
+ * b200raster.h -- C ABI of libb200raster.so, the B200 (sm_100a) differentiable
+ * mesh rasterizer that drops in behind Jittor/jrender's rasterizer Functions.
+ *
+ * Every entry point replaces one `jt.code(...)` op of the reference (paths are
+ * relative to the reference checkout):
+ *
+ *   b200r_softras_forward   <- jrender/renderer/dr/softras/cuda/soft_rasterize.py:3-521
+ *                              (forward_soft_rasterize: memsets + K1 + K2), called from
+ *                              jrender/renderer/dr/softras/soft_rasterize.py:75-82; also
+ *                              serves the bin_size>0 call site (:91-99,
+ *                              soft_rasterize_coarse_to_fine.py:7-879) -- binning is
+ *                              internal here and exact, so one entry point covers both.
+ *   b200r_softras_backward  <- jrender/renderer/dr/softras/cuda/soft_rasterize.py:966-1416
+ *                              (backward_soft_rasterize, top-K), called from
+ *                              jrender/renderer/dr/softras/soft_rasterize.py:125-132.
+ *   b200r_nmr_forward       <- jrender/renderer/dr/n3mr/cuda/rasterize.py:5-217 and :219-339
+ *                              (forward_face_index_map + forward_texture_sampling),
+ *                              called from jrender/renderer/dr/n3mr/n3mr.py:125-133.
+ *   b200r_nmr_backward      <- jrender/renderer/dr/n3mr/cuda/rasterize.py:342-648, :650-727,
+ *                              :729-822 (backward_pixel_map, backward_textures,
+ *                              backward_depth_map), called from n3mr.py:29-67.
+ *
+ * Conventions
+ *   - All tensor pointers are DEVICE pointers owned by the caller (contiguous, fp32 /
+ *     int32).  No allocation and no host synchronisation happens inside; all work is
+ *     enqueued on `stream` (a cudaStream_t passed as void*; NULL = legacy default stream).
+ *   - Scalar parameters are runtime arguments (the reference bakes them into JIT source).
+ *   - Return 0 on success; a negative B200R_E* code for argument errors; a positive
+ *     cudaError_t for CUDA failures.  b200r_last_error() returns a thread-local message.
+ *   - There is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef B200RASTER_H
+#define B200RASTER_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define B200R_API __attribute__((visibility("default")))
+#else
+#define B200R_API
+#endif
+
+#define B200R_EINVAL (-1)      /* bad argument (NULL pointer, size, enum out of range) */
+#define B200R_EWORKSPACE (-2)  /* workspace too small */
+#define B200R_EUNSUPPORTED (-3)
+
+/* enum values = the reference's maps, jrender/renderer/dr/softras/soft_rasterize.py:39-42 */
+enum { B200R_DIST_HARD = 0, B200R_DIST_BARYCENTRIC = 1, B200R_DIST_EUCLIDEAN = 2 };
+enum { B200R_RGB_HARD = 0, B200R_RGB_SOFTMAX = 1, B200R_RGB_NONE = 2 };
+enum { B200R_ALPHA_HARD = 0, B200R_ALPHA_SUM = 1, B200R_ALPHA_PROD = 2 };
+enum { B200R_TEX_SURFACE = 0, B200R_TEX_VERTEX = 1 };
+
+#define B200R_MAX_FACES_PER_PIXEL 64 /* kMaxPointsPerPixel, cuda/soft_rasterize.py:16 */
+
+B200R_API const char* b200r_version(void);
+B200R_API const char* b200r_last_error(void);
+
+/* Bytes of device scratch the SoftRas forward needs for (batch, num_faces, image_size).
+ * The same buffer, untouched, must be handed to the backward (it holds the per-face
+ * records the reference keeps in `faces_info`, soft_rasterize.py:62,101). */
+B200R_API size_t b200r_softras_workspace_bytes(int batch_size, int num_faces, int image_size);
+
+/* SoftRas forward.
+ *   face_vertices  [B, nf, 3, 3]  NDC x,y (+y up) and camera-space z per vertex
+ *   textures       [B, nf, T, 3]  T = R*R texels (surface) or 3 (vertex)
+ *   soft_colors    [B, 4, H, W]   out, planar RGBA, row 0 = top (y = +1)
+ *   aggrs_info     [B, 2, H, W]   out: softmax -> (sum, max); hard rgb -> (depth_min, face_index_min)
+ *   faces_id_buffer[B, K, H, W]   out, int32, the <=K nearest-z face ids per pixel in the
+ *                                 reference's slot order, -1 padded
+ *   faces_info     [B, nf, 27]    out, optional (may be NULL): the reference's K1 output
+ *   dist_eps_logit = ln(1/dist_eps - 1) computed by the host as soft_rasterize.py:25
+ * Background colour is always 0, as in the reference (the op memsets soft_colors). */
+B200R_API int b200r_softras_forward(const float* face_vertices, const float* textures,
+                          float* soft_colors, float* aggrs_info, int32_t* faces_id_buffer,
+                          float* faces_info, void* workspace, size_t workspace_bytes,
+                          int batch_size, int num_faces, int texture_size, int image_size,
+                          int max_faces_per_pixel, float near, float far, float eps,
+                          float sigma_val, float gamma_val, float dist_eps_logit,
+                          int dist_func, int rgb_func, int alpha_func, int texture_type,
+                          int double_side, void* stream);
+
+/* SoftRas top-K backward.  grad_face_vertices [B,nf,3,3] and grad_textures [B,nf,T,3]
+ * are overwritten (zeroed inside, then accumulated). */
+B200R_API int b200r_softras_backward(const float* face_vertices, const float* textures,
+                           const float* soft_colors, const float* aggrs_info,
+                           const int32_t* faces_id_buffer, const void* workspace,
+                           size_t workspace_bytes, const float* grad_soft_colors,
+                           float* grad_face_vertices, float* grad_textures,
+                           int batch_size, int num_faces, int texture_size, int image_size,
+                           int max_faces_per_pixel, float near, float far, float eps,
+                           float sigma_val, float gamma_val, float dist_eps_logit,
+                           int dist_func, int rgb_func, int alpha_func, int texture_type,
+                           int double_side, void* stream);
+
+/* Launch counter: number of kernels this library has launched in this process
+ * (bench.py reports the delta over the timed region as "gpu_launches"). */
+B200R_API unsigned long long b200r_launch_count(void);
+
+/* Per-kernel device timing (CUDA events recorded on the launch stream around every kernel
+ * this library launches).  Off by default.  bench.py uses it for the roofline of the
+ * dominant kernel; b200r_profile_read synchronises the outstanding events. */
+enum { B200R_K_FACE_SETUP = 0, B200R_K_COARSE_BIN = 1, B200R_K_SOFTRAS_FWD = 2, B200R_K_SOFTRAS_BWD = 3 };
+B200R_API void b200r_profile_enable(int on);
+B200R_API void b200r_profile_reset(void);
+B200R_API int b200r_profile_read(int kernel, double* total_ms, long long* launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200RASTER_H */

@@ -1,0 +1,52 @@
+"""ctypes binding of libb200raster.so (C ABI declared in include/b200raster.h).
+
+The product path has no CPU fallback: if the library is missing or a call fails, an
+exception is raised.  The library is never built implicitly at import time on a GPU box --
+`__graft_entry__.build()` / `python -m jrender_b200.build` produce it in-tree.
+"""
+import ctypes as C
+import os
+
+from . import build as _build
+
+_lib = None
+
+
+class B200RasterError(RuntimeError):
+    pass
+
+
+_F = C.c_float
+_I = C.c_int
+_P = C.c_void_p
+
+_SOFTRAS_SCALARS = [_I, _I, _I, _I, _I, _F, _F, _F, _F, _F, _F, _I, _I, _I, _I, _I, _P]
+
+
+def lib():
+    """Load (once) and return the C ABI library; raises B200RasterError when it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB
+    if not os.path.exists(path):
+        raise B200RasterError(
+            "libb200raster.so not built (%s). Run `python -m jrender_b200.build` "
+            "(needs nvcc); there is no CPU fallback." % path)
+    L = C.CDLL(path)
+    L.b200r_version.restype = C.c_char_p
+    L.b200r_last_error.restype = C.c_char_p
+    L.b200r_launch_count.restype = C.c_ulonglong
+    L.b200r_softras_workspace_bytes.restype = C.c_size_t
+    L.b200r_softras_workspace_bytes.argtypes = [_I, _I, _I]
+    L.b200r_softras_forward.restype = _I
+    L.b200r_softras_forward.argtypes = [_P, _P, _P, _P, _P, _P, _P, C.c_size_t] + _SOFTRAS_SCALARS
+    L.b200r_softras_backward.restype = _I
+    L.b200r_softras_backward.argtypes = [_P, _P, _P, _P, _P, _P, C.c_size_t, _P, _P, _P] + _SOFTRAS_SCALARS
+    _lib = L
+    return L
+
+
+def check(rc, what):
+    if rc != 0:
+        raise B200RasterError("%s failed (rc=%d): %s" % (what, rc, lib().b200r_last_error().decode()))

@@ -1,0 +1,87 @@
+// common.cuh -- shared definitions of the B200 rasterizer kernels.
+//
+// Arithmetic contract: this translation unit set is compiled with -fmad=false
+// (no a*b+c contraction), IEEE division and sqrt (nvcc defaults -prec-div=true,
+// -prec-sqrt=true, -ftz=false).  Every +,-,*,/ below is therefore a separately
+// rounded fp32 operation evaluated in the same order as the reference kernel
+// source, which makes all discrete decisions of the rasterizer (border reject,
+// inside tests, distance threshold, near/far reject, top-K membership, nearest
+// face) bit-identical to oracle/softras_oracle.c.  Only expf() differs (<= 2 ulp).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define B200R_TILE 16          // fine tile edge in pixels (one CTA of 256 threads)
+#define B200R_TILE_THREADS 256
+#define B200R_MAX_COARSE_SIDE 16
+
+// Per-face record, 128 bytes, written once by the setup kernel and staged through
+// shared memory by the raster kernels.  Replaces the reference's faces_info
+// ([inv 9 | sym 9 | obt 3], cuda/soft_rasterize.py:190-192) plus the per-pixel
+// recomputation of the face bounding box (check_border, :28-34).
+struct __align__(16) FaceRec {
+    uint32_t rect_x;   // x0 | x1 << 16 : pixel columns passing check_border (inclusive)
+    uint32_t rect_r;   // r0 | r1 << 16 : output rows passing check_border (inclusive, row 0 = top)
+    uint32_t flags;    // bit k (k<3): face_obt[k] == 1 ; bit 3: check_face_frontside
+    uint32_t face_id;  // index within the batch element
+    float inv[9];      // face_inv  (:205-217)
+    float v[9];        // x0 y0 z0 x1 y1 z1 x2 y2 z2
+    float a0[9];       // a0[k][j] = sym[3k+j] - sym[3((k+1)%3)+j]   (:77-79, :128-130)
+    float pad;
+};
+static_assert(sizeof(FaceRec) == 128, "FaceRec must be 128 bytes");
+
+struct SoftRasParams {
+    int B, nf, T, R, is, K;
+    float near_, far_, eps, sigma, gamma, dist_eps;  // dist_eps = ln(1/dist_eps - 1)
+    int dist_func, rgb_func, alpha_func, tex_type, double_side;
+    int ntx;        // fine tiles per image side
+    int coarse_px;  // coarse bin edge in pixels (multiple of B200R_TILE)
+    int ncs;        // coarse bins per image side
+};
+
+// Workspace carve-up (all offsets 256-byte aligned).
+struct SoftRasWorkspace {
+    FaceRec* recs;       // [B*nf]
+    uint2* rects;        // [B*nf]  (rect_x, rect_r) copy for the binning scans
+    int* coarse_cnt;     // [B*ncs*ncs]
+    int* coarse_ids;     // [B*ncs*ncs][nf]
+    size_t bytes;
+};
+
+static inline size_t b200r_align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static inline void b200r_geometry(int image_size, int* ntx, int* coarse_px, int* ncs) {
+    const int nt = (image_size + B200R_TILE - 1) / B200R_TILE;
+    int ctiles = (nt + B200R_MAX_COARSE_SIDE - 1) / B200R_MAX_COARSE_SIDE;  // tiles per coarse bin edge
+    if (ctiles < 4) ctiles = 4;
+    *ntx = nt;
+    *coarse_px = ctiles * B200R_TILE;
+    *ncs = (image_size + *coarse_px - 1) / *coarse_px;
+}
+
+static inline SoftRasWorkspace b200r_carve(void* base, int B, int nf, int image_size) {
+    int ntx, cpx, ncs;
+    b200r_geometry(image_size, &ntx, &cpx, &ncs);
+    SoftRasWorkspace w;
+    size_t off = 0;
+    char* p = (char*)base;
+    w.recs = (FaceRec*)(p + off);
+    off += b200r_align256((size_t)B * nf * sizeof(FaceRec));
+    w.rects = (uint2*)(p + off);
+    off += b200r_align256((size_t)B * nf * sizeof(uint2));
+    w.coarse_cnt = (int*)(p + off);
+    off += b200r_align256((size_t)B * ncs * ncs * sizeof(int));
+    w.coarse_ids = (int*)(p + off);
+    off += b200r_align256((size_t)B * ncs * ncs * (size_t)nf * sizeof(int));
+    w.bytes = off;
+    return w;
+}
+
+#ifdef __CUDACC__
+// NDC coordinate of pixel index i (x: column; y: is-1-row), evaluated in double and
+// rounded to float exactly like `(2. * xi + 1. - is) / is` (cuda/soft_rasterize.py:282-283).
+__device__ __forceinline__ float b200r_pix_coord(int i, int is) {
+    return (float)((2.0 * (double)i + 1.0 - (double)is) / (double)is);
+}
+#endif

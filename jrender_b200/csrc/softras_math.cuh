@@ -1,0 +1,148 @@
+// softras_math.cuh -- per-(pixel, face) arithmetic of the SoftRas rasterizer.
+//
+// Semantics follow the reference device functions (jrender/renderer/dr/softras/cuda/
+// soft_rasterize.py:20-173 forward, :1118-1174 backward); the evaluation ORDER of every
+// fp32 expression is kept so that results are bit-identical to oracle/softras_oracle.c
+// (see common.cuh for the arithmetic contract).  Where the reference promotes to double
+// through a literal (`1. / (1. + exp(..))`, `alpha *= 1. - D`) the same promotion is
+// done here; where the promotion provably cannot change the fp32 result (clamps against
+// representable constants, `1./x` of a float: 53 >= 2*24+2 so double rounding is
+// innocuous) plain fp32 is used.
+#pragma once
+#include "common.cuh"
+
+namespace b200r {
+
+// :20-25
+__device__ __forceinline__ void barycentric_coordinate(float w[3], float x, float y, const float* inv) {
+    w[0] = inv[0] * x + inv[1] * y + inv[2];
+    w[1] = inv[3] * x + inv[4] * y + inv[5];
+    w[2] = inv[6] * x + inv[7] * y + inv[8];
+}
+
+// :43-46
+__device__ __forceinline__ bool check_pixel_inside(const float w[3]) {
+    return w[0] <= 1.f && w[0] >= 0.f && w[1] <= 1.f && w[1] >= 0.f && w[2] <= 1.f && w[2] >= 0.f;
+}
+
+// :49-54  (max(min(w,1.),0.) and max(sum,1e-5) are exact in fp32, see header comment)
+__device__ __forceinline__ void barycentric_clip(float w[3]) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) w[k] = fmaxf(fminf(w[k], 1.f), 0.f);
+    const float w_sum = fmaxf(w[0] + w[1] + w[2], 1e-5f);
+#pragma unroll
+    for (int k = 0; k < 3; k++) w[k] = w[k] / w_sum;
+}
+
+__device__ __forceinline__ float sel3(int i, float a, float b, float c) { return i == 0 ? a : (i == 1 ? b : c); }
+
+// :57-147.  rec->a0 holds the pre-subtracted Gram-matrix rows.  Returns sign; writes
+// dis_x, dis_y and (for the backward) t[3].
+__device__ __forceinline__ float euclidean_p2f_distance(float& dis_x, float& dis_y, float t[3],
+                                                        const float w[3], const FaceRec* rec,
+                                                        float xp, float yp) {
+    const float* f = rec->v;
+    if (w[0] > 0.f && w[1] > 0.f && w[2] > 0.f && w[0] < 1.f && w[1] < 1.f && w[2] < 1.f) {
+        float dis_min = 100000000.f;
+        float dis_x_min = 0.f, dis_y_min = 0.f;
+        t[0] = t[1] = t[2] = 0.f;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const int v0 = k, v1 = (k + 1) % 3, v2 = (k + 2) % 3;
+            const float* a = rec->a0 + 3 * k;
+            float t0[3];
+            t0[v0] = (w[0] * a[0] + w[1] * a[1] + w[2] * a[2] - a[v1]) / (a[v0] - a[v1]);
+            t0[v1] = 1.f - t0[v0];
+            t0[v2] = 0.f;
+            t0[0] -= w[0];
+            t0[1] -= w[1];
+            t0[2] -= w[2];
+            const float dx = t0[0] * f[0] + t0[1] * f[3] + t0[2] * f[6];
+            const float dy = t0[0] * f[1] + t0[1] * f[4] + t0[2] * f[7];
+            const float dis = dx * dx + dy * dy;
+            if (dis < dis_min) {
+                dis_min = dis;
+                dis_x_min = dx;
+                dis_y_min = dy;
+                t[0] = t0[0];
+                t[1] = t0[1];
+                t[2] = t0[2];
+            }
+        }
+        dis_x = dis_x_min;
+        dis_y = dis_y_min;
+        return 1.f;
+    } else {
+        const uint32_t obt = rec->flags;
+        int v0 = 0;  // the reference leaves v0 = -1 (UB) when no branch fires; oracle uses 0 too
+        if (w[1] <= 0.f && w[2] <= 0.f) {
+            v0 = 0;
+            if ((obt & 1u) && (xp - f[0]) * (f[6] - f[0]) + (yp - f[1]) * (f[7] - f[1]) > 0.f) v0 = 2;
+        } else if (w[2] <= 0.f && w[0] <= 0.f) {
+            v0 = 1;
+            if ((obt & 2u) && (xp - f[3]) * (f[0] - f[3]) + (yp - f[4]) * (f[1] - f[4]) > 0.f) v0 = 0;
+        } else if (w[0] <= 0.f && w[1] <= 0.f) {
+            v0 = 2;
+            if ((obt & 4u) && (xp - f[6]) * (f[3] - f[6]) + (yp - f[7]) * (f[4] - f[7]) > 0.f) v0 = 1;
+        } else if (w[0] <= 0.f) v0 = 1;
+        else if (w[1] <= 0.f) v0 = 2;
+        else if (w[2] <= 0.f) v0 = 0;
+
+        const int v1 = v0 == 2 ? 0 : v0 + 1;
+        const float* a = rec->a0 + 3 * v0;
+        const float a_0 = a[0], a_1 = a[1], a_2 = a[2];
+        const float a_v0 = sel3(v0, a_0, a_1, a_2);
+        const float a_v1 = sel3(v1, a_0, a_1, a_2);
+        const float tv0 = (w[0] * a_0 + w[1] * a_1 + w[2] * a_2 - a_v1) / (a_v0 - a_v1);
+        const float tv1 = 1.f - tv0;
+        const float c0 = fminf(fmaxf(tv0, 0.f), 1.f);
+        const float c1 = fminf(fmaxf(tv1, 0.f), 1.f);
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const float tk = (k == v0) ? c0 : ((k == v1) ? c1 : 0.f);
+            t[k] = tk - w[k];
+        }
+        dis_x = t[0] * f[0] + t[1] * f[3] + t[2] * f[6];
+        dis_y = t[0] * f[1] + t[1] * f[4] + t[2] * f[7];
+        return -1.f;
+    }
+}
+
+// :150-154
+__device__ __forceinline__ float barycentric_p2f_distance(const float w[3]) {
+    float dis = w[0] > w[1] ? (w[1] > w[2] ? w[2] : w[1]) : (w[0] > w[2] ? w[2] : w[0]);
+    dis = dis > 0.f ? dis * dis : -dis * dis;
+    return dis;
+}
+
+// `1. / (1. + exp(x))` with x already = -sign*dis/sigma  (:338, :344)
+__device__ __forceinline__ float sigmoid_from_negarg(float x) {
+    return (float)(1.0 / (1.0 + (double)expf(x)));
+}
+
+// surface texel index of forward_sample_texture / backward_sample_texture (:159-166, :1157-1168)
+__device__ __forceinline__ int surface_texel(const float w[3], int R) {
+    const int w_x = (int)fminf(w[0] * R, (float)(R - 1));
+    const int w_y = (int)fminf(w[1] * R, (float)(R - 1));
+    if ((w[0] + w[1]) * R - w_x - w_y <= 1.f) return w_y * R + w_x;
+    return (R - 1 - w_y) * R + (R - 1 - w_x);
+}
+
+// :156-173 forward flavour (vertex mode perspective-correct); tex points at this face's texels
+__device__ __forceinline__ void sample_texture_fwd(float col[3], const float* __restrict__ tex,
+                                                   const float w[3], int R, int tex_type,
+                                                   const float* f, float z) {
+    if (tex_type == 0) {
+        const int j = surface_texel(w, R);
+#pragma unroll
+        for (int k = 0; k < 3; k++) col[k] = __ldg(tex + j * 3 + k);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            float c = w[0] * __ldg(tex + k) / f[2] + w[1] * __ldg(tex + 3 + k) / f[5] + w[2] * __ldg(tex + 6 + k) / f[8];
+            col[k] = c * z;
+        }
+    }
+}
+
+}  // namespace b200r

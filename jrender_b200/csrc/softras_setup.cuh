@@ -1,0 +1,185 @@
+// softras_setup.cuh -- per-face setup (K1 replacement) and deterministic coarse binning.
+#pragma once
+#include "common.cuh"
+
+namespace b200r {
+
+// First index i in [0, is] whose coordinate does NOT satisfy (coord < lim); i.e. the first
+// pixel that survives the `x < min - threshold` half of check_border (:31,:33).
+__device__ __forceinline__ int first_not_below(float lim, int is) {
+    if (isnan(lim)) return 0;  // comparisons with NaN are false -> nothing is rejected
+    const double e = ceil(((double)lim * (double)is + (double)is - 1.0) * 0.5);
+    int i = e < 0.0 ? 0 : (e > (double)is ? is : (int)e);
+    while (i > 0 && !(b200r_pix_coord(i - 1, is) < lim)) --i;
+    while (i < is && (b200r_pix_coord(i, is) < lim)) ++i;
+    return i;
+}
+
+// Last index i in [-1, is-1] whose coordinate does NOT satisfy (coord > lim) (:30,:32).
+__device__ __forceinline__ int last_not_above(float lim, int is) {
+    if (isnan(lim)) return is - 1;
+    const double e = floor(((double)lim * (double)is + (double)is - 1.0) * 0.5);
+    int i = e < -1.0 ? -1 : (e > (double)(is - 1) ? is - 1 : (int)e);
+    while (i < is - 1 && !(b200r_pix_coord(i + 1, is) > lim)) ++i;
+    while (i >= 0 && (b200r_pix_coord(i, is) > lim)) --i;
+    return i;
+}
+
+// One thread per (batch, face).  Computes the 128-byte record, the exact pixel rectangle
+// equivalent to check_border, and (optionally) the reference's faces_info[27].
+// Reference: forward_soft_rasterize_inv_cuda_kernel, cuda/soft_rasterize.py:176-236.
+__global__ void __launch_bounds__(256) k_face_setup(const float* __restrict__ faces, FaceRec* __restrict__ recs,
+                                                    uint2* __restrict__ rects, float* __restrict__ faces_info,
+                                                    int total_faces, int nf, int is, float border) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total_faces) return;
+    const float* face = faces + (size_t)i * 9;
+    float f[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) f[k] = __ldg(face + k);
+
+    const float p00 = f[0], p01 = f[1], p10 = f[3], p11 = f[4], p20 = f[6], p21 = f[7];
+    float star[9] = {p11 - p21, p20 - p10, p10 * p21 - p20 * p11,
+                     p21 - p01, p00 - p20, p20 * p01 - p00 * p21,
+                     p01 - p11, p10 - p00, p00 * p11 - p10 * p01};
+    float det = p20 * (p01 - p11) + p00 * (p11 - p21) + p10 * (p21 - p01);
+    det = det > 0.f ? fmaxf(det, 1e-10f) : fminf(det, -1e-10f);
+
+    FaceRec r;
+#pragma unroll
+    for (int k = 0; k < 9; k++) r.inv[k] = star[k] / det;
+#pragma unroll
+    for (int k = 0; k < 9; k++) r.v[k] = f[k];
+    float sym[9];
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+#pragma unroll
+        for (int k = 0; k < 3; k++) sym[j * 3 + k] = f[j * 3 + 0] * f[k * 3 + 0] + f[j * 3 + 1] * f[k * 3 + 1] + 1.f;
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) r.a0[3 * k + j] = sym[3 * k + j] - sym[3 * ((k + 1) % 3) + j];
+
+    uint32_t flags = 0;
+    {
+        const float px[3] = {p00, p10, p20}, py[3] = {p01, p11, p21};
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const int k1 = (k + 1) % 3, k2 = (k + 2) % 3;
+            if (flags == 0 && (px[k1] - px[k]) * (px[k2] - px[k]) + (py[k1] - py[k]) * (py[k2] - py[k]) < 0.f)
+                flags = 1u << k;
+        }
+    }
+    // check_face_frontside (:37-40)
+    if ((f[7] - f[1]) * (f[3] - f[0]) < (f[4] - f[1]) * (f[6] - f[0])) flags |= 8u;
+    r.flags = flags;
+    r.face_id = (uint32_t)(i % nf);
+    r.pad = 0.f;
+
+    // check_border (:28-34) as an exact pixel rectangle
+    const float xhi = fmaxf(fmaxf(f[0], f[3]), f[6]) + border;
+    const float xlo = fminf(fminf(f[0], f[3]), f[6]) - border;
+    const float yhi = fmaxf(fmaxf(f[1], f[4]), f[7]) + border;
+    const float ylo = fminf(fminf(f[1], f[4]), f[7]) - border;
+    int x0 = first_not_below(xlo, is), x1 = last_not_above(xhi, is);
+    const int y0 = first_not_below(ylo, is), y1 = last_not_above(yhi, is);
+    int r0 = is - 1 - y1, r1 = is - 1 - y0;  // row = is-1-yi (:280)
+    if (x0 > x1 || r0 > r1) { x0 = 1; x1 = 0; r0 = 1; r1 = 0; }
+    r.rect_x = (uint32_t)x0 | ((uint32_t)x1 << 16);
+    r.rect_r = (uint32_t)r0 | ((uint32_t)r1 << 16);
+
+    // 128-byte record as 8 x 16-byte stores
+    const uint4* src = reinterpret_cast<const uint4*>(&r);
+    uint4* dst = reinterpret_cast<uint4*>(recs + i);
+#pragma unroll
+    for (int k = 0; k < 8; k++) dst[k] = src[k];
+    rects[i] = make_uint2(r.rect_x, r.rect_r);
+
+    if (faces_info != nullptr) {
+        float* fi = faces_info + (size_t)i * 27;
+#pragma unroll
+        for (int k = 0; k < 9; k++) fi[k] = r.inv[k];
+#pragma unroll
+        for (int k = 0; k < 9; k++) fi[9 + k] = sym[k];
+#pragma unroll
+        for (int k = 0; k < 3; k++) fi[18 + k] = (flags >> k) & 1u ? 1.f : 0.f;
+#pragma unroll
+        for (int k = 21; k < 27; k++) fi[k] = 0.f;
+    }
+}
+
+__device__ __forceinline__ bool rect_overlaps(uint2 rc, int x0, int x1, int r0, int r1) {
+    const int fx0 = (int)(rc.x & 0xffffu), fx1 = (int)(rc.x >> 16);
+    const int fr0 = (int)(rc.y & 0xffffu), fr1 = (int)(rc.y >> 16);
+    return fx0 <= x1 && fx1 >= x0 && fr0 <= r1 && fr1 >= r0 && fx0 <= fx1;
+}
+
+// Block-wide ORDERED compaction step: thread `tid` contributes `cnt` items; returns the
+// exclusive prefix over the block (in thread order) and the block total.  256 threads.
+__device__ __forceinline__ int block_excl_scan_256(int cnt, int* s_warp /*[8]*/, int& total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int n = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += n;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    int base = 0, tot = 0;
+#pragma unroll
+    for (int wi = 0; wi < 8; wi++) {
+        const int v = s_warp[wi];
+        if (wi < warp) base += v;
+        tot += v;
+    }
+    __syncthreads();
+    total = tot;
+    return base + incl - cnt;
+}
+
+// Coarse binning, tile-centric and deterministic: CTA (bin, b) scans the face rectangles of
+// batch element b in ascending face id and appends the overlapping ids, in order, to its
+// list.  Replaces TriangleBoundingBoxKernel + RasterizeCoarseCudaKernel
+// (cuda/soft_rasterize_coarse_to_fine.py:96-280) whose per-bin order is race-dependent and
+// whose fixed-capacity bins silently overflow; here capacity is nf per bin and the test is
+// the exact check_border rectangle.
+#define B200R_COARSE_PER_THREAD 4
+__global__ void __launch_bounds__(256) k_coarse_bin(const uint2* __restrict__ rects, int* __restrict__ coarse_cnt,
+                                                    int* __restrict__ coarse_ids, int nf, int is,
+                                                    int coarse_px, int ncs) {
+    __shared__ int s_warp[8];
+    const int bin = blockIdx.x, b = blockIdx.y;
+    const int bx = bin % ncs, by = bin / ncs;
+    const int x0 = bx * coarse_px, x1 = min(is, x0 + coarse_px) - 1;
+    const int r0 = by * coarse_px, r1 = min(is, r0 + coarse_px) - 1;
+    const uint2* rc = rects + (size_t)b * nf;
+    int* out = coarse_ids + ((size_t)b * ncs * ncs + bin) * nf;
+    int n_out = 0;
+    const bool vec_ok = (reinterpret_cast<uintptr_t>(rc) & 15) == 0;  // (b*nf) even
+    for (int base = 0; base < nf; base += 256 * B200R_COARSE_PER_THREAD) {
+        const int first = base + threadIdx.x * B200R_COARSE_PER_THREAD;
+        uint32_t mask = 0;
+        if (vec_ok && first + B200R_COARSE_PER_THREAD <= nf) {
+            const uint4 a = __ldg(reinterpret_cast<const uint4*>(rc + first));
+            const uint4 c = __ldg(reinterpret_cast<const uint4*>(rc + first + 2));
+            mask |= rect_overlaps(make_uint2(a.x, a.y), x0, x1, r0, r1) ? 1u : 0u;
+            mask |= rect_overlaps(make_uint2(a.z, a.w), x0, x1, r0, r1) ? 2u : 0u;
+            mask |= rect_overlaps(make_uint2(c.x, c.y), x0, x1, r0, r1) ? 4u : 0u;
+            mask |= rect_overlaps(make_uint2(c.z, c.w), x0, x1, r0, r1) ? 8u : 0u;
+        } else {
+#pragma unroll
+            for (int u = 0; u < B200R_COARSE_PER_THREAD; u++)
+                if (first + u < nf && rect_overlaps(__ldg(rc + first + u), x0, x1, r0, r1)) mask |= 1u << u;
+        }
+        int total;
+        int off = n_out + block_excl_scan_256(__popc(mask), s_warp, total);
+#pragma unroll
+        for (int u = 0; u < B200R_COARSE_PER_THREAD; u++)
+            if (mask & (1u << u)) out[off++] = first + u;
+        n_out += total;
+    }
+    if (threadIdx.x == 0) coarse_cnt[b * ncs * ncs + bin] = n_out;
+}
+
+}  // namespace b200r

@@ -1,0 +1,51 @@
+"""Shared helpers of the parity tests: run the CUDA path / the oracle on the same inputs."""
+import numpy as np
+
+from oracle import softras as osr
+
+
+def run_oracle(fv, tex, params, grad=None, rows=None):
+    out = osr.forward(fv, tex, params, rows=rows)
+    if grad is not None:
+        out["grad_faces"], out["grad_textures"] = osr.backward(fv, tex, out, grad, params, accumulate_double=True, rows=rows)
+    return out
+
+
+def run_cuda(fv, tex, params, grad=None, device="cuda:0", want_faces_info=True):
+    """Through the public torch API -> ctypes -> C ABI -> sm_100a kernels."""
+    import torch
+    from jrender_b200 import SoftRasterizeFunction
+    dev = torch.device(device)
+    fvt = torch.from_numpy(np.ascontiguousarray(fv)).to(dev).requires_grad_(grad is not None)
+    txt = torch.from_numpy(np.ascontiguousarray(tex)).to(dev).requires_grad_(grad is not None)
+    fn = SoftRasterizeFunction(
+        image_size=params["image_size"], near=params["near"], far=params["far"], fill_back=params["fill_back"],
+        eps=params["eps"], sigma_val=params["sigma_val"], dist_func=params["dist_func"], dist_eps=params["dist_eps"],
+        gamma_val=params["gamma_val"], aggr_func_rgb=params["aggr_func_rgb"], aggr_func_alpha=params["aggr_func_alpha"],
+        texture_type=params["texture_type"], max_faces_per_pixel_for_grad=params["max_faces_per_pixel_for_grad"])
+    fn.return_faces_info = want_faces_info
+    soft_colors, aggrs_info, ids = fn.raw(fvt, txt)
+    out = dict(soft_colors=soft_colors.detach().cpu().numpy(), aggrs_info=aggrs_info.cpu().numpy(),
+               faces_id_buffer=ids.cpu().numpy())
+    if want_faces_info:
+        out["faces_info"] = fn.save_vars[3].cpu().numpy()
+    if grad is not None:
+        soft_colors.backward(torch.from_numpy(np.ascontiguousarray(grad)).to(dev))
+        out["grad_faces"] = fvt.grad.cpu().numpy()
+        out["grad_textures"] = txt.grad.cpu().numpy()
+    torch.cuda.synchronize()
+    return out
+
+
+def sorted_ids(ids):
+    """[B,K,H,W] -> per-pixel ascending id sets with -1 (empty) moved last."""
+    a = ids.astype(np.int64).copy()
+    a[a < 0] = np.iinfo(np.int32).max
+    a.sort(axis=1)
+    return a
+
+
+def rel_err(a, b):
+    """max |a-b| / max(|b|, tiny): scale-relative error of a whole tensor."""
+    denom = max(float(np.abs(b).max()), 1e-30)
+    return float(np.abs(a.astype(np.float64) - b.astype(np.float64)).max()) / denom
