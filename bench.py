@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""bench.py -- SoftRas forward+backward throughput on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload c3|c2|tiny]
+    (N>1: python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...)
+
+Workload (default "c3", BASELINE.json configs[2] / the README's 39k-face row): UV sphere with
+39 200 faces at 1024x1024, T=1 surface textures, renderer defaults (sigma 1e-5, gamma 1e-4,
+euclidean / softmax / prod, K=16), 4 images per GPU -- B=32 at 8 GPUs, weak scaling.  One
+"step" = one forward + one top-K backward over the rank's 4 images.
+
+Prints ONE JSON line (rank 0).  `value` = frames/s over all ranks with inputs resident in
+HBM; `e2e` = same through the public API with pinned HOST inputs, H2D/D2H inside the timed
+region; `roofline` = the dominant kernel against the measured HBM peak; `cpu_baseline` =
+the CPU oracle (restatement of the reference kernels; the reference has no CPU path,
+SURVEY.md F1) on this box's host cores on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "softras_fwd_bwd_frames_per_s_1024px_39k_faces"
+WORKLOADS = {
+    # name: (num_faces, image_size, images_per_gpu, description)
+    "c3": (39200, 1024, 4, "C3: SoftRas fwd+bwd 1024x1024, UV sphere 39200 faces, 4 images/GPU (B=32 at 8 GPUs)"),
+    "c2": (3280, 1024, 8, "C2: SoftRas fwd+bwd 1024x1024, UV sphere 3280 faces, 8 images/GPU"),
+    "tiny": (280, 256, 2, "tiny: SoftRas fwd+bwd 256x256, UV sphere 280 faces, 2 images/GPU (smoke only)"),
+}
+README_39K_MS = 35.5  # Jrender SoftRas 39k faces, 1024^2, hardware/batch unstated
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU-baseline sample time")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def build_inputs(workload, rank, world):
+    from jrender_b200 import workloads as wl
+    nf, H, bpg, _ = WORKLOADS[workload]
+    total = bpg * world
+    # global batch index -> azimuth 360*b/B; this rank owns [rank*bpg, (rank+1)*bpg)
+    fv_all, tex_all = wl.make_scene(nf, batch=total)
+    sl = slice(rank * bpg, (rank + 1) * bpg)
+    rng = np.random.default_rng(2 + rank)
+    grad = rng.uniform(-1.0, 1.0, (bpg, 4, H, H)).astype(np.float32)
+    return np.ascontiguousarray(fv_all[sl]), np.ascontiguousarray(tex_all[sl]), grad
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi sampler running DURING the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()  # exact PID we started
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------- CPU oracle timing
+def time_oracle(workload, target_s, nthreads=0, want_steps=1):
+    """Times the CPU oracle (oracle/softras_oracle.c) on evenly spaced rows of ONE image of the
+    workload and extrapolates to frames/s.  Returns (frames_per_s, info dict, per-step times)."""
+    from oracle import softras as osr
+    from jrender_b200 import workloads as wl
+    nf, H, _, _ = WORKLOADS[workload]
+    fv, tex = wl.make_scene(nf, batch=1)
+    P = osr.Params(image_size=H)
+    g = np.random.default_rng(2).uniform(-1.0, 1.0, (1, 4, H, H)).astype(np.float32)
+    cores = osr.max_threads() if nthreads <= 0 else nthreads
+    # calibrate on 4 rows
+    stride0 = max(1, H // 4)
+    t0 = time.perf_counter()
+    out = osr.forward(fv, tex, P, row_stride=stride0, nthreads=nthreads)
+    osr.backward(fv, tex, out, g, P, row_stride=stride0)
+    per_row = (time.perf_counter() - t0) / max(1, len(range(0, H, stride0)))
+    rows = int(min(H, max(2, target_s / max(per_row, 1e-9))))
+    stride = max(1, H // rows)
+    n_rows = len(range(0, H, stride))
+    times = []
+    for _ in range(want_steps):
+        t0 = time.perf_counter()
+        out = osr.forward(fv, tex, P, row_stride=stride, nthreads=nthreads)
+        t1 = time.perf_counter()
+        osr.backward(fv, tex, out, g, P, row_stride=stride)
+        t2 = time.perf_counter()
+        times.append((t1 - t0, t2 - t1))
+    return n_rows, H, cores, times
+
+
+def cpu_frames_per_s(n_rows, H, times):
+    t = float(np.mean([a + b for a, b in times]))
+    full_image_s = t * H / n_rows
+    return 1.0 / full_image_s
+
+
+# --------------------------------------------------------------------------- reference arm
+def run_reference(args, rank, world):
+    """The reference has no CPU implementation (every op is CUDA-only) and Jittor is
+    not installable here, so this arm times the CPU restatement of the reference kernels
+    (oracle/, kind "port") with all host threads on rank 0."""
+    if rank != 0:
+        return
+    total_steps = args.steps + args.warmup
+    target = max(0.5, min(15.0, 150.0 / max(1, total_steps)))
+    n_rows, H, cores, times = time_oracle(args.workload, target, want_steps=total_steps)
+    timed = times[args.warmup:] if len(times) > args.warmup else times
+    v = cpu_frames_per_s(n_rows, H, timed)
+    nf, _, bpg, desc = WORKLOADS[args.workload]
+    sample = "fwd+bwd of %d evenly spaced rows of one %dx%d image (%d faces), extrapolated x%.1f to a full image; fwd OpenMP %d threads, bwd 1 thread" % (
+        n_rows, H, H, nf, H / n_rows, cores)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1000.0 * bpg * args.gpus / v, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": v / (1000.0 / README_39K_MS) if args.workload == "c3" else None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc, "note": "CPU restatement of the reference CUDA kernels; the reference ships no CPU path"},
+        "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- our arm
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from jrender_b200 import SoftRasterizeFunction, _lib
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    L = _lib.lib()
+    nf, H, bpg, desc = WORKLOADS[args.workload]
+    fv_h, tex_h, grad_h = build_inputs(args.workload, rank, world)
+    fv = torch.from_numpy(fv_h).to(dev).requires_grad_(True)
+    tex = torch.from_numpy(tex_h).to(dev).requires_grad_(True)
+    grad = torch.from_numpy(grad_h).to(dev)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
+
+    def step():
+        fv.grad = None
+        tex.grad = None
+        img = SoftRasterizeFunction(image_size=H)(fv, tex)
+        img.backward(grad)
+        return img
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    warmup = max(3, args.warmup)
+    for _ in range(warmup):
+        step()
+    barrier()
+
+    sampler = ClockSampler(local_rank if "CUDA_VISIBLE_DEVICES" not in os.environ else
+                           os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local_rank])
+    if rank == 0:
+        sampler.start()
+    launches0 = L.b200r_launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for a, b in ev:
+        flush.fill_(1.0)          # L2 flush between timed iterations (outside the event pair)
+        a.record()
+        step()
+        b.record()
+    barrier()
+    launches = L.b200r_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    t_rank = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_rank, op=dist.ReduceOp.MAX)
+    total_ms = float(t_rank.item())
+    frames = bpg * world * args.steps
+    value = frames / (total_ms / 1000.0)
+
+    # ---- per-kernel device times (library event profiler, separate un-timed steps)
+    import ctypes as C
+    L.b200r_profile_reset()
+    L.b200r_profile_enable(1)
+    nprof = 5
+    for _ in range(nprof):
+        flush.fill_(1.0)
+        step()
+    torch.cuda.synchronize(dev)
+    L.b200r_profile_enable(0)
+    kern = {}
+    for kid, name in [(0, "k_face_setup"), (1, "k_coarse_bin"), (2, "k_softras_forward"), (3, "k_softras_backward")]:
+        ms, n = C.c_double(0), C.c_longlong(0)
+        L.b200r_profile_read(kid, C.byref(ms), C.byref(n))
+        kern[name] = {"avg_ms": ms.value / max(1, n.value), "launches_per_step": n.value / nprof}
+
+    # ---- end-to-end through the public API with pinned host buffers
+    fv_p = torch.from_numpy(fv_h).pin_memory()
+    tex_p = torch.from_numpy(tex_h).pin_memory()
+    gf_p = torch.empty_like(fv_p).pin_memory()
+    gt_p = torch.empty_like(tex_p).pin_memory()
+    target = torch.zeros((bpg, 4, H, H), dtype=torch.float32, device=dev)
+
+    def e2e_step():
+        a = fv_p.to(dev, non_blocking=True).requires_grad_(True)
+        t = tex_p.to(dev, non_blocking=True).requires_grad_(True)
+        img = SoftRasterizeFunction(image_size=H)(a, t)
+        loss = ((img - target) ** 2).mean()      # loss gradient is produced on the device
+        loss.backward()
+        gf_p.copy_(a.grad, non_blocking=True)
+        gt_p.copy_(t.grad, non_blocking=True)
+        return float(loss.item())                # D2H read of the step's result; also syncs
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    e2e_steps = max(3, min(args.steps, 10))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    t_e2e = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e_value = bpg * world * e2e_steps / (float(t_e2e.item()) / 1000.0)
+    h2d = fv_h.nbytes + tex_h.nbytes
+    d2h = fv_h.nbytes + tex_h.nbytes + 4
+
+    # ---- optional all-gather of the output images, reported separately
+    gather_ms = None
+    if world > 1:
+        img = step().detach()
+        out = torch.empty((bpg * world,) + tuple(img.shape[1:]), dtype=img.dtype, device=dev)
+        for _ in range(2):
+            dist.all_gather_into_tensor(out, img)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(5):
+            dist.all_gather_into_tensor(out, img)
+        g1.record()
+        barrier()
+        tg = torch.tensor([g0.elapsed_time(g1) / 5], dtype=torch.float64, device=dev)
+        dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+        gather_ms = float(tg.item())
+
+    if rank != 0:
+        return
+    # ---- roofline of the dominant kernel.  Algorithmic bytes per launch:
+    #   forward : B*[ (36+12T)*nf (read fv+tex) + 16*P (write RGBA) ]
+    #   backward: B*[ 32*P (read grad + RGBA) + 2*(36+12T)*nf (re-read inputs, write grads) ]
+    T, P = 1, H * H
+    alg = {"k_softras_forward": bpg * ((36 + 12 * T) * nf + 16 * P),
+           "k_softras_backward": bpg * (32 * P + 2 * (36 + 12 * T) * nf)}
+    dom = max(alg, key=lambda k: kern[k]["avg_ms"])
+    peak, peak_src = peaks()
+    achieved = alg[dom] / (kern[dom]["avg_ms"] / 1000.0) / 1e9
+    step_alg = bpg * (48 * P + 3 * (36 + 12 * T) * nf)
+    line = {
+        "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+        "warmup": warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": value / (1000.0 / README_39K_MS) if args.workload == "c3" else None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc, "images_per_gpu": bpg, "global_batch": bpg * world, "faces": nf, "image_size": H,
+                   "params": "T=1 sigma=1e-5 gamma=1e-4 euclidean/softmax/prod K=16 near=1 far=100 fill_back",
+                   "parallelism": "batch-sharded dp%d, no data-path collective" % world,
+                   "l2": "256 MiB buffer written between timed steps (outside the event pairs)",
+                   "baseline_note": "vs_baseline = value / (1000/35.5 ms): README.md:69, GPU and batch unstated"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "what": "pinned host face_vertices+textures -> H2D -> forward -> on-device MSE loss -> backward -> D2H grads + loss scalar"},
+        "gpu_launches": int(launches),
+        "kernels": kern,
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": int(alg[dom]),
+                     "note": "SIMT fp32 rasterization is issue-bound, not HBM-bound (SURVEY.md F9); see profiles/"},
+        "roofline_step": {"algorithmic_bytes_per_step": int(step_alg),
+                          "achieved_gbs": step_alg / (total_ms / args.steps / 1000.0) / 1e9,
+                          "frac": step_alg / (total_ms / args.steps / 1000.0) / 1e9 / peak},
+    }
+    if gather_ms is not None:
+        line["allgather_images_ms"] = gather_ms
+    if world == 1 and not args.no_cpu_baseline:
+        n_rows, HH, cores, times = time_oracle(args.workload, args.cpu_seconds, want_steps=1)
+        v = cpu_frames_per_s(n_rows, HH, times)
+        line["cpu_baseline"] = {
+            "value": v, "unit": "frames/s", "cores": cores, "kind": "port",
+            "sample": "oracle fwd+bwd on %d evenly spaced rows of one %dx%d image (%d faces), x%.1f extrapolated; fwd OpenMP %d threads, bwd 1 thread"
+                      % (n_rows, HH, HH, nf, HH / n_rows, cores)}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -110,6 +110,11 @@ B200R_API void b200r_profile_enable(int on);
 B200R_API void b200r_profile_reset(void);
 B200R_API int b200r_profile_read(int kernel, double* total_ms, long long* launches);
 
+/* Test hook: checks the exact-arithmetic helpers (csrc/exact_math.cuh) against the plain
+ * IEEE expressions they replace on n (a[i], b[i]) pairs; mismatch7[0..5] count bit
+ * differences (must all be 0), mismatch7[6] counts pairs that took the reciprocal fast path. */
+B200R_API int b200r_debug_exact_math(const float* a, const float* b, int n, int* mismatch7, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -43,6 +43,14 @@ def lib():
     L.b200r_softras_forward.argtypes = [_P, _P, _P, _P, _P, _P, _P, C.c_size_t] + _SOFTRAS_SCALARS
     L.b200r_softras_backward.restype = _I
     L.b200r_softras_backward.argtypes = [_P, _P, _P, _P, _P, _P, C.c_size_t, _P, _P, _P] + _SOFTRAS_SCALARS
+    L.b200r_profile_enable.restype = None
+    L.b200r_profile_enable.argtypes = [_I]
+    L.b200r_profile_reset.restype = None
+    L.b200r_profile_reset.argtypes = []
+    L.b200r_profile_read.restype = _I
+    L.b200r_profile_read.argtypes = [_I, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
+    L.b200r_debug_exact_math.restype = _I
+    L.b200r_debug_exact_math.argtypes = [_P, _P, _I, _P, _P]
     _lib = L
     return L
 

@@ -15,21 +15,27 @@
 #define B200R_TILE_THREADS 256
 #define B200R_MAX_COARSE_SIDE 16
 
-// Per-face record, 128 bytes, written once by the setup kernel and staged through
+// Per-face record, 160 bytes, written once by the setup kernel and staged through
 // shared memory by the raster kernels.  Replaces the reference's faces_info
 // ([inv 9 | sym 9 | obt 3], cuda/soft_rasterize.py:190-192) plus the per-pixel
-// recomputation of the face bounding box (check_border, :28-34).
+// recomputation of the face bounding box (check_border, :28-34), and carries the
+// pre-computed refined reciprocals that make every per-face division MUFU-free
+// (exact_math.cuh) and, for T == 1 surface textures, the face colour.
 struct __align__(16) FaceRec {
     uint32_t rect_x;   // x0 | x1 << 16 : pixel columns passing check_border (inclusive)
     uint32_t rect_r;   // r0 | r1 << 16 : output rows passing check_border (inclusive, row 0 = top)
-    uint32_t flags;    // bit k (k<3): face_obt[k] == 1 ; bit 3: check_face_frontside
+    uint32_t flags;    // bit k (k<3): face_obt[k]; bit 3: check_face_frontside;
+                       // bit 4+k: midrange(z_k); bit 7+k: midrange(den_k)
     uint32_t face_id;  // index within the batch element
     float inv[9];      // face_inv  (:205-217)
     float v[9];        // x0 y0 z0 x1 y1 z1 x2 y2 z2
     float a0[9];       // a0[k][j] = sym[3k+j] - sym[3((k+1)%3)+j]   (:77-79, :128-130)
-    float pad;
+    float rz[3];       // rcp_refined(z_k)
+    float rden[3];     // rcp_refined(den_k), den_k = a0[k][k] - a0[k][(k+1)%3]  (:81, :132)
+    float col[3];      // textures[face][0][0..2] when T == 1 (surface), else 0
 };
-static_assert(sizeof(FaceRec) == 128, "FaceRec must be 128 bytes");
+static_assert(sizeof(FaceRec) == 160, "FaceRec must be 160 bytes");
+#define B200R_REC_UINT4 10  // 160 / 16
 
 struct SoftRasParams {
     int B, nf, T, R, is, K;

@@ -60,7 +60,7 @@ template <int DIST, int RGB>
 cudaError_t launch_backward(const SoftRasParams& P, const SoftRasWorkspace& W, const float* textures,
                             const float* soft_colors, const float* aggrs_info, const int32_t* ids,
                             const float* grad_soft_colors, float* grad_faces, float* grad_textures, cudaStream_t st) {
-    const size_t smem = (size_t)P.K * B200R_TILE_THREADS * 4 + 8 * 32 * 4;
+    const size_t smem = (size_t)P.K * B200R_TILE_THREADS * 4 + 8 * sizeof(FaceRec);
     cudaError_t e = cudaFuncSetAttribute(k_softras_backward<DIST, RGB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     dim3 grid(P.ntx * P.ntx, P.B);
@@ -118,7 +118,7 @@ int b200r_softras_forward(const float* face_vertices, const float* textures, flo
     const int total = B * nf;
     {
         B200rProfScope prof(B200R_K_FACE_SETUP, st);
-        k_face_setup<<<(total + 255) / 256, 256, 0, st>>>(face_vertices, W.recs, W.rects, faces_info, total, nf, is, border);
+        k_face_setup<<<(total + 255) / 256, 256, 0, st>>>(face_vertices, textures, W.recs, W.rects, faces_info, total, nf, T, texture_type, is, border);
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return b200r_cuda_fail(e, "k_face_setup");

@@ -26,7 +26,7 @@ k_softras_backward(const SoftRasParams P, const FaceRec* __restrict__ recs, cons
                    float* __restrict__ grad_faces, float* __restrict__ grad_textures) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     int* s_id = reinterpret_cast<int*>(smem_raw);                                     // [K][256]
-    float* s_wrec = reinterpret_cast<float*>(s_id + (size_t)P.K * B200R_TILE_THREADS);  // [8][32]
+    float* s_wrec = reinterpret_cast<float*>(s_id + (size_t)P.K * B200R_TILE_THREADS);  // [8][40]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int is = P.is, nf = P.nf, K = P.K, T = P.T;
@@ -39,6 +39,8 @@ k_softras_backward(const SoftRasParams P, const FaceRec* __restrict__ recs, cons
     const float yp = b200r_pix_coord(is - 1 - row, is);
     const size_t npix = (size_t)is * is;
     const size_t pn = (size_t)row * is + px;
+    DivConst dc;
+    dc.init(P);
 
     // ---- load + insertion-sort this pixel's ids (ascending; list ends at the first -1, :1236)
     int n = 0;
@@ -73,11 +75,20 @@ k_softras_backward(const SoftRasParams P, const FaceRec* __restrict__ recs, cons
         softmax_max = __ldg(aggrs_info + ((size_t)b * 2 + 1) * npix + pn);
     }
 
+    // per-pixel / per-launch denominators of the backward
+    const float r_ssum = rcp_refined(softmax_sum);
+    const bool s_ssum = midrange(softmax_sum);
+    const double d_galpha = (double)g[3];
+    const double d_one_minus_alpha = (double)(1.f - oc[3]);
+    const float nmf = P.near_ - P.far_;
+    const float r_nmf = rcp_refined(nmf);
+    const bool s_nmf = midrange(nmf);
+
     const FaceRec* brecs = recs + (size_t)b * nf;
     const float* btex = textures + (size_t)b * nf * T * 3;
     float* bgf = grad_faces + (size_t)b * nf * 9;
     float* bgt = grad_textures + (size_t)b * nf * T * 3;
-    FaceRec* wrec = reinterpret_cast<FaceRec*>(s_wrec + warp * 32);
+    FaceRec* wrec = reinterpret_cast<FaceRec*>(s_wrec + warp * 40);
 
     int p = 0;
     int cur = (p < n) ? s_id[tid] : 0x7fffffff;
@@ -87,6 +98,7 @@ k_softras_backward(const SoftRasParams P, const FaceRec* __restrict__ recs, cons
         // stage the record for the warp: one 4-byte word per lane
         __syncwarp();
         reinterpret_cast<uint32_t*>(wrec)[lane] = __ldg(reinterpret_cast<const uint32_t*>(brecs + fn) + lane);
+        if (lane < 8) reinterpret_cast<uint32_t*>(wrec)[32 + lane] = __ldg(reinterpret_cast<const uint32_t*>(brecs + fn) + 32 + lane);
         __syncwarp();
         const bool mine = (cur == fn);
 
@@ -103,11 +115,11 @@ k_softras_backward(const SoftRasParams P, const FaceRec* __restrict__ recs, cons
             } else if (DIST == 1) {
                 dis = barycentric_p2f_distance(w);
                 t[0] = w[0]; t[1] = w[1]; t[2] = w[2];
-                soft_fragment = sigmoid_from_negarg(-dis / P.sigma);
+                soft_fragment = sigmoid_from_negarg(dc.by_sigma(-dis));
             } else {
                 sign = euclidean_p2f_distance(dis_x, dis_y, t, w, rec, xp, yp);
                 dis = dis_x * dis_x + dis_y * dis_y;
-                soft_fragment = sigmoid_from_negarg(-sign * dis / P.sigma);
+                soft_fragment = sigmoid_from_negarg(dc.by_sigma(-sign * dis));
             }
 
             float C_grad_xy = 0.f;
@@ -115,14 +127,17 @@ k_softras_backward(const SoftRasParams P, const FaceRec* __restrict__ recs, cons
             if (P.alpha_func == 1) {
                 C_grad_xy_alpha = C_grad_xy_alpha / (float)nf;
             } else if (P.alpha_func == 2) {
-                C_grad_xy_alpha = (float)((double)C_grad_xy_alpha *
-                                          ((double)(1.f - oc[3]) / fmax((double)(1.f - soft_fragment), 1e-6)));
+                // (float)((double)g_a * ((double)(1 - alpha_out) / max((double)(1 - D), 1e-6)))  (:1289)
+                const float omd = 1.f - soft_fragment;
+                const double den = fmax(midrange(omd) ? f2d_mid(omd) : (double)omd, 1e-6);
+                const double prod = d_galpha * (d_one_minus_alpha / den);
+                C_grad_xy_alpha = d_midrange(prod) ? d2f_mid(prod) : (float)prod;
             }
             C_grad_xy += C_grad_xy_alpha;
 
             const float w0[3] = {w[0], w[1], w[2]};
             barycentric_clip(w);
-            const float zp = 1.f / (w[0] / f[2] + w[1] / f[5] + w[2] / f[8]);
+            const float zp = interp_z(w, rec);
 
             const float* tex = btex + (size_t)fn * T * 3;
             if (RGB == 0) {
@@ -143,13 +158,16 @@ k_softras_backward(const SoftRasParams P, const FaceRec* __restrict__ recs, cons
                 }
             } else if (RGB == 1) {
                 float C_grad_xyz_rgb = 0.f;
-                const float zp_norm = (P.far_ - zp) / (P.far_ - P.near_);
-                const float zp_softmax = soft_fragment * expf((zp_norm - softmax_max) / P.gamma) / softmax_sum;
+                const float zp_norm = dc.by_span(P.far_ - zp);
+                const float zp_softmax = fast_div(soft_fragment * expf(dc.by_gamma(zp_norm - softmax_max)), softmax_sum, r_ssum, s_ssum);
                 float col[3];
                 if (P.tex_type == 0) {
                     const int j = surface_texel(w, P.R);
+                    if (T == 1) { col[0] = rec->col[0]; col[1] = rec->col[1]; col[2] = rec->col[2]; }
+                    else {
 #pragma unroll
-                    for (int k = 0; k < 3; k++) col[k] = __ldg(tex + j * 3 + k);
+                        for (int k = 0; k < 3; k++) col[k] = __ldg(tex + j * 3 + k);
+                    }
                     if (T == 1) {
 #pragma unroll
                         for (int k = 0; k < 3; k++) gt[k] = zp_softmax * g[k];
@@ -171,13 +189,17 @@ k_softras_backward(const SoftRasParams P, const FaceRec* __restrict__ recs, cons
                 C_grad_xyz_rgb *= zp_softmax;
                 C_grad_xy += C_grad_xyz_rgb / soft_fragment;
 
-                const float C_grad_z_rgb = C_grad_xyz_rgb / P.gamma / (P.near_ - P.far_) * zp * zp;
-                gv[0 * 3 + 2] = C_grad_z_rgb * w[0] / f[2] / f[2];
-                gv[1 * 3 + 2] = C_grad_z_rgb * w[1] / f[5] / f[5];
-                gv[2 * 3 + 2] = C_grad_z_rgb * w[2] / f[8] / f[8];
+                const float C_grad_z_rgb = fast_div(dc.by_gamma(C_grad_xyz_rgb), nmf, r_nmf, s_nmf) * zp * zp;
+                const uint32_t fl = rec->flags;
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    const bool sz = (fl & (16u << k)) != 0;
+                    const float z = f[3 * k + 2], rz = rec->rz[k];
+                    gv[k * 3 + 2] = fast_div(fast_div(C_grad_z_rgb * w[k], z, rz, sz), z, rz, sz);
+                }
             }
 
-            C_grad_xy *= soft_fragment * (1.f - soft_fragment) / P.sigma;  // :1336
+            C_grad_xy *= dc.by_sigma(soft_fragment * (1.f - soft_fragment));  // :1336
             if (DIST == 1) {  // backward_barycentric_p2f_distance (:1118-1132), w := t (unclipped)
                 const int pm = t[0] > t[1] ? (t[1] > t[2] ? 2 : 1) : (t[0] > t[2] ? 2 : 0);
                 const float* inv = rec->inv;

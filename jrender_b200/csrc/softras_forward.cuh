@@ -5,7 +5,7 @@
 // One CTA = one 16x16 pixel tile of one batch element, one thread = one pixel, warp w
 // owns an 8x4 sub-rectangle.  The CTA walks its coarse bin's face list (ascending face id),
 // keeps the faces whose check_border rectangle touches the tile (ordered ballot
-// compaction), stages their 128-byte records in shared memory in chunks, and every warp
+// compaction), stages their 160-byte records in shared memory in chunks, and every warp
 // narrows the chunk to the faces touching its 8x4 footprint before the per-pixel loop.
 // Faces are therefore visited per pixel in ascending id exactly like the reference's
 // `for (fn = 0; fn < nf; fn++)` (:311), minus the faces check_border would skip.
@@ -18,7 +18,7 @@ namespace b200r {
 #define B200R_CHUNK 128  // staged faces per round (index fits uint8)
 
 struct FwdSmem {
-    FaceRec rec[B200R_CHUNK];            // 16 KB (reused as the output staging area)
+    FaceRec rec[B200R_CHUNK];            // 20 KB (reused as the output staging area)
     int ids[B200R_CHUNK + 256];          // pending tile-face ids, ascending
     unsigned char wlist[8][B200R_CHUNK]; // per-warp sub-list (indices into rec[])
     int s_warp[8];
@@ -51,6 +51,8 @@ k_softras_forward(const SoftRasParams P, const FaceRec* __restrict__ recs, const
     const int wr0 = tr0 + (warp >> 1) * 4, wr1 = wr0 + 3;
 
     const float threshold = P.dist_eps * P.sigma;  // :289
+    DivConst dc;
+    dc.init(P);
 
     // ---- per-pixel state, initialised as :291-309 (background buffer is all zero, Q1)
     float softmax_sum = expf(P.eps / P.gamma);
@@ -95,9 +97,9 @@ k_softras_forward(const SoftRasParams P, const FaceRec* __restrict__ recs, const
         while (n_pending >= B200R_CHUNK || (last && n_pending > 0)) {
             const int m = min(n_pending, B200R_CHUNK);
             __syncthreads();  // S.ids complete; previous round's readers of S.rec done
-            // ---- stage m records: 8 x uint4 per face, coalesced
-            for (int j = tid; j < m * 8; j += B200R_TILE_THREADS) {
-                const int f = j >> 3, q = j & 7;
+            // ---- stage m records: 10 x uint4 per face, coalesced
+            for (int j = tid; j < m * B200R_REC_UINT4; j += B200R_TILE_THREADS) {
+                const int f = j / B200R_REC_UINT4, q = j - f * B200R_REC_UINT4;
                 reinterpret_cast<uint4*>(&S.rec[f])[q] =
                     __ldg(reinterpret_cast<const uint4*>(brecs + S.ids[f]) + q);
             }
@@ -138,13 +140,13 @@ k_softras_forward(const SoftRasParams P, const FaceRec* __restrict__ recs, const
                 } else if (DIST == 1) {
                     const float dis = barycentric_p2f_distance(w);
                     if (-dis >= threshold) continue;  // :337
-                    soft_fragment = sigmoid_from_negarg(-dis / P.sigma);
+                    soft_fragment = sigmoid_from_negarg(dc.by_sigma(-dis));
                 } else {
                     float dis_x, dis_y, t[3];
                     const float sign = euclidean_p2f_distance(dis_x, dis_y, t, w, rec, xp, yp);
                     const float dis = dis_x * dis_x + dis_y * dis_y;
                     if (sign < 0.f && dis >= threshold) continue;  // :343
-                    soft_fragment = sigmoid_from_negarg(-sign * dis / P.sigma);
+                    soft_fragment = sigmoid_from_negarg(dc.by_sigma(-sign * dis));
                 }
 
                 // alpha aggregation, before any z test (:349-358, Q2)
@@ -153,13 +155,12 @@ k_softras_forward(const SoftRasParams P, const FaceRec* __restrict__ recs, const
                 } else if (P.alpha_func == 1) {
                     alpha += soft_fragment;
                 } else {
-                    alpha = (float)((double)alpha * (1.0 - (double)soft_fragment));
+                    alpha = alpha_prod(alpha, soft_fragment);
                 }
 
                 float wc[3] = {w[0], w[1], w[2]};
                 barycentric_clip(wc);
-                const float* f = rec->v;
-                const float zp = 1.f / (wc[0] / f[2] + wc[1] / f[5] + wc[2] / f[8]);  // :364
+                const float zp = interp_z(wc, rec);  // :364
                 if (zp < P.near_ || zp > P.far_) continue;                               // :365
 
                 const int fn = (int)rec->face_id;
@@ -185,21 +186,21 @@ k_softras_forward(const SoftRasParams P, const FaceRec* __restrict__ recs, const
                         depth_min = zp;
                         face_index_min = fn;
                         float col[3];
-                        sample_texture_fwd(col, btex + (size_t)fn * P.T * 3, wc, P.R, P.tex_type, f, zp);
+                        sample_texture_fwd(col, btex + (size_t)fn * P.T * 3, wc, P.R, P.tex_type, rec, zp);
                         sc0 = col[0]; sc1 = col[1]; sc2 = col[2];
                     }
                 } else if (RGB == 1) {  // :399-419
                     if (front || P.double_side) {
-                        const float zp_norm = (P.far_ - zp) / (P.far_ - P.near_);
+                        const float zp_norm = dc.by_span(P.far_ - zp);
                         float exp_delta_zp = 1.f;
                         if (zp_norm > softmax_max) {
-                            exp_delta_zp = expf((softmax_max - zp_norm) / P.gamma);
+                            exp_delta_zp = expf(dc.by_gamma(softmax_max - zp_norm));
                             softmax_max = zp_norm;
                         }
-                        const float exp_z = expf((zp_norm - softmax_max) / P.gamma);
+                        const float exp_z = expf(dc.by_gamma(zp_norm - softmax_max));
                         softmax_sum = exp_delta_zp * softmax_sum + exp_z * soft_fragment;
                         float col[3];
-                        sample_texture_fwd(col, btex + (size_t)fn * P.T * 3, wc, P.R, P.tex_type, f, zp);
+                        sample_texture_fwd(col, btex + (size_t)fn * P.T * 3, wc, P.R, P.tex_type, rec, zp);
                         sc0 = exp_delta_zp * sc0 + exp_z * soft_fragment * col[0];
                         sc1 = exp_delta_zp * sc1 + exp_z * soft_fragment * col[1];
                         sc2 = exp_delta_zp * sc2 + exp_z * soft_fragment * col[2];

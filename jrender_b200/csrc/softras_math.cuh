@@ -7,11 +7,27 @@
 // through a literal (`1. / (1. + exp(..))`, `alpha *= 1. - D`) the same promotion is
 // done here; where the promotion provably cannot change the fp32 result (clamps against
 // representable constants, `1./x` of a float: 53 >= 2*24+2 so double rounding is
-// innocuous) plain fp32 is used.
+// innocuous) plain fp32 is used.  Divisions go through exact_math.cuh's fast_div, which
+// returns the correctly rounded quotient without a MUFU when the reciprocal is known.
 #pragma once
 #include "common.cuh"
+#include "exact_math.cuh"
 
 namespace b200r {
+
+// Reciprocals of the per-launch constant denominators, computed once per thread.
+struct DivConst {
+    float sigma, r_sigma, gamma, r_gamma, span, r_span;  // span = far - near
+    bool s_sigma, s_gamma, s_span;
+    __device__ __forceinline__ void init(const SoftRasParams& P) {
+        sigma = P.sigma; gamma = P.gamma; span = P.far_ - P.near_;
+        r_sigma = rcp_refined(sigma); r_gamma = rcp_refined(gamma); r_span = rcp_refined(span);
+        s_sigma = midrange(sigma); s_gamma = midrange(gamma); s_span = midrange(span);
+    }
+    __device__ __forceinline__ float by_sigma(float a) const { return fast_div(a, sigma, r_sigma, s_sigma); }
+    __device__ __forceinline__ float by_gamma(float a) const { return fast_div(a, gamma, r_gamma, s_gamma); }
+    __device__ __forceinline__ float by_span(float a) const { return fast_div(a, span, r_span, s_span); }
+};
 
 // :20-25
 __device__ __forceinline__ void barycentric_coordinate(float w[3], float x, float y, const float* inv) {
@@ -30,8 +46,21 @@ __device__ __forceinline__ void barycentric_clip(float w[3]) {
 #pragma unroll
     for (int k = 0; k < 3; k++) w[k] = fmaxf(fminf(w[k], 1.f), 0.f);
     const float w_sum = fmaxf(w[0] + w[1] + w[2], 1e-5f);
+    if (w_sum != 1.f) {  // x / 1 == x exactly
+        const float r = rcp_refined(w_sum);
+        const bool safe = midrange(w_sum);
 #pragma unroll
-    for (int k = 0; k < 3; k++) w[k] = w[k] / w_sum;
+        for (int k = 0; k < 3; k++) w[k] = fast_div(w[k], w_sum, r, safe);
+    }
+}
+
+// zp = 1. / (w0/z0 + w1/z1 + w2/z2)   (:364, :1296)
+__device__ __forceinline__ float interp_z(const float wc[3], const FaceRec* rec) {
+    const uint32_t fl = rec->flags;
+    const float a = fast_div(wc[0], rec->v[2], rec->rz[0], (fl & 16u) != 0);
+    const float b = fast_div(wc[1], rec->v[5], rec->rz[1], (fl & 32u) != 0);
+    const float c = fast_div(wc[2], rec->v[8], rec->rz[2], (fl & 64u) != 0);
+    return 1.f / (a + b + c);
 }
 
 __device__ __forceinline__ float sel3(int i, float a, float b, float c) { return i == 0 ? a : (i == 1 ? b : c); }
@@ -42,6 +71,7 @@ __device__ __forceinline__ float euclidean_p2f_distance(float& dis_x, float& dis
                                                         const float w[3], const FaceRec* rec,
                                                         float xp, float yp) {
     const float* f = rec->v;
+    const uint32_t fl = rec->flags;
     if (w[0] > 0.f && w[1] > 0.f && w[2] > 0.f && w[0] < 1.f && w[1] < 1.f && w[2] < 1.f) {
         float dis_min = 100000000.f;
         float dis_x_min = 0.f, dis_y_min = 0.f;
@@ -51,7 +81,8 @@ __device__ __forceinline__ float euclidean_p2f_distance(float& dis_x, float& dis
             const int v0 = k, v1 = (k + 1) % 3, v2 = (k + 2) % 3;
             const float* a = rec->a0 + 3 * k;
             float t0[3];
-            t0[v0] = (w[0] * a[0] + w[1] * a[1] + w[2] * a[2] - a[v1]) / (a[v0] - a[v1]);
+            t0[v0] = fast_div(w[0] * a[0] + w[1] * a[1] + w[2] * a[2] - a[v1], a[v0] - a[v1], rec->rden[k],
+                              (fl & (128u << k)) != 0);
             t0[v1] = 1.f - t0[v0];
             t0[v2] = 0.f;
             t0[0] -= w[0];
@@ -73,17 +104,16 @@ __device__ __forceinline__ float euclidean_p2f_distance(float& dis_x, float& dis
         dis_y = dis_y_min;
         return 1.f;
     } else {
-        const uint32_t obt = rec->flags;
         int v0 = 0;  // the reference leaves v0 = -1 (UB) when no branch fires; oracle uses 0 too
         if (w[1] <= 0.f && w[2] <= 0.f) {
             v0 = 0;
-            if ((obt & 1u) && (xp - f[0]) * (f[6] - f[0]) + (yp - f[1]) * (f[7] - f[1]) > 0.f) v0 = 2;
+            if ((fl & 1u) && (xp - f[0]) * (f[6] - f[0]) + (yp - f[1]) * (f[7] - f[1]) > 0.f) v0 = 2;
         } else if (w[2] <= 0.f && w[0] <= 0.f) {
             v0 = 1;
-            if ((obt & 2u) && (xp - f[3]) * (f[0] - f[3]) + (yp - f[4]) * (f[1] - f[4]) > 0.f) v0 = 0;
+            if ((fl & 2u) && (xp - f[3]) * (f[0] - f[3]) + (yp - f[4]) * (f[1] - f[4]) > 0.f) v0 = 0;
         } else if (w[0] <= 0.f && w[1] <= 0.f) {
             v0 = 2;
-            if ((obt & 4u) && (xp - f[6]) * (f[3] - f[6]) + (yp - f[7]) * (f[4] - f[7]) > 0.f) v0 = 1;
+            if ((fl & 4u) && (xp - f[6]) * (f[3] - f[6]) + (yp - f[7]) * (f[4] - f[7]) > 0.f) v0 = 1;
         } else if (w[0] <= 0.f) v0 = 1;
         else if (w[1] <= 0.f) v0 = 2;
         else if (w[2] <= 0.f) v0 = 0;
@@ -93,7 +123,8 @@ __device__ __forceinline__ float euclidean_p2f_distance(float& dis_x, float& dis
         const float a_0 = a[0], a_1 = a[1], a_2 = a[2];
         const float a_v0 = sel3(v0, a_0, a_1, a_2);
         const float a_v1 = sel3(v1, a_0, a_1, a_2);
-        const float tv0 = (w[0] * a_0 + w[1] * a_1 + w[2] * a_2 - a_v1) / (a_v0 - a_v1);
+        const float tv0 = fast_div(w[0] * a_0 + w[1] * a_1 + w[2] * a_2 - a_v1, a_v0 - a_v1, rec->rden[v0],
+                                   (fl & (128u << v0)) != 0);
         const float tv1 = 1.f - tv0;
         const float c0 = fminf(fmaxf(tv0, 0.f), 1.f);
         const float c1 = fminf(fmaxf(tv1, 0.f), 1.f);
@@ -116,12 +147,12 @@ __device__ __forceinline__ float barycentric_p2f_distance(const float w[3]) {
 }
 
 // `1. / (1. + exp(x))` with x already = -sign*dis/sigma  (:338, :344)
-__device__ __forceinline__ float sigmoid_from_negarg(float x) {
-    return (float)(1.0 / (1.0 + (double)expf(x)));
-}
+__device__ __forceinline__ float sigmoid_from_negarg(float x) { return sigmoid_tail(expf(x)); }
 
-// surface texel index of forward_sample_texture / backward_sample_texture (:159-166, :1157-1168)
+// surface texel index of forward_sample_texture / backward_sample_texture (:159-166, :1157-1168).
+// R == 1: both branches of the reference give texel 0 (w is clipped to >= 0).
 __device__ __forceinline__ int surface_texel(const float w[3], int R) {
+    if (R == 1) return 0;
     const int w_x = (int)fminf(w[0] * R, (float)(R - 1));
     const int w_y = (int)fminf(w[1] * R, (float)(R - 1));
     if ((w[0] + w[1]) * R - w_x - w_y <= 1.f) return w_y * R + w_x;
@@ -131,15 +162,22 @@ __device__ __forceinline__ int surface_texel(const float w[3], int R) {
 // :156-173 forward flavour (vertex mode perspective-correct); tex points at this face's texels
 __device__ __forceinline__ void sample_texture_fwd(float col[3], const float* __restrict__ tex,
                                                    const float w[3], int R, int tex_type,
-                                                   const float* f, float z) {
+                                                   const FaceRec* rec, float z) {
     if (tex_type == 0) {
-        const int j = surface_texel(w, R);
+        if (R == 1) {
+            col[0] = rec->col[0]; col[1] = rec->col[1]; col[2] = rec->col[2];
+        } else {
+            const int j = surface_texel(w, R);
 #pragma unroll
-        for (int k = 0; k < 3; k++) col[k] = __ldg(tex + j * 3 + k);
+            for (int k = 0; k < 3; k++) col[k] = __ldg(tex + j * 3 + k);
+        }
     } else {
+        const uint32_t fl = rec->flags;
 #pragma unroll
         for (int k = 0; k < 3; k++) {
-            float c = w[0] * __ldg(tex + k) / f[2] + w[1] * __ldg(tex + 3 + k) / f[5] + w[2] * __ldg(tex + 6 + k) / f[8];
+            const float c = fast_div(w[0] * __ldg(tex + k), rec->v[2], rec->rz[0], (fl & 16u) != 0) +
+                            fast_div(w[1] * __ldg(tex + 3 + k), rec->v[5], rec->rz[1], (fl & 32u) != 0) +
+                            fast_div(w[2] * __ldg(tex + 6 + k), rec->v[8], rec->rz[2], (fl & 64u) != 0);
             col[k] = c * z;
         }
     }

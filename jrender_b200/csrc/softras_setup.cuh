@@ -1,6 +1,7 @@
 // softras_setup.cuh -- per-face setup (K1 replacement) and deterministic coarse binning.
 #pragma once
 #include "common.cuh"
+#include "exact_math.cuh"
 
 namespace b200r {
 
@@ -25,12 +26,13 @@ __device__ __forceinline__ int last_not_above(float lim, int is) {
     return i;
 }
 
-// One thread per (batch, face).  Computes the 128-byte record, the exact pixel rectangle
+// One thread per (batch, face).  Computes the 160-byte record, the exact pixel rectangle
 // equivalent to check_border, and (optionally) the reference's faces_info[27].
 // Reference: forward_soft_rasterize_inv_cuda_kernel, cuda/soft_rasterize.py:176-236.
-__global__ void __launch_bounds__(256) k_face_setup(const float* __restrict__ faces, FaceRec* __restrict__ recs,
-                                                    uint2* __restrict__ rects, float* __restrict__ faces_info,
-                                                    int total_faces, int nf, int is, float border) {
+__global__ void __launch_bounds__(256) k_face_setup(const float* __restrict__ faces, const float* __restrict__ textures,
+                                                    FaceRec* __restrict__ recs, uint2* __restrict__ rects,
+                                                    float* __restrict__ faces_info, int total_faces, int nf,
+                                                    int T, int tex_type, int is, float border) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total_faces) return;
     const float* face = faces + (size_t)i * 9;
@@ -72,9 +74,20 @@ __global__ void __launch_bounds__(256) k_face_setup(const float* __restrict__ fa
     }
     // check_face_frontside (:37-40)
     if ((f[7] - f[1]) * (f[3] - f[0]) < (f[4] - f[1]) * (f[6] - f[0])) flags |= 8u;
+    // refined reciprocals of the per-face denominators (exact_math.cuh)
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const float z = f[3 * k + 2];
+        const float den = r.a0[3 * k + k] - r.a0[3 * k + (k + 1) % 3];
+        r.rz[k] = rcp_refined(z);
+        r.rden[k] = rcp_refined(den);
+        if (midrange(z)) flags |= 16u << k;
+        if (midrange(den)) flags |= 128u << k;
+    }
     r.flags = flags;
     r.face_id = (uint32_t)(i % nf);
-    r.pad = 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; k++) r.col[k] = (T == 1 && tex_type == 0) ? __ldg(textures + (size_t)i * 3 + k) : 0.f;
 
     // check_border (:28-34) as an exact pixel rectangle
     const float xhi = fmaxf(fmaxf(f[0], f[3]), f[6]) + border;
@@ -88,11 +101,11 @@ __global__ void __launch_bounds__(256) k_face_setup(const float* __restrict__ fa
     r.rect_x = (uint32_t)x0 | ((uint32_t)x1 << 16);
     r.rect_r = (uint32_t)r0 | ((uint32_t)r1 << 16);
 
-    // 128-byte record as 8 x 16-byte stores
+    // 160-byte record as 10 x 16-byte stores
     const uint4* src = reinterpret_cast<const uint4*>(&r);
     uint4* dst = reinterpret_cast<uint4*>(recs + i);
 #pragma unroll
-    for (int k = 0; k < 8; k++) dst[k] = src[k];
+    for (int k = 0; k < B200R_REC_UINT4; k++) dst[k] = src[k];
     rects[i] = make_uint2(r.rect_x, r.rect_r);
 
     if (faces_info != nullptr) {
@@ -102,7 +115,7 @@ __global__ void __launch_bounds__(256) k_face_setup(const float* __restrict__ fa
 #pragma unroll
         for (int k = 0; k < 9; k++) fi[9 + k] = sym[k];
 #pragma unroll
-        for (int k = 0; k < 3; k++) fi[18 + k] = (flags >> k) & 1u ? 1.f : 0.f;
+        for (int k = 0; k < 3; k++) fi[18 + k] = ((flags >> k) & 1u) ? 1.f : 0.f;
 #pragma unroll
         for (int k = 21; k < 27; k++) fi[k] = 0.f;
     }

@@ -1,0 +1,189 @@
+"""Lighting (host-side mirror in PyTorch; O(nf) elementwise work before the rasterizer, no
+custom kernels -- SURVEY.md section 2.1 marks it "next / out of scope for kernels").
+
+Mirrors jrender/renderer/lighting/{ambient_lighting,directional_lighting,lighting}.py for the
+paths the rasterizer demos use: ambient + directional light in 'surface' and 'vertex' modes,
+including the Cook-Torrance specular branch the reference takes by default
+(Mesh.with_specular defaults to True, structures/mesh.py:74).  Normal-mapped meshes
+(surface_ResNormals), SSS and the Gbuffer debug modes are not mirrored.
+"""
+import torch
+from torch import nn
+import torch.nn.functional as F
+
+
+def _t(x, like):
+    if isinstance(x, torch.Tensor):
+        return x.to(device=like.device, dtype=torch.float32)
+    return torch.tensor(x, dtype=torch.float32, device=like.device)
+
+
+def ambient_lighting(light, light_intensity=0.5, light_color=(1, 1, 1)):
+    """ambient_lighting.py:4-9."""
+    light_color = _t(light_color, light)
+    if light_color.dim() == 1:
+        light_color = light_color[None, :]
+    return light + light_intensity * light_color[:, None, :]
+
+
+def GGX(N, H, roughness):
+    a = roughness * roughness
+    a2 = a * a
+    NdotH = F.relu(torch.sum(N * H, dim=2))
+    NdotH2 = (NdotH * NdotH)[:, :, None]
+    denom = (NdotH2 * (a2 - 1.0) + 1.0)
+    denom = 3.1415 * denom * denom
+    return a2 / denom
+
+
+def SchlickGGX(NdotV, roughness):
+    r = roughness + 1.0
+    k = (r * r) / 8.0
+    NdotV = NdotV[:, :, None]
+    return NdotV / (NdotV * (1.0 - k) + k)
+
+
+def GeometrySmith(N, V, L, roughness):
+    NdotV = F.relu(torch.sum(N * V, dim=2))
+    NdotL = F.relu(torch.sum(N * L, dim=2))
+    return SchlickGGX(NdotL, roughness) * SchlickGGX(NdotV, roughness)
+
+
+def fresnelSchlick(cosTheta, F0):
+    return F0 + (1.0 - F0) * torch.pow(1.0 - cosTheta, 5)[:, :, None]
+
+
+def directional_lighting(diffuseLight, specularLight, normals, light_intensity=0.5, light_color=(1, 1, 1),
+                         light_direction=(0, 1, 0), positions=None, eye=None, with_specular=False,
+                         metallic_textures=None, roughness_textures=None):
+    """directional_lighting.py:54-145 for 3-D normals ([B, n, 3])."""
+    light_color = _t(light_color, normals)
+    light_direction = F.normalize(_t(light_direction, normals), dim=0, eps=1e-12)
+    if light_color.dim() == 1:
+        light_color = light_color[None, :]
+    if light_direction.dim() == 1:
+        light_direction = light_direction[None, :]
+    cosine = F.relu(torch.sum(normals * light_direction, dim=2))
+
+    if with_specular and metallic_textures is not None and roughness_textures is not None:
+        if metallic_textures.dim() == 4:
+            total = metallic_textures.shape[2] * 1.0
+            metallic_textures = torch.sum(metallic_textures, dim=2) / total
+            roughness_textures = torch.sum(roughness_textures, dim=2) / total
+        elif metallic_textures.dim() == 6:
+            total = metallic_textures.shape[2] * metallic_textures.shape[3] * metallic_textures.shape[4] * 1.0
+            metallic_textures = metallic_textures.sum(dim=(2, 3, 4)) / total
+            roughness_textures = roughness_textures.sum(dim=(2, 3, 4)) / total
+
+    if with_specular and eye is not None and positions is not None and metallic_textures is not None \
+            and roughness_textures is not None:
+        eye = _t(eye, normals)
+        if eye.dim() == 1:
+            eye = eye[None, :]
+        if eye.dim() == 2:
+            eye = eye[:, None, :]
+        N = normals
+        V = F.normalize(eye - positions, dim=2, eps=1e-12)
+        L = light_direction
+        H = F.normalize(V + L, dim=2, eps=1e-12)
+        metallic = metallic_textures
+        roughness = roughness_textures
+        F0 = _t((0.4, 0.4, 0.4), normals)[None, None, :] * (1 - metallic) + _t((1.0, 1.0, 1.0), normals)[None, None, :] * metallic
+        radiance = light_intensity * (light_color[:, None, :] * cosine[:, :, None])
+        NDF = GGX(N, H, roughness)
+        G = GeometrySmith(N, V, L, roughness)
+        Fr = fresnelSchlick(F.relu(torch.sum(H * V, dim=2)), F0)
+        KD = (1.0 - Fr) * (1.0 - metallic)
+        diffuseLight = diffuseLight + KD * radiance
+        numerator = NDF * G * Fr
+        denominator = (4.0 * F.relu(torch.sum(N * V, dim=2)) * F.relu(torch.sum(N * L, dim=2)))[:, :, None]
+        specular = numerator / torch.clamp(denominator, min=0.01)
+        specularLight = specularLight + specular * radiance
+    else:
+        diffuseLight = diffuseLight + light_intensity * (light_color[:, None, :] * cosine[:, :, None])
+    return [diffuseLight, specularLight]
+
+
+class AmbientLighting(nn.Module):
+    def __init__(self, light_intensity=0.5, light_color=(1, 1, 1)):
+        super(AmbientLighting, self).__init__()
+        self.light_intensity = light_intensity
+        self.light_color = light_color
+
+    def forward(self, light):
+        return ambient_lighting(light, self.light_intensity, self.light_color)
+
+    execute = forward
+
+
+class DirectionalLighting(nn.Module):
+    def __init__(self, light_intensity=0.5, light_color=(1, 1, 1), light_direction=(0, 1, 0)):
+        super(DirectionalLighting, self).__init__()
+        self.light_intensity = light_intensity
+        self.light_color = light_color
+        self.light_direction = light_direction
+
+    def forward(self, diffuseLight, specularLight, normals, positions=None, eye=None, with_specular=False,
+                metallic_textures=None, roughness_textures=None):
+        return directional_lighting(diffuseLight, specularLight, normals, self.light_intensity, self.light_color,
+                                    self.light_direction, positions, eye, with_specular, metallic_textures,
+                                    roughness_textures)
+
+    execute = forward
+
+
+class Lighting(nn.Module):
+    """lighting.py:159-223."""
+
+    def __init__(self, light_mode='surface',
+                 intensity_ambient=0.5, color_ambient=[1, 1, 1],
+                 intensity_directionals=0.5, color_directionals=[1, 1, 1],
+                 directions=[0, 1, 0], Gbuffer='None', transform=None):
+        super(Lighting, self).__init__()
+        if light_mode not in ['surface', 'vertex']:
+            raise ValueError('Lighting mode only support surface and vertex')
+        if Gbuffer not in ('None', None, 'albedo'):
+            raise NotImplementedError("Gbuffer=%r (render2 debug outputs) is outside this repo's scope" % (Gbuffer,))
+        self.Gbuffer = Gbuffer
+        self.transform = transform
+        self.light_mode = light_mode
+        self.ambient = AmbientLighting(intensity_ambient, color_ambient)
+        self.directionals = nn.ModuleList([DirectionalLighting(intensity_directionals, color_directionals, directions)])
+
+    def forward(self, mesh, eyes=None):
+        if self.Gbuffer == "albedo":
+            return mesh
+        if self.light_mode == 'surface':
+            diffuseLight = torch.zeros(mesh.faces.shape, dtype=torch.float32, device=mesh.vertices.device)
+            specularLight = torch.zeros_like(diffuseLight)
+            diffuseLight = self.ambient(diffuseLight)
+            for directional in self.directionals:
+                diffuseLight, specularLight = directional(
+                    diffuseLight, specularLight, mesh.surface_normals, torch.sum(mesh.face_vertices, dim=2) / 3.0, eyes,
+                    mesh.with_specular, mesh.metallic_textures, mesh.roughness_textures)
+            diffuseLight = diffuseLight[:, :, None, :]
+            specularLight = specularLight[:, :, None, :]
+            if mesh.textures.dim() == 4:
+                mesh.textures = torch.clamp(mesh.textures * diffuseLight + torch.ones_like(mesh.textures) * specularLight, 0.0, 1.0)
+            elif mesh.textures.dim() == 6:
+                mesh.textures = torch.clamp(mesh.textures * diffuseLight[:, :, :, None, None, :] +
+                                            torch.ones_like(mesh.textures) * specularLight[:, :, :, None, None, :], 0.0, 1.0)
+        elif self.light_mode == 'vertex':
+            diffuseLight = torch.zeros(mesh.vertices.shape, dtype=torch.float32, device=mesh.vertices.device)
+            specularLight = torch.zeros_like(diffuseLight)
+            diffuseLight = self.ambient(diffuseLight)
+            for directional in self.directionals:
+                diffuseLight, specularLight = directional(
+                    diffuseLight, specularLight, mesh.vertex_normals, mesh.vertices, eyes,
+                    mesh.with_specular, mesh.metallic_textures, mesh.roughness_textures)
+            # The reference only applies vertex lighting to 4-D / 6-D textures (lighting.py:214-220);
+            # the documented vertex texture shape [B, nv, 3] therefore passes through unlit.
+            if mesh.textures.dim() == 4:
+                mesh.textures = torch.clamp(mesh.textures * diffuseLight[:, :, None, :] +
+                                            torch.ones_like(mesh.textures) * specularLight[:, :, None, :], 0.0, 1.0)
+            elif mesh.textures.dim() == 6:
+                mesh.textures = torch.clamp(mesh.textures * diffuseLight[:, :, None, None, None, :] +
+                                            torch.ones_like(mesh.textures) * specularLight[:, :, None, None, None, :], 0.0, 1.0)
+        return mesh
+
+    execute = forward

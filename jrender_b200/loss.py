@@ -1,0 +1,95 @@
+"""Mesh-fitting losses (host-side mirror in PyTorch of jrender/loss/*.py).
+
+neg_iou_loss  (iou_loss.py:1-5), LaplacianLoss (laplacian_loss.py:5-36, stored sparse here
+instead of the reference's dense nv x nv matrix -- same values), FlattenLoss
+(flatten_loss.py:5-79, edge table built with a dictionary instead of the O(E*F) scan).
+"""
+import numpy as np
+import torch
+from torch import nn
+
+
+def neg_iou_loss(predict, target):
+    dims = tuple(range(predict.dim())[1:])
+    intersect = (predict * target).sum(dims)
+    union = (predict + target - predict * target).sum(dims) + 1e-6
+    return 1. - (intersect / union).sum() / intersect.nelement()
+
+
+class LaplacianLoss(nn.Module):
+    def __init__(self, vertex, faces, average=False):
+        super(LaplacianLoss, self).__init__()
+        self.nv = vertex.shape[0]
+        self.nf = faces.shape[0]
+        self.average = average
+        f = faces.detach().cpu().numpy().astype(np.int64)
+        # off-diagonal -1 for every (undirected) edge, diagonal = degree, rows divided by the diagonal
+        e = np.concatenate([f[:, [0, 1]], f[:, [1, 0]], f[:, [1, 2]], f[:, [2, 1]], f[:, [2, 0]], f[:, [0, 2]]], 0)
+        e = np.unique(e, axis=0)
+        deg = np.bincount(e[:, 0], minlength=self.nv).astype(np.float32)
+        rows = np.concatenate([e[:, 0], np.arange(self.nv)])
+        cols = np.concatenate([e[:, 1], np.arange(self.nv)])
+        with np.errstate(divide='ignore', invalid='ignore'):
+            vals = np.concatenate([-1.0 / deg[e[:, 0]], deg / deg]).astype(np.float32)
+        lap = torch.sparse_coo_tensor(np.stack([rows, cols]), vals, (self.nv, self.nv)).coalesce()
+        self.register_buffer('laplacian', lap)
+
+    def forward(self, x):
+        batch_size = x.shape[0]
+        lap = self.laplacian.to(x.device)
+        y = torch.stack([torch.sparse.mm(lap, x[b]) for b in range(batch_size)], 0)
+        dims = tuple(range(y.dim())[1:])
+        y = y.pow(2).sum(dims)
+        if self.average:
+            return y.sum() / batch_size
+        return y
+
+    execute = forward
+
+
+class FlattenLoss(nn.Module):
+    def __init__(self, faces, average=False):
+        super(FlattenLoss, self).__init__()
+        self.nf = faces.shape[0]
+        self.average = average
+        f = faces.detach().cpu().numpy().astype(np.int64)
+        opp = {}
+        for tri in f:
+            for a, b_, c in ((tri[0], tri[1], tri[2]), (tri[1], tri[2], tri[0]), (tri[2], tri[0], tri[1])):
+                opp.setdefault((min(a, b_), max(a, b_)), []).append(c)
+        edges = sorted(k for k, v in opp.items() if len(v) >= 2)   # the reference assumes a closed manifold
+        v0s = np.array([e[0] for e in edges], np.int64)
+        v1s = np.array([e[1] for e in edges], np.int64)
+        v2s = np.array([opp[e][0] for e in edges], np.int64)
+        v3s = np.array([opp[e][1] for e in edges], np.int64)
+        for name, v in (('v0s', v0s), ('v1s', v1s), ('v2s', v2s), ('v3s', v3s)):
+            self.register_buffer(name, torch.from_numpy(v))
+
+    def forward(self, vertices, eps=1e-6):
+        batch_size = vertices.shape[0]
+        v0s = vertices[:, self.v0s, :]
+        v1s = vertices[:, self.v1s, :]
+        v2s = vertices[:, self.v2s, :]
+        v3s = vertices[:, self.v3s, :]
+
+        def half(b):
+            a = v1s - v0s
+            al2 = a.pow(2).sum(-1)
+            bl2 = b.pow(2).sum(-1)
+            al1 = (al2 + eps).sqrt()
+            bl1 = (bl2 + eps).sqrt()
+            ab = (a * b).sum(-1)
+            cos = ab / (al1 * bl1 + eps)
+            sin = (1 - cos.pow(2) + eps).sqrt()
+            c = a * (ab / (al2 + eps))[..., None]
+            return b - c, bl1 * sin
+        cb1, cb1l1 = half(v2s - v0s)
+        cb2, cb2l1 = half(v3s - v0s)
+        cos = (cb1 * cb2).sum(-1) / (cb1l1 * cb2l1 + eps)
+        dims = tuple(range(cos.dim())[1:])
+        loss = (cos + 1).pow(2).sum(dims)
+        if self.average:
+            return loss.sum() / batch_size
+        return loss
+
+    execute = forward

@@ -1,0 +1,189 @@
+"""Build oracle/_ref/libjrender_ref.so from the reference's OWN kernel sources (TEST INFRASTRUCTURE).
+
+The reference keeps its CUDA C++ in Python string literals (`jt.code(cuda_header=..., cuda_src=...)`)
+and needs Jittor to JIT them; Jittor is not installable here.  This recipe reads the `.py` files
+where they lie under /root/reference (never copied into this repo), captures the `cuda_header`
+strings through a stub `jittor` module, writes them -- plus a small hand-written launcher that
+restates each op's `cuda_src` (memsets, grid/block sizes, argument order) -- to oracle/_ref/*.cu
+and compiles them for sm_100a with nvcc defaults (fmad on, as a stock nvcc/Jittor build would).
+
+    python -m oracle.build_ref
+
+Outputs only into oracle/_ref/ (git-ignored, but shipped to the GPU box by gpurun).  Used to
+(a) generate golden vectors from the real reference kernels on a B200 (oracle/make_ref_golden.py),
+(b) cross-check the product kernels on the GPU, (c) time "the reference kernels on the same B200".
+"""
+import os
+import subprocess
+import sys
+import types
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REFERENCE = "/root/reference"
+OUT = os.path.join(HERE, "_ref")
+LIB = os.path.join(OUT, "libjrender_ref.so")
+
+PREAMBLE = "#include <cstdio>\n#include <cstdint>\ntypedef float float32;\n"
+
+
+class _Dummy:
+    def __init__(self, shape=(1,), dtype="float32"):
+        self.shape, self.dtype = list(shape), dtype
+
+
+def _capture(path, func, nargs, extra=()):
+    """Import one reference .py with a stub jittor whose code() returns its kwargs."""
+    stub = types.ModuleType("jittor")
+    stub.code = lambda *a, **kw: kw
+    stub.empty = lambda *a, **kw: _Dummy()
+    saved = sys.modules.get("jittor")
+    sys.modules["jittor"] = stub
+    try:
+        src = open(path).read()
+        mod = types.ModuleType("ref_capture")
+        exec(compile(src, path, "exec"), mod.__dict__)
+        kw = getattr(mod, func)(*([_Dummy()] * nargs + list(extra)))
+    finally:
+        if saved is None:
+            sys.modules.pop("jittor", None)
+        else:
+            sys.modules["jittor"] = saved
+    return kw["cuda_header"]
+
+
+LAUNCH_FWD = r'''
+// ---- launcher: restates cuda_src of forward_soft_rasterize (cuda/soft_rasterize.py:459-521)
+extern "C" int ref_softras_forward(const float* faces, const float* textures, float* faces_info,
+        float* aggrs_info, float* soft_colors, int* faces_id_buffer, int batch_size, int num_faces,
+        int texture_size, int image_size, int max_faces_id, float near, float far, float eps,
+        float sigma_val, int func_id_dist, float dist_eps, float gamma_val, int func_id_rgb,
+        int func_id_alpha, int texture_sample_type, int double_side, cudaStream_t st) {
+    const size_t npix = (size_t)image_size * image_size;
+    cudaMemsetAsync(faces_info, 0, sizeof(float) * 27 * (size_t)batch_size * num_faces, st);
+    cudaMemsetAsync(aggrs_info, 0, sizeof(float) * 2 * npix * batch_size, st);
+    cudaMemsetAsync(soft_colors, 0, sizeof(float) * 4 * npix * batch_size, st);
+    cudaMemsetAsync(faces_id_buffer, -1, sizeof(int) * (size_t)max_faces_id * npix * batch_size, st);
+    const int texture_res = int(sqrt((double)texture_size));
+    const int threads = 512;
+    const dim3 blocks_1((batch_size * num_faces - 1) / threads + 1);
+    forward_soft_rasterize_inv_cuda_kernel<float32><<<blocks_1, threads, 0, st>>>(faces, faces_info, batch_size, num_faces, image_size);
+    const dim3 blocks_2((batch_size * image_size * image_size - 1) / threads + 1);
+    forward_soft_rasterize_cuda_kernel<float32><<<blocks_2, threads, 0, st>>>(faces, textures, faces_info, aggrs_info,
+        soft_colors, faces_id_buffer, batch_size, num_faces, image_size, max_faces_id, texture_size, texture_res,
+        near, far, eps, sigma_val, func_id_dist, dist_eps, gamma_val, func_id_rgb, func_id_alpha,
+        texture_sample_type, double_side);
+    return (int)cudaGetLastError();
+}
+'''
+
+LAUNCH_BWD = r'''
+// ---- launcher: restates cuda_src of backward_soft_rasterize (cuda/soft_rasterize.py:1363-1416)
+// faces_id_buffer is [B,H,W,K] here (the host transposes first, soft_rasterize.py:108).
+extern "C" int ref_softras_backward(const float* faces, const float* textures, const float* soft_colors,
+        const float* faces_info, const float* aggrs_info, const int* faces_id_buffer_bhwk,
+        float* grad_soft_colors, float* grad_faces, float* grad_textures, int batch_size, int num_faces,
+        int texture_size, int image_size, int max_faces_id, float near, float far, float eps,
+        float sigma_val, int func_id_dist, float dist_eps, float gamma_val, int func_id_rgb,
+        int func_id_alpha, int texture_sample_type, int double_side, cudaStream_t st) {
+    cudaMemsetAsync(grad_faces, 0, sizeof(float) * 9 * (size_t)batch_size * num_faces, st);
+    cudaMemsetAsync(grad_textures, 0, sizeof(float) * 3 * (size_t)texture_size * batch_size * num_faces, st);
+    const int texture_res = int(sqrt((double)texture_size));
+    const int threads = 512;
+    const dim3 blocks((batch_size * image_size * image_size - 1) / threads + 1);
+    backward_soft_rasterize_cuda_kernel<float32><<<blocks, threads, 0, st>>>(faces, faces_id_buffer_bhwk, textures,
+        soft_colors, faces_info, aggrs_info, grad_faces, grad_textures, grad_soft_colors, batch_size, num_faces,
+        image_size, max_faces_id, texture_size, texture_res, near, far, eps, sigma_val, func_id_dist, dist_eps,
+        gamma_val, func_id_rgb, func_id_alpha, texture_sample_type, (bool)double_side);
+    return (int)cudaGetLastError();
+}
+'''
+
+LAUNCH_C2F = r'''
+// ---- launcher: restates cuda_src of forward_soft_rasterize_coarse_to_fine
+// (cuda/soft_rasterize_coarse_to_fine.py:765-879), including its cudaMalloc / cudaMemset /
+// cudaDeviceSynchronize / cudaFree calls, which are part of the reference op.
+extern "C" int ref_softras_forward_c2f(const float* faces, const float* textures, float* faces_info,
+        float* aggrs_info, float* soft_colors, int* faces_id_buffer, int batch_size, int num_faces,
+        int texture_size, int image_size, int max_faces_id, float near, float far, float eps,
+        float sigma_val, int func_id_dist, float dist_eps, float gamma_val, int func_id_rgb,
+        int func_id_alpha, int texture_sample_type, int double_side, int bin_size, int max_elems_per_bin) {
+    const size_t npix = (size_t)image_size * image_size;
+    cudaMemsetAsync(faces_info, 0, sizeof(float) * 27 * (size_t)batch_size * num_faces);
+    cudaMemsetAsync(aggrs_info, 0, sizeof(float) * 2 * npix * batch_size);
+    cudaMemsetAsync(soft_colors, 0, sizeof(float) * 4 * npix * batch_size);
+    cudaMemsetAsync(faces_id_buffer, -1, sizeof(int) * (size_t)max_faces_id * npix * batch_size);
+    const int texture_res = int(sqrt((double)texture_size));
+    const size_t threads_1 = 512;
+    const size_t blocks_1 = ((batch_size * num_faces - 1) / threads_1 + 1);
+    float* bboxes; bool* should_skip;
+    cudaMalloc((void**)&bboxes, (size_t)batch_size * num_faces * 4 * sizeof(float));
+    cudaMalloc((void**)&should_skip, (size_t)batch_size * num_faces * sizeof(bool));
+    forward_soft_rasterize_inv_cuda_kernel<float32><<<blocks_1, threads_1>>>(faces, faces_info, batch_size, num_faces, image_size);
+    TriangleBoundingBoxKernel<<<128, 256>>>(faces, batch_size * num_faces, 0.01, bboxes, should_skip);
+    const int num_bins_edge = 1 + (image_size - 1) / bin_size;
+    int* elems_per_bin; int* bin_elems;
+    size_t size2 = (size_t)batch_size * num_bins_edge * num_bins_edge * sizeof(int);
+    cudaMalloc((void**)&elems_per_bin, size2);
+    cudaMemset(elems_per_bin, 0, size2);
+    size_t size1 = (size_t)batch_size * num_bins_edge * num_bins_edge * max_elems_per_bin * sizeof(int);
+    cudaMalloc((void**)&bin_elems, size1);
+    cudaMemset(bin_elems, -1, size1);
+    cudaDeviceSynchronize();
+    const int chunk_size = 512;
+    const int shared_size = num_bins_edge * num_bins_edge * chunk_size / 8;
+    RasterizeCoarseCudaKernel<<<64, 512, shared_size>>>(bboxes, should_skip, batch_size, num_faces, image_size,
+        bin_size, chunk_size, max_elems_per_bin, elems_per_bin, bin_elems);
+    cudaDeviceSynchronize();
+    cudaFree(bboxes);
+    cudaFree(should_skip);
+    const size_t threads_4 = 128;
+    const size_t blocks_4 = (((size_t)batch_size * bin_size * bin_size * num_bins_edge * num_bins_edge - 1) / threads_4 + 1);
+    forward_soft_rasterize_cuda_kernel<float32><<<blocks_4, threads_4>>>(faces, textures, faces_info, bin_elems,
+        elems_per_bin, aggrs_info, soft_colors, faces_id_buffer, num_bins_edge, max_elems_per_bin, bin_size,
+        batch_size, num_faces, image_size, max_faces_id, texture_size, texture_res, near, far, eps, sigma_val,
+        func_id_dist, dist_eps, gamma_val, func_id_rgb, func_id_alpha, texture_sample_type, double_side);
+    cudaError_t err = cudaGetLastError();
+    cudaDeviceSynchronize();
+    cudaFree(elems_per_bin);
+    cudaFree(bin_elems);
+    return (int)err;
+}
+'''
+
+
+def generate():
+    os.makedirs(OUT, exist_ok=True)
+    base = os.path.join(REFERENCE, "jrender/renderer/dr/softras/cuda")
+    files = []
+    hdr = _capture(os.path.join(base, "soft_rasterize.py"), "forward_soft_rasterize", 6, extra=[64, 1, 100, 1e-3, 1e-5, 2, 9.21, 1e-4, 1, 2, 0, 1])
+    files.append(("ref_softras_fwd.cu", PREAMBLE + hdr + LAUNCH_FWD))
+    hdr = _capture(os.path.join(base, "soft_rasterize.py"), "backward_soft_rasterize", 9, extra=[64, 1, 100, 1e-3, 1e-5, 2, 9.21, 1e-4, 1, 2, 0, 1])
+    files.append(("ref_softras_bwd.cu", PREAMBLE + hdr + LAUNCH_BWD))
+    hdr = _capture(os.path.join(base, "soft_rasterize_coarse_to_fine.py"), "forward_soft_rasterize_coarse_to_fine", 6,
+                   extra=[64, 1, 100, 1e-3, 1e-5, 2, 9.21, 1e-4, 1, 2, 0, 1, 64, 100])
+    files.append(("ref_softras_c2f.cu", PREAMBLE + hdr + LAUNCH_C2F))
+    paths = []
+    for name, text in files:
+        p = os.path.join(OUT, name)
+        if not os.path.exists(p) or open(p).read() != text:
+            open(p, "w").write(text)
+        paths.append(p)
+    return paths
+
+
+def build(force=False, verbose=False):
+    if not os.path.isdir(REFERENCE):
+        raise RuntimeError("%s not present (GPU box?): use the prebuilt oracle/_ref" % REFERENCE)
+    paths = generate()
+    if not force and os.path.exists(LIB) and all(os.path.getmtime(p) <= os.path.getmtime(LIB) for p in paths + [os.path.abspath(__file__)]):
+        return LIB
+    cmd = ["/usr/local/cuda/bin/nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+           "-w", "-Xcompiler", "-fPIC", "-shared", "-o", LIB] + paths
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.run(cmd, check=True)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

@@ -1,0 +1,79 @@
+"""Generate golden vectors by running the reference's OWN kernels on a GPU (TEST INFRASTRUCTURE).
+
+    gpurun -- python -m oracle.make_ref_golden        # writes gpurun_out/golden/ref_gpu_*.npz
+    cp gpurun_out/golden/*.npz tests/golden/          # commit them
+
+Needs oracle/_ref/libjrender_ref.so (python -m oracle.build_ref, built where /root/reference
+exists; it travels to the GPU box).  The reference ships no tests or golden vectors of its own
+(SURVEY.md F2), so these files are what pins oracle/softras_oracle.c to the real reference:
+tests/test_golden.py compares the CPU oracle to them on every run.
+
+Each .npz holds the inputs (face_vertices, textures, upstream gradient), the parameters, and
+the reference kernels' outputs (soft_colors, aggrs_info, faces_id_buffer, faces_info,
+grad_faces, grad_textures), plus the nvcc flags and GPU the reference was run with.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from jrender_b200 import workloads as wl  # noqa: E402
+from oracle import ref_gpu, softras as osr  # noqa: E402
+
+
+def fixtures():
+    fv, tex = wl.make_scene(280, batch=1)
+    yield "sphere280_default_64", fv, tex, dict(image_size=64)
+    yield "sphere280_demo2_64", fv, tex, dict(image_size=64, sigma_val=1e-4, aggr_func_rgb="hard")
+    yield "sphere280_bary_sum_48", fv, tex, dict(image_size=48, dist_func="barycentric", aggr_func_alpha="sum", sigma_val=1e-4)
+    yield "sphere280_hard_hard_48", fv, tex, dict(image_size=48, dist_func="hard", aggr_func_rgb="hard", aggr_func_alpha="hard")
+    fvv, texv = wl.make_scene(280, batch=1, texture_type="vertex")
+    yield "sphere280_vertex_48", fvv, texv, dict(image_size=48, texture_type="vertex")
+    fv5, tex5 = wl.make_scene(280, batch=1, texture_res=3)
+    yield "sphere280_T9_hardrgb_48", fv5, tex5, dict(image_size=48, aggr_func_rgb="hard")
+    fvr, texr = wl.random_triangles(2, 120, seed=11)
+    yield "random120_K4_40", fvr, texr, dict(image_size=40, max_faces_per_pixel_for_grad=4, sigma_val=1e-4)
+    fv3, tex3 = wl.make_scene(3280, batch=1)
+    yield "sphere3280_default_64", fv3, tex3, dict(image_size=64)
+
+
+def main():
+    import torch
+    out_dir = os.path.join("gpurun_out", "golden")
+    os.makedirs(out_dir, exist_ok=True)
+    report = []
+    for name, fv, tex, kw in fixtures():
+        P = osr.Params(**kw)
+        H = P["image_size"]
+        g = np.random.default_rng(2).uniform(-1, 1, (fv.shape[0], 4, H, H)).astype(np.float32)
+        ref = ref_gpu.run(fv, tex, P, grad=g)
+        cpu = osr.forward(fv, tex, P)
+        cpu["grad_faces"], cpu["grad_textures"] = osr.backward(fv, tex, cpu, g, P)
+        ids_ref = ref["faces_id_buffer"]
+        assert ids_ref.max() < 32767
+        np.savez_compressed(
+            os.path.join(out_dir, "ref_gpu_%s.npz" % name),
+            face_vertices=fv, textures=tex, grad_soft_colors=g,
+            params=json.dumps(dict(P)), soft_colors=ref["soft_colors"], aggrs_info=ref["aggrs_info"],
+            faces_id_buffer=ids_ref.astype(np.int16), faces_info=ref["faces_info"],
+            grad_faces=ref["grad_faces"], grad_textures=ref["grad_textures"],
+            provenance=json.dumps(dict(gpu=torch.cuda.get_device_name(0), nvcc="12.9 -O3 -gencode arch=compute_100a,code=sm_100a (fmad default on)",
+                                       source="jrender/renderer/dr/softras/cuda/soft_rasterize.py kernels via oracle/build_ref.py")))
+        r = dict(name=name)
+        r["ids_equal_px_frac"] = float((np.sort(ids_ref, 1) == np.sort(cpu["faces_id_buffer"], 1)).all(1).mean())
+        r["ids_exact"] = bool(np.array_equal(ids_ref, cpu["faces_id_buffer"]))
+        for k in ("soft_colors", "aggrs_info", "faces_info", "grad_faces", "grad_textures"):
+            a, b = ref[k].astype(np.float64), cpu[k].astype(np.float64)
+            m = ~(np.isnan(a) | np.isnan(b))
+            d = np.abs(a - b)[m]
+            r[k] = dict(max_abs=float(d.max()) if d.size else 0.0, mean_abs=float(d.mean()) if d.size else 0.0,
+                        max_ref=float(np.abs(a[m]).max()) if d.size else 0.0, nan_ref=int(np.isnan(a).sum()), nan_cpu=int(np.isnan(b).sum()))
+        report.append(r)
+        print(json.dumps(r), flush=True)
+    json.dump(report, open(os.path.join(out_dir, "report.json"), "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
