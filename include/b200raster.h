@@ -102,10 +102,16 @@ B200R_API int b200r_softras_backward(const float* face_vertices, const float* te
  * (bench.py reports the delta over the timed region as "gpu_launches"). */
 B200R_API unsigned long long b200r_launch_count(void);
 
+/* Tuning knobs (process-wide; results are identical for every setting, only speed changes):
+ *   "softras_fwd_variant"    0 = warp-uniform face loop, 1 = per-lane face lists (default)
+ *   "softras_fwd_persistent" 0 = one CTA per tile, 1 = persistent grid + tile queue (default) */
+B200R_API int b200r_set_option(const char* name, int value);
+
 /* Per-kernel device timing (CUDA events recorded on the launch stream around every kernel
  * this library launches).  Off by default.  bench.py uses it for the roofline of the
  * dominant kernel; b200r_profile_read synchronises the outstanding events. */
-enum { B200R_K_FACE_SETUP = 0, B200R_K_COARSE_BIN = 1, B200R_K_SOFTRAS_FWD = 2, B200R_K_SOFTRAS_BWD = 3 };
+enum { B200R_K_FACE_SETUP = 0, B200R_K_COARSE_BIN = 1, B200R_K_SOFTRAS_FWD = 2, B200R_K_SOFTRAS_BWD = 3,
+       B200R_K_TILE_ORDER = 4 };
 B200R_API void b200r_profile_enable(int on);
 B200R_API void b200r_profile_reset(void);
 B200R_API int b200r_profile_read(int kernel, double* total_ms, long long* launches);

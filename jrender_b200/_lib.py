@@ -51,6 +51,8 @@ def lib():
     L.b200r_profile_read.argtypes = [_I, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
     L.b200r_debug_exact_math.restype = _I
     L.b200r_debug_exact_math.argtypes = [_P, _P, _I, _P, _P]
+    L.b200r_set_option.restype = _I
+    L.b200r_set_option.argtypes = [C.c_char_p, _I]
     _lib = L
     return L
 
@@ -58,3 +60,7 @@ def lib():
 def check(rc, what):
     if rc != 0:
         raise B200RasterError("%s failed (rc=%d): %s" % (what, rc, lib().b200r_last_error().decode()))
+
+
+def set_option(name, value):
+    check(lib().b200r_set_option(name.encode(), int(value)), "b200r_set_option(%s)" % name)

@@ -44,6 +44,7 @@ struct SoftRasParams {
     int ntx;        // fine tiles per image side
     int coarse_px;  // coarse bin edge in pixels (multiple of B200R_TILE)
     int ncs;        // coarse bins per image side
+    int tile_stride;  // persistent scheduler: odd stride coprime with the tile count
 };
 
 // Workspace carve-up (all offsets 256-byte aligned).
@@ -52,6 +53,9 @@ struct SoftRasWorkspace {
     uint2* rects;        // [B*nf]  (rect_x, rect_r) copy for the binning scans
     int* coarse_cnt;     // [B*ncs*ncs]
     int* coarse_ids;     // [B*ncs*ncs][nf]
+    int* counters;       // [256] scheduler state, zeroed per launch: [0] queue head, [64..127] cost histogram, [128..191] scatter cursors
+    int* tile_cost;      // [B*ntx*ntx] (pixel, face) pairs per fine tile
+    int* tile_order;     // [B*ntx*ntx] tile ids, most expensive first
     size_t bytes;
 };
 
@@ -80,6 +84,12 @@ static inline SoftRasWorkspace b200r_carve(void* base, int B, int nf, int image_
     off += b200r_align256((size_t)B * ncs * ncs * sizeof(int));
     w.coarse_ids = (int*)(p + off);
     off += b200r_align256((size_t)B * ncs * ncs * (size_t)nf * sizeof(int));
+    w.counters = (int*)(p + off);
+    off += b200r_align256(256 * sizeof(int));
+    w.tile_cost = (int*)(p + off);
+    off += b200r_align256((size_t)B * ntx * ntx * sizeof(int));
+    w.tile_order = (int*)(p + off);
+    off += b200r_align256((size_t)B * ntx * ntx * sizeof(int));
     w.bytes = off;
     return w;
 }

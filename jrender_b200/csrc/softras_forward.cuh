@@ -2,13 +2,23 @@
 // forward_soft_rasterize_cuda_kernel, cuda/soft_rasterize.py:243-456 and
 // cuda/soft_rasterize_coarse_to_fine.py:513-761).
 //
-// One CTA = one 16x16 pixel tile of one batch element, one thread = one pixel, warp w
-// owns an 8x4 sub-rectangle.  The CTA walks its coarse bin's face list (ascending face id),
-// keeps the faces whose check_border rectangle touches the tile (ordered ballot
-// compaction), stages their 160-byte records in shared memory in chunks, and every warp
-// narrows the chunk to the faces touching its 8x4 footprint before the per-pixel loop.
-// Faces are therefore visited per pixel in ascending id exactly like the reference's
+// One CTA processes 16x16 pixel tiles, one thread = one pixel, warp w owns an 8x4
+// sub-rectangle.  Per tile the CTA walks its coarse bin's face list (ascending face id),
+// keeps the faces whose check_border rectangle touches the tile (ordered ballot compaction),
+// stages their 160-byte records in shared memory in rounds of <=128, and every warp narrows
+// the round to the faces touching its 8x4 footprint.  Then
+//   VARIANT 0: the warp walks that list in lock-step; a lane works when its pixel lies in
+//              the face's rectangle (~50 % lane utilisation on small triangles);
+//   VARIANT 1: every lane first compacts ITS OWN list of faces (indices in shared memory)
+//              and the lanes then walk their private lists in lock-step, so all lanes work
+//              until the shortest lists run out.
+// Either way each pixel visits its faces in ascending id exactly like the reference's
 // `for (fn = 0; fn < nf; fn++)` (:311), minus the faces check_border would skip.
+//
+// Scheduling: `tile_counter == nullptr` -> one CTA per tile (blockIdx); otherwise a
+// persistent grid pulls tiles from an atomic queue ordered by descending cost (number of
+// (pixel, face) pairs per tile, computed by k_coarse_bin and bucket-sorted by k_tile_order):
+// tiles at poles / silhouettes of a mesh can cost 10x the mean and must start first.
 #pragma once
 #include "softras_math.cuh"
 #include "softras_setup.cuh"
@@ -17,260 +27,323 @@ namespace b200r {
 
 #define B200R_CHUNK 128  // staged faces per round (index fits uint8)
 
+// shared-memory copy of a record, padded to 176 B: consecutive records then start 11
+// 16-byte bank groups apart (11 is odd), so divergent per-lane record reads spread over
+// the banks instead of hitting 4 of 8 groups as a 160-byte stride would.
+struct __align__(16) FaceRecS {
+    FaceRec r;
+    uint4 pad;
+};
+
 struct FwdSmem {
-    FaceRec rec[B200R_CHUNK];            // 20 KB (reused as the output staging area)
+    FaceRecS rec[B200R_CHUNK];           // 22 KB (reused as the output staging area)
     int ids[B200R_CHUNK + 256];          // pending tile-face ids, ascending
     unsigned char wlist[8][B200R_CHUNK]; // per-warp sub-list (indices into rec[])
     int s_warp[8];
+    int s_tile;
 };
 
+struct PixState {
+    float sc0, sc1, sc2, alpha, softmax_sum, softmax_max, depth_min, q_max_z;
+    int face_index_min, q_size, q_max_id;
+};
+
+// The reference's per-face loop body (:318-420) for one (pixel, face) pair whose pixel is
+// inside the face's check_border rectangle.
 template <int DIST, int RGB>
+__device__ __forceinline__ void shade_face(const FaceRec* rec, PixState& st, const SoftRasParams& P, const DivConst& dc,
+                                           float xp, float yp, float threshold, float* s_qz, int* s_qid, int tid,
+                                           const float* __restrict__ btex) {
+    float w[3];
+    barycentric_coordinate(w, xp, yp, rec->inv);
+
+    float soft_fragment;
+    if (DIST == 0) {
+        if (!check_pixel_inside(w)) return;  // :332-333
+        soft_fragment = 1.f;
+    } else if (DIST == 1) {
+        const float dis = barycentric_p2f_distance(w);
+        if (-dis >= threshold) return;  // :337
+        soft_fragment = sigmoid_from_negarg(dc.by_sigma(-dis));
+    } else {
+        float dis_x, dis_y, t[3];
+        const float sign = euclidean_p2f_distance(dis_x, dis_y, t, w, rec, xp, yp);
+        const float dis = dis_x * dis_x + dis_y * dis_y;
+        if (sign < 0.f && dis >= threshold) return;  // :343
+        soft_fragment = sigmoid_from_negarg(dc.by_sigma(-sign * dis));
+    }
+
+    // alpha aggregation, before any z test (:349-358, Q2)
+    if (P.alpha_func == 0) {
+        if (soft_fragment > 0.5f) st.alpha = 1.f;
+    } else if (P.alpha_func == 1) {
+        st.alpha += soft_fragment;
+    } else {
+        st.alpha = alpha_prod(st.alpha, soft_fragment);
+    }
+
+    float wc[3] = {w[0], w[1], w[2]};
+    barycentric_clip(wc);
+    const float zp = interp_z(wc, rec);            // :364
+    if (zp < P.near_ || zp > P.far_) return;       // :365
+
+    const int fn = (int)rec->face_id;
+    const int K = P.K;
+    // top-K by z, "replace the current max" policy (:367-385)
+    if (st.q_size < K) {
+        s_qz[st.q_size * B200R_TILE_THREADS + tid] = zp;
+        s_qid[st.q_size * B200R_TILE_THREADS + tid] = fn;
+        if (zp > st.q_max_z) { st.q_max_z = zp; st.q_max_id = st.q_size; }
+        st.q_size++;
+    } else if (zp < st.q_max_z) {
+        s_qz[st.q_max_id * B200R_TILE_THREADS + tid] = zp;
+        s_qid[st.q_max_id * B200R_TILE_THREADS + tid] = fn;
+        st.q_max_z = -1.f;
+        for (int k = 0; k < st.q_size; k++) {
+            const float z = s_qz[k * B200R_TILE_THREADS + tid];
+            if (z > st.q_max_z) { st.q_max_z = z; st.q_max_id = k; }
+        }
+    }
+
+    const bool front = (rec->flags & 8u) != 0;
+    if (RGB == 0) {  // :390-397
+        if (zp < st.depth_min && check_pixel_inside(w) && (P.double_side || front)) {
+            st.depth_min = zp;
+            st.face_index_min = fn;
+            float col[3];
+            sample_texture_fwd(col, btex + (size_t)fn * P.T * 3, wc, P.R, P.tex_type, rec, zp);
+            st.sc0 = col[0]; st.sc1 = col[1]; st.sc2 = col[2];
+        }
+    } else if (RGB == 1) {  // :399-419
+        if (front || P.double_side) {
+            const float zp_norm = dc.by_span(P.far_ - zp);
+            float exp_delta_zp = 1.f;
+            if (zp_norm > st.softmax_max) {
+                exp_delta_zp = expf(dc.by_gamma(st.softmax_max - zp_norm));
+                st.softmax_max = zp_norm;
+            }
+            const float exp_z = expf(dc.by_gamma(zp_norm - st.softmax_max));
+            st.softmax_sum = exp_delta_zp * st.softmax_sum + exp_z * soft_fragment;
+            float col[3];
+            sample_texture_fwd(col, btex + (size_t)fn * P.T * 3, wc, P.R, P.tex_type, rec, zp);
+            st.sc0 = exp_delta_zp * st.sc0 + exp_z * soft_fragment * col[0];
+            st.sc1 = exp_delta_zp * st.sc1 + exp_z * soft_fragment * col[1];
+            st.sc2 = exp_delta_zp * st.sc2 + exp_z * soft_fragment * col[2];
+        }
+    }
+}
+
+__device__ __forceinline__ bool pixel_in_rect(const FaceRec* rec, int px, int row) {
+    const uint32_t rx = rec->rect_x, rr = rec->rect_r;
+    const uint32_t x0 = rx & 0xffffu, r0 = rr & 0xffffu;
+    return (uint32_t)(px - (int)x0) <= (rx >> 16) - x0 && (uint32_t)(row - (int)r0) <= (rr >> 16) - r0;
+}
+
+template <int DIST, int RGB, int VARIANT>
 __global__ void __launch_bounds__(B200R_TILE_THREADS, 2)
 k_softras_forward(const SoftRasParams P, const FaceRec* __restrict__ recs, const uint2* __restrict__ rects,
                   const int* __restrict__ coarse_cnt, const int* __restrict__ coarse_ids,
                   const float* __restrict__ textures, float* __restrict__ soft_colors,
-                  float* __restrict__ aggrs_info, int* __restrict__ ids_out) {
+                  float* __restrict__ aggrs_info, int* __restrict__ ids_out, int* tile_counter,
+                  const int* __restrict__ tile_order) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FwdSmem& S = *reinterpret_cast<FwdSmem*>(smem_raw);
     float* s_qz = reinterpret_cast<float*>(smem_raw + sizeof(FwdSmem));  // [K][256]
     int* s_qid = reinterpret_cast<int*>(s_qz + (size_t)P.K * B200R_TILE_THREADS);
+    unsigned char* s_plist = reinterpret_cast<unsigned char*>(s_qid + (size_t)P.K * B200R_TILE_THREADS);  // VARIANT 1: [CHUNK][256]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int is = P.is, nf = P.nf, K = P.K;
-    const int b = blockIdx.y;
-    const int tx = blockIdx.x % P.ntx, ty = blockIdx.x / P.ntx;
+    const int tiles_per_image = P.ntx * P.ntx;
+    const int total_tiles = tiles_per_image * P.B;
     const int lx = (warp & 1) * 8 + (lane & 7), ly = (warp >> 1) * 4 + (lane >> 3);
-    const int px = tx * B200R_TILE + lx, row = ty * B200R_TILE + ly;
-    const float xp = b200r_pix_coord(px, is);
-    const float yp = b200r_pix_coord(is - 1 - row, is);
-
-    // tile / warp footprints (inclusive pixel ranges)
-    const int tx0 = tx * B200R_TILE, tx1 = tx0 + B200R_TILE - 1;
-    const int tr0 = ty * B200R_TILE, tr1 = tr0 + B200R_TILE - 1;
-    const int wx0 = tx0 + (warp & 1) * 8, wx1 = wx0 + 7;
-    const int wr0 = tr0 + (warp >> 1) * 4, wr1 = wr0 + 3;
-
     const float threshold = P.dist_eps * P.sigma;  // :289
+    const size_t npix = (size_t)is * is;
     DivConst dc;
     dc.init(P);
+    const float softmax_sum0 = expf(P.eps / P.gamma);
 
-    // ---- per-pixel state, initialised as :291-309 (background buffer is all zero, Q1)
-    float softmax_sum = expf(P.eps / P.gamma);
-    float softmax_max = P.eps;
-    float sc0, sc1, sc2;
-    if (RGB == 0) { sc0 = sc1 = sc2 = 0.f; }
-    else if (RGB == 1) { sc0 = sc1 = sc2 = 0.f * softmax_sum; }
-    else { sc0 = sc1 = sc2 = 1.f; }
-    float alpha = (P.alpha_func == 2) ? 1.f : 0.f;
-    float depth_min = 10000000.f;
-    int face_index_min = -1;
-    int q_size = 0;
-    float q_max_z = -1.f;
-    int q_max_id = -1;
-
-    const int cbin = (tr0 / P.coarse_px) * P.ncs + (tx0 / P.coarse_px);
-    const int n_coarse = coarse_cnt[b * P.ncs * P.ncs + cbin];
-    const int* clist = coarse_ids + ((size_t)b * P.ncs * P.ncs + cbin) * nf;
-    const uint2* brects = rects + (size_t)b * nf;
-    const FaceRec* brecs = recs + (size_t)b * nf;
-    const float* btex = textures + (size_t)b * nf * P.T * 3;
-
-    int n_pending = 0;  // uniform across the CTA
-    for (int base = 0; base < n_coarse || n_pending > 0; base += B200R_TILE_THREADS) {
-        // ---- fine filter: next 256 coarse entries -> S.ids (ordered)
-        if (base < n_coarse) {
-            const int i = base + tid;
-            int id = -1;
-            bool pass = false;
-            if (i < n_coarse) {
-                id = __ldg(clist + i);
-                pass = rect_overlaps(__ldg(brects + id), tx0, tx1, tr0, tr1);
-            }
-            int total;
-            const int off = n_pending + block_excl_scan_256(pass ? 1 : 0, S.s_warp, total);
-            if (pass) S.ids[off] = id;
-            n_pending += total;
-        }
-        const bool last = base + B200R_TILE_THREADS >= n_coarse;
-        if (n_pending < B200R_CHUNK && !last) continue;
-
-        while (n_pending >= B200R_CHUNK || (last && n_pending > 0)) {
-            const int m = min(n_pending, B200R_CHUNK);
-            __syncthreads();  // S.ids complete; previous round's readers of S.rec done
-            // ---- stage m records: 10 x uint4 per face, coalesced
-            for (int j = tid; j < m * B200R_REC_UINT4; j += B200R_TILE_THREADS) {
-                const int f = j / B200R_REC_UINT4, q = j - f * B200R_REC_UINT4;
-                reinterpret_cast<uint4*>(&S.rec[f])[q] =
-                    __ldg(reinterpret_cast<const uint4*>(brecs + S.ids[f]) + q);
-            }
+    for (int titer = 0;; titer++) {
+        // ---- which tile
+        int t;
+        if (tile_counter == nullptr) {
+            if (titer > 0) break;
+            t = blockIdx.y * tiles_per_image + blockIdx.x;
+        } else {
+            __syncthreads();  // previous tile fully written, S.s_tile free
+            if (tid == 0) S.s_tile = atomicAdd(tile_counter, 1);
             __syncthreads();
-            // ---- shift the not-yet-staged ids to the front (through registers)
-            const int rest = n_pending - m;
-            int keep0 = 0, keep1 = 0;
-            if (tid < rest) keep0 = S.ids[m + tid];
-            if (tid + 256 < rest) keep1 = S.ids[m + tid + 256];
-            // ---- warp sub-list
-            int wcnt = 0;
-            for (int j0 = 0; j0 < m; j0 += 32) {
-                const int j = j0 + lane;
+            const int q = S.s_tile;
+            if (q >= total_tiles) break;
+            t = __ldg(tile_order + q);  // most expensive tiles first (k_tile_order)
+        }
+        const int b = t / tiles_per_image;
+        const int tt = t - b * tiles_per_image;
+        const int tx = tt % P.ntx, ty = tt / P.ntx;
+        const int px = tx * B200R_TILE + lx, row = ty * B200R_TILE + ly;
+        const float xp = b200r_pix_coord(px, is);
+        const float yp = b200r_pix_coord(is - 1 - row, is);
+
+        // tile / warp footprints (inclusive pixel ranges)
+        const int tx0 = tx * B200R_TILE, tx1 = tx0 + B200R_TILE - 1;
+        const int tr0 = ty * B200R_TILE, tr1 = tr0 + B200R_TILE - 1;
+        const int wx0 = tx0 + (warp & 1) * 8, wx1 = wx0 + 7;
+        const int wr0 = tr0 + (warp >> 1) * 4, wr1 = wr0 + 3;
+
+        // ---- per-pixel state, initialised as :291-309 (background buffer is all zero, Q1)
+        PixState st;
+        st.softmax_sum = softmax_sum0;
+        st.softmax_max = P.eps;
+        if (RGB == 0) { st.sc0 = st.sc1 = st.sc2 = 0.f; }
+        else if (RGB == 1) { st.sc0 = st.sc1 = st.sc2 = 0.f * softmax_sum0; }
+        else { st.sc0 = st.sc1 = st.sc2 = 1.f; }
+        st.alpha = (P.alpha_func == 2) ? 1.f : 0.f;
+        st.depth_min = 10000000.f;
+        st.face_index_min = -1;
+        st.q_size = 0;
+        st.q_max_z = -1.f;
+        st.q_max_id = -1;
+
+        const int cbin = (tr0 / P.coarse_px) * P.ncs + (tx0 / P.coarse_px);
+        const int n_coarse = coarse_cnt[b * P.ncs * P.ncs + cbin];
+        const int* clist = coarse_ids + ((size_t)b * P.ncs * P.ncs + cbin) * nf;
+        const uint2* brects = rects + (size_t)b * nf;
+        const FaceRec* brecs = recs + (size_t)b * nf;
+        const float* btex = textures + (size_t)b * nf * P.T * 3;
+
+        int n_pending = 0;  // uniform across the CTA
+        for (int base = 0; base < n_coarse; base += B200R_TILE_THREADS) {
+            // ---- fine filter: next 256 coarse entries -> S.ids (ordered)
+            {
+                const int i = base + tid;
+                int id = -1;
                 bool pass = false;
-                if (j < m) pass = rect_overlaps(make_uint2(S.rec[j].rect_x, S.rec[j].rect_r), wx0, wx1, wr0, wr1);
-                const unsigned bal = __ballot_sync(0xffffffffu, pass);
-                if (pass) S.wlist[warp][wcnt + __popc(bal & ((1u << lane) - 1u))] = (unsigned char)j;
-                wcnt += __popc(bal);
+                if (i < n_coarse) {
+                    id = __ldg(clist + i);
+                    pass = rect_overlaps(__ldg(brects + id), tx0, tx1, tr0, tr1);
+                }
+                int total;
+                const int off = n_pending + block_excl_scan_256(pass ? 1 : 0, S.s_warp, total);
+                if (pass) S.ids[off] = id;
+                n_pending += total;
             }
-            __syncwarp();
+            const bool last = base + B200R_TILE_THREADS >= n_coarse;
+            if (n_pending < B200R_CHUNK && !last) continue;
 
-            // ---- per-pixel loop over the warp's faces (ascending id)
-            for (int it = 0; it < wcnt; it++) {
-                const FaceRec* rec = &S.rec[S.wlist[warp][it]];
-                {   // check_border as the exact pixel rectangle
-                    const uint32_t rx = rec->rect_x, rr = rec->rect_r;
-                    const uint32_t x0 = rx & 0xffffu, r0 = rr & 0xffffu;
-                    if ((uint32_t)(px - (int)x0) > (rx >> 16) - x0) continue;
-                    if ((uint32_t)(row - (int)r0) > (rr >> 16) - r0) continue;
+            while (n_pending >= B200R_CHUNK || (last && n_pending > 0)) {
+                const int m = min(n_pending, B200R_CHUNK);
+                __syncthreads();  // S.ids complete; previous round's readers of S.rec done
+                // ---- stage m records: 10 x uint4 per face, coalesced
+                for (int j = tid; j < m * B200R_REC_UINT4; j += B200R_TILE_THREADS) {
+                    const int f = j / B200R_REC_UINT4, q = j - f * B200R_REC_UINT4;
+                    reinterpret_cast<uint4*>(&S.rec[f])[q] =
+                        __ldg(reinterpret_cast<const uint4*>(brecs + S.ids[f]) + q);
                 }
-                float w[3];
-                barycentric_coordinate(w, xp, yp, rec->inv);
-
-                float soft_fragment;
-                if (DIST == 0) {
-                    if (!check_pixel_inside(w)) continue;  // :332-333
-                    soft_fragment = 1.f;
-                } else if (DIST == 1) {
-                    const float dis = barycentric_p2f_distance(w);
-                    if (-dis >= threshold) continue;  // :337
-                    soft_fragment = sigmoid_from_negarg(dc.by_sigma(-dis));
-                } else {
-                    float dis_x, dis_y, t[3];
-                    const float sign = euclidean_p2f_distance(dis_x, dis_y, t, w, rec, xp, yp);
-                    const float dis = dis_x * dis_x + dis_y * dis_y;
-                    if (sign < 0.f && dis >= threshold) continue;  // :343
-                    soft_fragment = sigmoid_from_negarg(dc.by_sigma(-sign * dis));
+                __syncthreads();
+                // ---- shift the not-yet-staged ids to the front (through registers)
+                const int rest = n_pending - m;
+                int keep0 = 0;
+                if (tid < rest) keep0 = S.ids[m + tid];  // rest <= 255
+                // ---- warp sub-list
+                int wcnt = 0;
+                for (int j0 = 0; j0 < m; j0 += 32) {
+                    const int j = j0 + lane;
+                    bool pass = false;
+                    if (j < m) pass = rect_overlaps(make_uint2(S.rec[j].r.rect_x, S.rec[j].r.rect_r), wx0, wx1, wr0, wr1);
+                    const unsigned bal = __ballot_sync(0xffffffffu, pass);
+                    if (pass) S.wlist[warp][wcnt + __popc(bal & ((1u << lane) - 1u))] = (unsigned char)j;
+                    wcnt += __popc(bal);
                 }
+                __syncwarp();
 
-                // alpha aggregation, before any z test (:349-358, Q2)
-                if (P.alpha_func == 0) {
-                    if (soft_fragment > 0.5f) alpha = 1.f;
-                } else if (P.alpha_func == 1) {
-                    alpha += soft_fragment;
-                } else {
-                    alpha = alpha_prod(alpha, soft_fragment);
-                }
-
-                float wc[3] = {w[0], w[1], w[2]};
-                barycentric_clip(wc);
-                const float zp = interp_z(wc, rec);  // :364
-                if (zp < P.near_ || zp > P.far_) continue;                               // :365
-
-                const int fn = (int)rec->face_id;
-                // top-K by z, "replace the current max" policy (:367-385)
-                if (q_size < K) {
-                    s_qz[q_size * B200R_TILE_THREADS + tid] = zp;
-                    s_qid[q_size * B200R_TILE_THREADS + tid] = fn;
-                    if (zp > q_max_z) { q_max_z = zp; q_max_id = q_size; }
-                    q_size++;
-                } else if (zp < q_max_z) {
-                    s_qz[q_max_id * B200R_TILE_THREADS + tid] = zp;
-                    s_qid[q_max_id * B200R_TILE_THREADS + tid] = fn;
-                    q_max_z = -1.f;
-                    for (int k = 0; k < q_size; k++) {
-                        const float z = s_qz[k * B200R_TILE_THREADS + tid];
-                        if (z > q_max_z) { q_max_z = z; q_max_id = k; }
+                if (VARIANT == 0) {
+                    // ---- warp walks its list in lock-step
+                    for (int it = 0; it < wcnt; it++) {
+                        const FaceRec* rec = &S.rec[S.wlist[warp][it]].r;
+                        if (!pixel_in_rect(rec, px, row)) continue;
+                        shade_face<DIST, RGB>(rec, st, P, dc, xp, yp, threshold, s_qz, s_qid, tid, btex);
                     }
-                }
-
-                const bool front = (rec->flags & 8u) != 0;
-                if (RGB == 0) {  // :390-397
-                    if (zp < depth_min && check_pixel_inside(w) && (P.double_side || front)) {
-                        depth_min = zp;
-                        face_index_min = fn;
-                        float col[3];
-                        sample_texture_fwd(col, btex + (size_t)fn * P.T * 3, wc, P.R, P.tex_type, rec, zp);
-                        sc0 = col[0]; sc1 = col[1]; sc2 = col[2];
-                    }
-                } else if (RGB == 1) {  // :399-419
-                    if (front || P.double_side) {
-                        const float zp_norm = dc.by_span(P.far_ - zp);
-                        float exp_delta_zp = 1.f;
-                        if (zp_norm > softmax_max) {
-                            exp_delta_zp = expf(dc.by_gamma(softmax_max - zp_norm));
-                            softmax_max = zp_norm;
+                } else {
+                    // ---- each lane compacts its own list, then lanes walk private lists
+                    int cnt = 0;
+                    for (int it = 0; it < wcnt; it++) {
+                        const int j = S.wlist[warp][it];
+                        if (pixel_in_rect(&S.rec[j].r, px, row)) {
+                            s_plist[cnt * B200R_TILE_THREADS + tid] = (unsigned char)j;
+                            cnt++;
                         }
-                        const float exp_z = expf(dc.by_gamma(zp_norm - softmax_max));
-                        softmax_sum = exp_delta_zp * softmax_sum + exp_z * soft_fragment;
-                        float col[3];
-                        sample_texture_fwd(col, btex + (size_t)fn * P.T * 3, wc, P.R, P.tex_type, rec, zp);
-                        sc0 = exp_delta_zp * sc0 + exp_z * soft_fragment * col[0];
-                        sc1 = exp_delta_zp * sc1 + exp_z * soft_fragment * col[1];
-                        sc2 = exp_delta_zp * sc2 + exp_z * soft_fragment * col[2];
+                    }
+                    const int maxcnt = __reduce_max_sync(0xffffffffu, cnt);
+                    for (int i = 0; i < maxcnt; i++) {
+                        if (i < cnt) {
+                            const FaceRec* rec = &S.rec[s_plist[i * B200R_TILE_THREADS + tid]].r;
+                            shade_face<DIST, RGB>(rec, st, P, dc, xp, yp, threshold, s_qz, s_qid, tid, btex);
+                        }
                     }
                 }
-            }
 
-            __syncthreads();  // everyone done reading S.ids (keep*) and S.rec
-            if (tid < rest) S.ids[tid] = keep0;
-            if (tid + 256 < rest) S.ids[tid + 256] = keep1;
-            n_pending = rest;
-        }
-    }
-
-    // ---- finalise (:425-455)
-    float out_a;
-    if (P.alpha_func == 0) out_a = alpha;
-    else if (P.alpha_func == 1) out_a = alpha / (float)nf;
-    else out_a = (float)(1.0 - (double)alpha);
-    float o0, o1, o2, g0, g1;
-    if (RGB == 0) {
-        o0 = sc0; o1 = sc1; o2 = sc2;  // stays at the (zero) background when no face was hit
-        g0 = depth_min; g1 = (float)face_index_min;
-    } else if (RGB == 1) {
-        o0 = sc0 / softmax_sum; o1 = sc1 / softmax_sum; o2 = sc2 / softmax_sum;
-        g0 = softmax_sum; g1 = softmax_max;
-    } else {
-        o0 = o1 = o2 = 0.f; g0 = g1 = 0.f;
-    }
-
-    // Stage the 6 output planes of the tile in shared memory and write each plane row with
-    // 16-byte stores (64 contiguous bytes per tile row).
-    __syncthreads();
-    float* s_out = reinterpret_cast<float*>(S.rec);  // 6 * 256 floats = 6 KB
-    const int tpix = ly * B200R_TILE + lx;
-    s_out[0 * 256 + tpix] = o0;
-    s_out[1 * 256 + tpix] = o1;
-    s_out[2 * 256 + tpix] = o2;
-    s_out[3 * 256 + tpix] = out_a;
-    s_out[4 * 256 + tpix] = g0;
-    s_out[5 * 256 + tpix] = g1;
-    __syncthreads();
-    const size_t npix = (size_t)is * is;
-    if ((is & 3) == 0) {
-        for (int j = tid; j < 6 * 64; j += B200R_TILE_THREADS) {
-            const int ch = j >> 6, r = (j & 63) >> 2, q = j & 3;
-            const int orow = tr0 + r, ocol = tx0 + q * 4;
-            if (orow < is && ocol < is) {
-                const float4 v = *reinterpret_cast<const float4*>(&s_out[ch * 256 + r * 16 + q * 4]);
-                float* dst = (ch < 4) ? soft_colors + ((size_t)b * 4 + ch) * npix
-                                      : aggrs_info + ((size_t)b * 2 + (ch - 4)) * npix;
-                *reinterpret_cast<float4*>(dst + (size_t)orow * is + ocol) = v;
+                __syncthreads();  // everyone done reading S.ids (keep0) and S.rec
+                if (tid < rest) S.ids[tid] = keep0;
+                n_pending = rest;
             }
         }
-    } else {
-        for (int j = tid; j < 6 * 256; j += B200R_TILE_THREADS) {
-            const int ch = j >> 8, r = (j & 255) >> 4, c = j & 15;
-            const int orow = tr0 + r, ocol = tx0 + c;
-            if (orow < is && ocol < is) {
-                float* dst = (ch < 4) ? soft_colors + ((size_t)b * 4 + ch) * npix
-                                      : aggrs_info + ((size_t)b * 2 + (ch - 4)) * npix;
-                dst[(size_t)orow * is + ocol] = s_out[j];
+
+        // ---- finalise (:425-455)
+        float out_a;
+        if (P.alpha_func == 0) out_a = st.alpha;
+        else if (P.alpha_func == 1) out_a = st.alpha / (float)nf;
+        else out_a = (float)(1.0 - (double)st.alpha);
+        float o0, o1, o2, g0, g1;
+        if (RGB == 0) {
+            o0 = st.sc0; o1 = st.sc1; o2 = st.sc2;  // stays at the (zero) background when no face was hit
+            g0 = st.depth_min; g1 = (float)st.face_index_min;
+        } else if (RGB == 1) {
+            o0 = st.sc0 / st.softmax_sum; o1 = st.sc1 / st.softmax_sum; o2 = st.sc2 / st.softmax_sum;
+            g0 = st.softmax_sum; g1 = st.softmax_max;
+        } else {
+            o0 = o1 = o2 = 0.f; g0 = g1 = 0.f;
+        }
+
+        // Stage the 6 output planes of the tile in shared memory and write each plane row with
+        // 16-byte stores (64 contiguous bytes per tile row).
+        __syncthreads();
+        float* s_out = reinterpret_cast<float*>(S.rec);  // 6 * 256 floats = 6 KB
+        const int tpix = ly * B200R_TILE + lx;
+        s_out[0 * 256 + tpix] = o0;
+        s_out[1 * 256 + tpix] = o1;
+        s_out[2 * 256 + tpix] = o2;
+        s_out[3 * 256 + tpix] = out_a;
+        s_out[4 * 256 + tpix] = g0;
+        s_out[5 * 256 + tpix] = g1;
+        __syncthreads();
+        if ((is & 3) == 0) {
+            for (int j = tid; j < 6 * 64; j += B200R_TILE_THREADS) {
+                const int ch = j >> 6, r = (j & 63) >> 2, q = j & 3;
+                const int orow = tr0 + r, ocol = tx0 + q * 4;
+                if (orow < is && ocol < is) {
+                    const float4 v = *reinterpret_cast<const float4*>(&s_out[ch * 256 + r * 16 + q * 4]);
+                    float* dst = (ch < 4) ? soft_colors + ((size_t)b * 4 + ch) * npix
+                                          : aggrs_info + ((size_t)b * 2 + (ch - 4)) * npix;
+                    *reinterpret_cast<float4*>(dst + (size_t)orow * is + ocol) = v;
+                }
+            }
+        } else {
+            for (int j = tid; j < 6 * 256; j += B200R_TILE_THREADS) {
+                const int ch = j >> 8, r = (j & 255) >> 4, c = j & 15;
+                const int orow = tr0 + r, ocol = tx0 + c;
+                if (orow < is && ocol < is) {
+                    float* dst = (ch < 4) ? soft_colors + ((size_t)b * 4 + ch) * npix
+                                          : aggrs_info + ((size_t)b * 2 + (ch - 4)) * npix;
+                    dst[(size_t)orow * is + ocol] = s_out[j];
+                }
             }
         }
-    }
-    // top-K ids, slot order, -1 padded (replaces cudaMemsetAsync(out3_p, -1, ...) :470 + :453-455)
-    if (px < is && row < is) {
-        int* dst = ids_out + (size_t)b * K * npix + (size_t)row * is + px;
-        for (int k = 0; k < K; k++)
-            dst[(size_t)k * npix] = (k < q_size) ? s_qid[k * B200R_TILE_THREADS + tid] : -1;
+        // top-K ids, slot order, -1 padded (replaces cudaMemsetAsync(out3_p, -1, ...) :470 + :453-455)
+        if (px < is && row < is) {
+            int* dst = ids_out + (size_t)b * K * npix + (size_t)row * is + px;
+            for (int k = 0; k < K; k++)
+                dst[(size_t)k * npix] = (k < st.q_size) ? s_qid[k * B200R_TILE_THREADS + tid] : -1;
+        }
     }
 }
 

@@ -158,14 +158,29 @@ __device__ __forceinline__ int block_excl_scan_256(int cnt, int* s_warp /*[8]*/,
 // whose fixed-capacity bins silently overflow; here capacity is nf per bin and the test is
 // the exact check_border rectangle.
 #define B200R_COARSE_PER_THREAD 4
+#define B200R_COST_BUCKETS 64
+
+// log-scale cost bucket, 4 per octave, larger cost -> larger bucket; cost 0 -> bucket 0
+__device__ __forceinline__ int cost_bucket(int cost) {
+    if (cost <= 0) return 0;
+    const int lg = 31 - __clz(cost);                       // floor(log2)
+    const int frac = lg >= 2 ? ((cost >> (lg - 2)) & 3) : 0;  // next two bits
+    const int bkt = 1 + lg * 4 + frac;
+    return bkt < B200R_COST_BUCKETS ? bkt : B200R_COST_BUCKETS - 1;
+}
+
 __global__ void __launch_bounds__(256) k_coarse_bin(const uint2* __restrict__ rects, int* __restrict__ coarse_cnt,
-                                                    int* __restrict__ coarse_ids, int nf, int is,
-                                                    int coarse_px, int ncs) {
+                                                    int* __restrict__ coarse_ids, int* __restrict__ tile_cost,
+                                                    int* __restrict__ cost_hist, int nf, int is,
+                                                    int coarse_px, int ncs, int ntx) {
     __shared__ int s_warp[8];
+    __shared__ int s_cost[B200R_MAX_COARSE_SIDE * B200R_MAX_COARSE_SIDE];  // fine tiles of this bin (<= 16x16)
     const int bin = blockIdx.x, b = blockIdx.y;
     const int bx = bin % ncs, by = bin / ncs;
     const int x0 = bx * coarse_px, x1 = min(is, x0 + coarse_px) - 1;
     const int r0 = by * coarse_px, r1 = min(is, r0 + coarse_px) - 1;
+    const int tpb = coarse_px / B200R_TILE;  // fine tiles per bin edge
+    for (int i = threadIdx.x; i < tpb * tpb; i += 256) s_cost[i] = 0;
     const uint2* rc = rects + (size_t)b * nf;
     int* out = coarse_ids + ((size_t)b * ncs * ncs + bin) * nf;
     int n_out = 0;
@@ -173,26 +188,70 @@ __global__ void __launch_bounds__(256) k_coarse_bin(const uint2* __restrict__ re
     for (int base = 0; base < nf; base += 256 * B200R_COARSE_PER_THREAD) {
         const int first = base + threadIdx.x * B200R_COARSE_PER_THREAD;
         uint32_t mask = 0;
+        uint2 rr[B200R_COARSE_PER_THREAD];
         if (vec_ok && first + B200R_COARSE_PER_THREAD <= nf) {
             const uint4 a = __ldg(reinterpret_cast<const uint4*>(rc + first));
             const uint4 c = __ldg(reinterpret_cast<const uint4*>(rc + first + 2));
-            mask |= rect_overlaps(make_uint2(a.x, a.y), x0, x1, r0, r1) ? 1u : 0u;
-            mask |= rect_overlaps(make_uint2(a.z, a.w), x0, x1, r0, r1) ? 2u : 0u;
-            mask |= rect_overlaps(make_uint2(c.x, c.y), x0, x1, r0, r1) ? 4u : 0u;
-            mask |= rect_overlaps(make_uint2(c.z, c.w), x0, x1, r0, r1) ? 8u : 0u;
-        } else {
+            rr[0] = make_uint2(a.x, a.y); rr[1] = make_uint2(a.z, a.w);
+            rr[2] = make_uint2(c.x, c.y); rr[3] = make_uint2(c.z, c.w);
 #pragma unroll
             for (int u = 0; u < B200R_COARSE_PER_THREAD; u++)
-                if (first + u < nf && rect_overlaps(__ldg(rc + first + u), x0, x1, r0, r1)) mask |= 1u << u;
+                if (rect_overlaps(rr[u], x0, x1, r0, r1)) mask |= 1u << u;
+        } else {
+#pragma unroll
+            for (int u = 0; u < B200R_COARSE_PER_THREAD; u++) {
+                rr[u] = make_uint2(1u, 1u);  // empty
+                if (first + u < nf) {
+                    rr[u] = __ldg(rc + first + u);
+                    if (rect_overlaps(rr[u], x0, x1, r0, r1)) mask |= 1u << u;
+                }
+            }
         }
         int total;
         int off = n_out + block_excl_scan_256(__popc(mask), s_warp, total);
 #pragma unroll
         for (int u = 0; u < B200R_COARSE_PER_THREAD; u++)
-            if (mask & (1u << u)) out[off++] = first + u;
+            if (mask & (1u << u)) {
+                out[off++] = first + u;
+                // cost model: (pixel, face) pairs = area of rect ∩ fine tile, for every fine tile of the bin
+                const int fx0 = max((int)(rr[u].x & 0xffffu), x0), fx1 = min((int)(rr[u].x >> 16), x1);
+                const int fr0 = max((int)(rr[u].y & 0xffffu), r0), fr1 = min((int)(rr[u].y >> 16), r1);
+                for (int ty = (fr0 - r0) / B200R_TILE; ty <= (fr1 - r0) / B200R_TILE; ty++) {
+                    const int h = min(fr1, r0 + ty * B200R_TILE + B200R_TILE - 1) - max(fr0, r0 + ty * B200R_TILE) + 1;
+                    for (int tx = (fx0 - x0) / B200R_TILE; tx <= (fx1 - x0) / B200R_TILE; tx++) {
+                        const int w = min(fx1, x0 + tx * B200R_TILE + B200R_TILE - 1) - max(fx0, x0 + tx * B200R_TILE) + 1;
+                        atomicAdd(&s_cost[ty * tpb + tx], w * h);
+                    }
+                }
+            }
         n_out += total;
     }
     if (threadIdx.x == 0) coarse_cnt[b * ncs * ncs + bin] = n_out;
+    __syncthreads();
+    for (int i = threadIdx.x; i < tpb * tpb; i += 256) {
+        const int gtx = bx * tpb + i % tpb, gty = by * tpb + i / tpb;
+        if (gtx < ntx && gty < ntx) {
+            const int c = s_cost[i];
+            tile_cost[(size_t)b * ntx * ntx + gty * ntx + gtx] = c;
+            atomicAdd(&cost_hist[cost_bucket(c)], 1);
+        }
+    }
+}
+
+// Orders all tiles by descending cost bucket (longest-processing-time-first for the persistent
+// raster grid).  hist[] must be complete (previous kernel); cursor[] zeroed.
+__global__ void __launch_bounds__(256) k_tile_order(const int* __restrict__ tile_cost, const int* __restrict__ hist,
+                                                    int* __restrict__ cursor, int* __restrict__ tile_order, int total) {
+    __shared__ int s_start[B200R_COST_BUCKETS];
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int k = B200R_COST_BUCKETS - 1; k >= 0; k--) { s_start[k] = acc; acc += hist[k]; }
+    }
+    __syncthreads();
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const int bkt = cost_bucket(tile_cost[t]);
+    tile_order[s_start[bkt] + atomicAdd(&cursor[bkt], 1)] = t;
 }
 
 }  // namespace b200r

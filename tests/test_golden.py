@@ -1,0 +1,67 @@
+"""Pins the CPU oracle to the REAL reference: tests/golden/ref_gpu_*.npz hold outputs of the
+reference's own kernel strings (jrender/renderer/dr/softras/cuda/soft_rasterize.py), compiled
+for sm_100a by oracle/build_ref.py and run on a B200 by oracle/make_ref_golden.py.
+
+The reference build contracts a*b+c into FMAs where nvcc chooses (nvcc defaults), the oracle
+and the product never do, and depth enters the colour softmax as exp((z-max)/1e-4): a 1-ulp
+difference in z moves a softmax weight by ~6e-4.  Tolerances are therefore statistical
+(measured values in profiles/parity_r01.md; thresholds ~4x above them):
+  * top-K id sets equal on >= 99.8 % of pixels (100 % on all fixtures but the sub-pixel mesh);
+  * soft_colors: max |diff| <= 2e-3 (sub-pixel-triangle fixture: <= 2 % of pixels above 2e-3);
+  * gradients: sum|diff| / sum|ref| <= 2e-3 (sub-pixel fixture: 5e-2);
+  * faces_info (K1): relative 1e-5 (sub-pixel fixture 5e-3: near-degenerate determinants).
+"""
+import glob
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import softras as osr
+from tests.conftest import ROOT
+
+FILES = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "ref_gpu_*.npz")))
+
+
+def rel_l1(ref, got):
+    m = np.isfinite(ref) & np.isfinite(got)
+    return float(np.abs(ref[m] - got[m]).sum() / max(np.abs(ref[m]).sum(), 1e-30))
+
+
+def test_golden_files_present():
+    assert len(FILES) >= 8
+    prov = json.loads(str(np.load(FILES[0])["provenance"]))
+    assert "B200" in prov["gpu"] and "soft_rasterize.py" in prov["source"]
+
+
+@pytest.mark.parametrize("path", FILES, ids=[os.path.basename(p)[8:-4] for p in FILES])
+def test_oracle_matches_reference_kernels(path):
+    z = np.load(path)
+    P = osr.Params(**json.loads(str(z["params"])))
+    fv, tex, g = z["face_vertices"], z["textures"], z["grad_soft_colors"]
+    cpu = osr.forward(fv, tex, P)
+    gf, gt = osr.backward(fv, tex, cpu, g, P)
+    subpixel = "3280" in path          # triangles smaller than a pixel: decisions flip with FMA contraction
+    ids_ref = z["faces_id_buffer"].astype(np.int32)
+    same = (np.sort(ids_ref, 1) == np.sort(cpu["faces_id_buffer"], 1)).all(1).mean()
+    assert same >= (0.998 if subpixel else 1.0), same
+    d = np.abs(z["soft_colors"] - cpu["soft_colors"]).max(1)
+    if subpixel:
+        assert (d > 2e-3).mean() <= 0.02 and d.mean() <= 2e-3
+    else:
+        assert d.max() <= 2e-3, d.max()
+    fi_rel = np.abs(z["faces_info"] - cpu["faces_info"]).max() / np.abs(cpu["faces_info"]).max()
+    assert fi_rel <= (5e-3 if subpixel else 1e-5)
+    assert rel_l1(z["grad_faces"], gf) <= (5e-2 if subpixel else 2e-3)
+    T = tex.shape[2]
+    if P["texture_type"] == "surface" and T > 1:
+        # Reference UB: backward_sample_texture returns an uninitialised value for
+        # non-hit texels; the nvcc-12.9 build materialises it as "every texel receives the hit
+        # texel's gradient".  The oracle defines non-hit texels as 0, so the reference's value at
+        # EVERY texel must equal the oracle's per-face total.
+        ref_gt = z["grad_textures"]
+        assert np.abs(ref_gt - ref_gt[:, :, :1]).max() <= 1e-5 * np.abs(ref_gt).max()   # atomic order only
+        assert rel_l1(ref_gt[:, :, 0], gt.sum(2)) <= 2e-3
+    else:
+        assert rel_l1(z["grad_textures"], gt) <= (5e-2 if subpixel else 2e-3)
