@@ -256,7 +256,8 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.synchronize(dev)
     L.b200r_profile_enable(0)
     kern = {}
-    for kid, name in [(0, "k_face_setup"), (1, "k_coarse_bin"), (2, "k_softras_forward"), (3, "k_softras_backward")]:
+    for kid, name in [(0, "k_face_setup"), (1, "k_coarse_bin"), (4, "k_tile_order"), (2, "k_softras_forward"),
+                      (3, "k_softras_backward"), (9, "k_softras_bwd_finalize")]:
         ms, n = C.c_double(0), C.c_longlong(0)
         L.b200r_profile_read(kid, C.byref(ms), C.byref(n))
         kern[name] = {"avg_ms": ms.value / max(1, n.value), "launches_per_step": n.value / nprof}
@@ -335,6 +336,7 @@ def run_ours(args, rank, world, local_rank):
                    "parallelism": "batch-sharded dp%d, no data-path collective" % world,
                    "l2": "256 MiB buffer written between timed steps (outside the event pairs)",
                    "baseline_note": "vs_baseline = value / (1000/35.5 ms): README.md:69, GPU and batch unstated"},
+        "step_ms": {"min": float(np.min(step_ms)), "median": float(np.median(step_ms)), "max": float(np.max(step_ms))},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "what": "pinned host face_vertices+textures -> H2D -> forward -> on-device MSE loss -> backward -> D2H grads + loss scalar"},

@@ -62,8 +62,9 @@ B200R_API const char* b200r_version(void);
 B200R_API const char* b200r_last_error(void);
 
 /* Bytes of device scratch the SoftRas forward needs for (batch, num_faces, image_size).
- * The same buffer, untouched, must be handed to the backward (it holds the per-face
- * records the reference keeps in `faces_info`, soft_rasterize.py:62,101). */
+ * The same buffer must be handed to the backward (it holds the per-face records the
+ * reference keeps in `faces_info`, soft_rasterize.py:62,101, and a gradient-accumulator region the
+ * backward uses as scratch). */
 B200R_API size_t b200r_softras_workspace_bytes(int batch_size, int num_faces, int image_size);
 
 /* SoftRas forward.
@@ -89,7 +90,7 @@ B200R_API int b200r_softras_forward(const float* face_vertices, const float* tex
  * are overwritten (zeroed inside, then accumulated). */
 B200R_API int b200r_softras_backward(const float* face_vertices, const float* textures,
                            const float* soft_colors, const float* aggrs_info,
-                           const int32_t* faces_id_buffer, const void* workspace,
+                           const int32_t* faces_id_buffer, void* workspace,
                            size_t workspace_bytes, const float* grad_soft_colors,
                            float* grad_face_vertices, float* grad_textures,
                            int batch_size, int num_faces, int texture_size, int image_size,
@@ -98,20 +99,54 @@ B200R_API int b200r_softras_backward(const float* face_vertices, const float* te
                            int dist_func, int rgb_func, int alpha_func, int texture_type,
                            int double_side, void* stream);
 
+/* ---- NMR (dr_type='n3mr') hard rasterizer -------------------------------------------------
+ * Maps keep the reference kernels' orientation [B, yi, xi] with yi UP (row 0 = bottom); the
+ * vertical flip to image orientation belongs to the caller (n3mr.py:239-247).
+ *   faces               [B, nf, 3, 3]
+ *   textures            [B, nf, ts, ts, ts, 3]           (return_rgb)
+ *   face_index_map      [B, H, W] int32, -1 = background
+ *   weight_map          [B, H, W, 3]      depth_map [B, H, W] (far where uncovered)
+ *   rgb_map             [B, H, W, 3]      already mixed with background_rgb (host float[3], may be NULL = black)
+ *   alpha_map           [B, H, W]         (face_index >= 0)
+ *   sampling_index_map  [B, H, W, 8] int32, sampling_weight_map [B, H, W, 8]
+ *   face_inv_map        [B, H, W, 9]      (return_depth)
+ * Equal-depth ties are won by the lowest face id (the reference's winner is race-dependent). */
+B200R_API size_t b200r_nmr_workspace_bytes(int batch_size, int num_faces, int image_size);
+B200R_API int b200r_nmr_forward(const float* faces, const float* textures, int32_t* face_index_map,
+                                float* weight_map, float* depth_map, float* rgb_map, float* alpha_map,
+                                int32_t* sampling_index_map, float* sampling_weight_map, float* face_inv_map,
+                                void* workspace, size_t workspace_bytes, int batch_size, int num_faces,
+                                int texture_size, int image_size, float near, float far, float eps,
+                                const float* background_rgb, int return_rgb, int return_alpha,
+                                int return_depth, void* stream);
+/* grad_faces [B,nf,3,3] and grad_textures [B,nf,ts,ts,ts,3] are overwritten.  Sub-ops follow
+ * n3mr.py:29-67: pixel-map gradient (x,y) -> texture gradient -> depth gradient accumulated in place. */
+B200R_API int b200r_nmr_backward(const float* faces, const int32_t* face_index_map, const float* weight_map,
+                                 const float* depth_map, const float* rgb_map, const float* alpha_map,
+                                 const int32_t* sampling_index_map, const float* sampling_weight_map,
+                                 const float* face_inv_map, const float* grad_rgb_map,
+                                 const float* grad_alpha_map, const float* grad_depth_map, float* grad_faces,
+                                 float* grad_textures, int batch_size, int num_faces, int texture_size,
+                                 int image_size, float eps, int return_rgb, int return_alpha,
+                                 int return_depth, void* stream);
+
 /* Launch counter: number of kernels this library has launched in this process
  * (bench.py reports the delta over the timed region as "gpu_launches"). */
 B200R_API unsigned long long b200r_launch_count(void);
 
 /* Tuning knobs (process-wide; results are identical for every setting, only speed changes):
  *   "softras_fwd_variant"    0 = warp-uniform face loop, 1 = per-lane face lists (default)
- *   "softras_fwd_persistent" 0 = one CTA per tile, 1 = persistent grid + tile queue (default) */
+ *   "softras_fwd_persistent" 0 = one CTA per tile, 1 = persistent grid + tile queue (default)
+ *   "softras_fwd_warps"      warps per forward CTA: 8 (16x16 tiles), 2 (16x4), 1 (8x4, warp-autonomous)
+ *   "softras_bwd_variant"    0 = warp union walk + scalar atomics, 1 = per-lane walk + 16-byte atomics (default) */
 B200R_API int b200r_set_option(const char* name, int value);
 
 /* Per-kernel device timing (CUDA events recorded on the launch stream around every kernel
  * this library launches).  Off by default.  bench.py uses it for the roofline of the
  * dominant kernel; b200r_profile_read synchronises the outstanding events. */
 enum { B200R_K_FACE_SETUP = 0, B200R_K_COARSE_BIN = 1, B200R_K_SOFTRAS_FWD = 2, B200R_K_SOFTRAS_BWD = 3,
-       B200R_K_TILE_ORDER = 4 };
+       B200R_K_TILE_ORDER = 4, B200R_K_NMR_SETUP = 5, B200R_K_NMR_FWD = 6, B200R_K_NMR_BWD_PIXEL = 7,
+       B200R_K_NMR_BWD_MAPS = 8, B200R_K_SOFTRAS_BWD_FINALIZE = 9 };
 B200R_API void b200r_profile_enable(int on);
 B200R_API void b200r_profile_reset(void);
 B200R_API int b200r_profile_read(int kernel, double* total_ms, long long* launches);

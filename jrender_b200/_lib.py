@@ -51,6 +51,12 @@ def lib():
     L.b200r_profile_read.argtypes = [_I, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
     L.b200r_debug_exact_math.restype = _I
     L.b200r_debug_exact_math.argtypes = [_P, _P, _I, _P, _P]
+    L.b200r_nmr_workspace_bytes.restype = C.c_size_t
+    L.b200r_nmr_workspace_bytes.argtypes = [_I, _I, _I]
+    L.b200r_nmr_forward.restype = _I
+    L.b200r_nmr_forward.argtypes = [_P] * 11 + [C.c_size_t, _I, _I, _I, _I, _F, _F, _F, _P, _I, _I, _I, _P]
+    L.b200r_nmr_backward.restype = _I
+    L.b200r_nmr_backward.argtypes = [_P] * 14 + [_I, _I, _I, _I, _F, _I, _I, _I, _P]
     L.b200r_set_option.restype = _I
     L.b200r_set_option.argtypes = [C.c_char_p, _I]
     _lib = L

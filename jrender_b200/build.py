@@ -14,9 +14,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libb200raster.so")
-SOURCES = ["softras_api.cu", "nmr_api.cu", "api_util.cu", "debug_api.cu"]
+SOURCES = ["softras_api.cu", "softras_fwd_nw8.cu", "softras_fwd_nw2.cu", "softras_fwd_nw1.cu", "softras_bwd.cu",
+           "nmr_api.cu", "api_util.cu", "debug_api.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-shared"]
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
+OBJDIR = os.path.join(HERE, "lib", "obj")
 
 
 def _nvcc():
@@ -43,13 +45,31 @@ def stale():
 
 
 def build(force=False, verbose=False):
+    """Compile every translation unit to an object file (in parallel), then link the .so."""
     if not force and not stale():
         return LIB
-    os.makedirs(LIBDIR, exist_ok=True)
+    from concurrent.futures import ThreadPoolExecutor
+    os.makedirs(OBJDIR, exist_ok=True)
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + srcs
+    headers = [f for f in _deps() if not f.endswith(".cu")] + [os.path.abspath(__file__)]
+    hdr_time = max(os.path.getmtime(h) for h in headers)
+
+    def compile_one(src):
+        obj = os.path.join(OBJDIR, os.path.basename(src)[:-3] + ".o")
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(src), hdr_time):
+            return obj, ""
+        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("nvcc failed for %s:\n%s" % (src, r.stderr))
+        return obj, r.stderr
+    with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
+        results = list(ex.map(compile_one, srcs))
     if verbose:
-        print(" ".join(cmd))
+        for _, log in results:
+            if log:
+                print(log)
+    cmd = [_nvcc(), "-shared", "-o", LIB] + [o for o, _ in results]
     subprocess.run(cmd, check=True)
     return LIB
 

@@ -41,7 +41,9 @@ struct SoftRasParams {
     int B, nf, T, R, is, K;
     float near_, far_, eps, sigma, gamma, dist_eps;  // dist_eps = ln(1/dist_eps - 1)
     int dist_func, rgb_func, alpha_func, tex_type, double_side;
-    int ntx;        // fine tiles per image side
+    int ntx;        // 16x16 tiles per image side (backward / NMR mapping)
+    int ftw, fth;   // forward tile size in pixels (8*WX x 4*WY, WX*WY warps per CTA)
+    int fntx, fnty; // forward tiles per image row / column
     int coarse_px;  // coarse bin edge in pixels (multiple of B200R_TILE)
     int ncs;        // coarse bins per image side
     int tile_stride;  // persistent scheduler: odd stride coprime with the tile count
@@ -54,8 +56,9 @@ struct SoftRasWorkspace {
     int* coarse_cnt;     // [B*ncs*ncs]
     int* coarse_ids;     // [B*ncs*ncs][nf]
     int* counters;       // [256] scheduler state, zeroed per launch: [0] queue head, [64..127] cost histogram, [128..191] scatter cursors
-    int* tile_cost;      // [B*ntx*ntx] (pixel, face) pairs per fine tile
-    int* tile_order;     // [B*ntx*ntx] tile ids, most expensive first
+    int* tile_cost;      // [B*max_tiles] (pixel, face) pairs per forward tile (smallest tile 8x4)
+    int* tile_order;     // [B*max_tiles] tile ids, most expensive first
+    float* gacc;         // [B*nf][12] backward gradient accumulator (3 x float4 per face)
     size_t bytes;
 };
 
@@ -86,10 +89,13 @@ static inline SoftRasWorkspace b200r_carve(void* base, int B, int nf, int image_
     off += b200r_align256((size_t)B * ncs * ncs * (size_t)nf * sizeof(int));
     w.counters = (int*)(p + off);
     off += b200r_align256(256 * sizeof(int));
+    const size_t max_tiles = (size_t)((image_size + 7) / 8) * ((image_size + 3) / 4);  // 8x4 is the smallest forward tile
     w.tile_cost = (int*)(p + off);
-    off += b200r_align256((size_t)B * ntx * ntx * sizeof(int));
+    off += b200r_align256((size_t)B * max_tiles * sizeof(int));
     w.tile_order = (int*)(p + off);
-    off += b200r_align256((size_t)B * ntx * ntx * sizeof(int));
+    off += b200r_align256((size_t)B * max_tiles * sizeof(int));
+    w.gacc = (float*)(p + off);
+    off += b200r_align256((size_t)B * nf * 12 * sizeof(float));
     w.bytes = off;
     return w;
 }

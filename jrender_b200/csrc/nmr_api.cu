@@ -1,0 +1,136 @@
+// nmr_api.cu -- C ABI entry points for the NMR (dr_type='n3mr') path (see include/b200raster.h).
+#include <cmath>
+#include <cstring>
+
+#include "../../include/b200raster.h"
+#include "api_util.cuh"
+#include "nmr_kernels.cuh"
+
+using namespace b200r;
+
+namespace {
+int nmr_sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
+}  // namespace
+
+extern "C" {
+
+size_t b200r_nmr_workspace_bytes(int batch_size, int num_faces, int image_size) {
+    if (batch_size <= 0 || num_faces <= 0 || image_size <= 0) return 0;
+    return b200r_carve(nullptr, batch_size, num_faces, image_size).bytes;  // NmrRec (128 B) fits the 160 B slots
+}
+
+int b200r_nmr_forward(const float* faces, const float* textures, int32_t* face_index_map, float* weight_map,
+                      float* depth_map, float* rgb_map, float* alpha_map, int32_t* sampling_index_map,
+                      float* sampling_weight_map, float* face_inv_map, void* workspace, size_t workspace_bytes,
+                      int B, int nf, int texture_size, int is, float near_, float far_, float eps,
+                      const float* background_rgb, int return_rgb, int return_alpha, int return_depth, void* stream) {
+    if (B <= 0 || nf <= 0 || is <= 0) return b200r_fail(B200R_EINVAL, "b200r_nmr_forward: non-positive size (B=%d nf=%d image_size=%d)", B, nf, is);
+    if (is > 4096) return b200r_fail(B200R_EUNSUPPORTED, "b200r_nmr_forward: image_size %d > 4096", is);
+    if (!faces || !face_index_map || !weight_map || !depth_map || !workspace)
+        return b200r_fail(B200R_EINVAL, "b200r_nmr_forward: NULL pointer argument");
+    if (return_rgb && (!textures || !rgb_map || !sampling_index_map || !sampling_weight_map || texture_size <= 0))
+        return b200r_fail(B200R_EINVAL, "b200r_nmr_forward: return_rgb needs textures, rgb_map, sampling maps and texture_size > 0");
+    if (return_alpha && !alpha_map) return b200r_fail(B200R_EINVAL, "b200r_nmr_forward: return_alpha needs alpha_map");
+    if (return_depth && !face_inv_map) return b200r_fail(B200R_EINVAL, "b200r_nmr_forward: return_depth needs face_inv_map");
+    const SoftRasWorkspace W = b200r_carve(workspace, B, nf, is);
+    if (workspace_bytes < W.bytes)
+        return b200r_fail(B200R_EWORKSPACE, "b200r_nmr_forward: workspace %zu < required %zu bytes", workspace_bytes, W.bytes);
+    NmrParams P;
+    P.B = B; P.nf = nf; P.ts = texture_size; P.is = is; P.near_ = near_; P.far_ = far_; P.eps = eps;
+    for (int k = 0; k < 3; k++) P.bg[k] = background_rgb ? background_rgb[k] : 0.f;
+    P.return_rgb = return_rgb ? 1 : 0; P.return_alpha = return_alpha ? 1 : 0; P.return_depth = return_depth ? 1 : 0;
+    b200r_geometry(is, &P.ntx, &P.coarse_px, &P.ncs);
+    cudaStream_t st = (cudaStream_t)stream;
+    NmrRec* recs = reinterpret_cast<NmrRec*>(W.recs);
+    const int total = B * nf;
+    {
+        B200rProfScope prof(B200R_K_NMR_SETUP, st);
+        k_nmr_setup<<<(total + 255) / 256, 256, 0, st>>>(faces, recs, W.rects, total, nf, is);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return b200r_cuda_fail(e, "k_nmr_setup");
+    e = cudaMemsetAsync(W.counters, 0, 256 * sizeof(int), st);
+    if (e != cudaSuccess) return b200r_cuda_fail(e, "memset counters");
+    {
+        B200rProfScope prof(B200R_K_COARSE_BIN, st);
+        k_coarse_bin<<<dim3(P.ncs * P.ncs, B), 256, 0, st>>>(W.rects, W.coarse_cnt, W.coarse_ids, W.tile_cost, W.counters + 64,
+                                                             nf, is, P.coarse_px, P.ncs, B200R_TILE, B200R_TILE, P.ntx, P.ntx);
+    }
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return b200r_cuda_fail(e, "k_coarse_bin");
+    const int total_tiles = P.ntx * P.ntx * B;
+    {
+        B200rProfScope prof(B200R_K_TILE_ORDER, st);
+        k_tile_order<<<(total_tiles + 255) / 256, 256, 0, st>>>(W.tile_cost, W.counters + 64, W.counters + 128, W.tile_order, total_tiles);
+    }
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return b200r_cuda_fail(e, "k_tile_order");
+    {
+        int occ = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_nmr_forward, B200R_TILE_THREADS, 0);
+        if (occ < 1) occ = 1;
+        const long long slots = (long long)nmr_sm_count() * occ;
+        const unsigned grid = (unsigned)(total_tiles < slots ? total_tiles : slots);
+        B200rProfScope prof(B200R_K_NMR_FWD, st);
+        k_nmr_forward<<<grid, B200R_TILE_THREADS, 0, st>>>(P, recs, W.rects, W.coarse_cnt, W.coarse_ids, faces, textures,
+                                                           face_index_map, weight_map, depth_map, rgb_map, alpha_map,
+                                                           sampling_index_map, sampling_weight_map, face_inv_map,
+                                                           W.counters, W.tile_order);
+    }
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return b200r_cuda_fail(e, "k_nmr_forward");
+    return 0;
+}
+
+int b200r_nmr_backward(const float* faces, const int32_t* face_index_map, const float* weight_map,
+                       const float* depth_map, const float* rgb_map, const float* alpha_map,
+                       const int32_t* sampling_index_map, const float* sampling_weight_map,
+                       const float* face_inv_map, const float* grad_rgb_map, const float* grad_alpha_map,
+                       const float* grad_depth_map, float* grad_faces, float* grad_textures, int B, int nf,
+                       int texture_size, int is, float eps, int return_rgb, int return_alpha, int return_depth,
+                       void* stream) {
+    if (B <= 0 || nf <= 0 || is <= 0) return b200r_fail(B200R_EINVAL, "b200r_nmr_backward: non-positive size");
+    if (!faces || !face_index_map || !grad_faces) return b200r_fail(B200R_EINVAL, "b200r_nmr_backward: NULL pointer argument");
+    if (return_rgb && (!rgb_map || !grad_rgb_map || !sampling_index_map || !sampling_weight_map || !grad_textures || texture_size <= 0))
+        return b200r_fail(B200R_EINVAL, "b200r_nmr_backward: return_rgb needs rgb_map, grad_rgb_map, sampling maps, grad_textures");
+    if (return_alpha && (!alpha_map || !grad_alpha_map)) return b200r_fail(B200R_EINVAL, "b200r_nmr_backward: return_alpha needs alpha_map and grad_alpha_map");
+    if (return_depth && (!depth_map || !weight_map || !face_inv_map || !grad_depth_map))
+        return b200r_fail(B200R_EINVAL, "b200r_nmr_backward: return_depth needs depth_map, weight_map, face_inv_map, grad_depth_map");
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(grad_faces, 0, sizeof(float) * 9 * (size_t)B * nf, st);   // rasterize.py:623
+    if (e != cudaSuccess) return b200r_cuda_fail(e, "memset grad_faces");
+    if (return_rgb) {
+        e = cudaMemsetAsync(grad_textures, 0, sizeof(float) * 3 * (size_t)texture_size * texture_size * texture_size * B * nf, st);  // :705
+        if (e != cudaSuccess) return b200r_cuda_fail(e, "memset grad_textures");
+    }
+    if (return_rgb || return_alpha) {  // n3mr.py:150-154
+        const long warps = (long)B * nf;
+        B200rProfScope prof(B200R_K_NMR_BWD_PIXEL, st);
+        k_nmr_backward_pixel_map<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(faces, face_index_map, rgb_map, alpha_map, grad_rgb_map,
+                                                                             grad_alpha_map, grad_faces, B, nf, is, eps,
+                                                                             return_rgb ? 1 : 0, return_alpha ? 1 : 0);
+    }
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return b200r_cuda_fail(e, "k_nmr_backward_pixel_map");
+    if (return_rgb || return_depth) {
+        const size_t npix = (size_t)B * is * is;
+        B200rProfScope prof(B200R_K_NMR_BWD_MAPS, st);
+        k_nmr_backward_maps<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(faces, face_index_map, weight_map, depth_map, face_inv_map,
+                                                                           sampling_index_map, sampling_weight_map, grad_rgb_map,
+                                                                           grad_depth_map, grad_faces, grad_textures, B, nf, is,
+                                                                           texture_size, return_rgb ? 1 : 0, return_depth ? 1 : 0);
+    }
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return b200r_cuda_fail(e, "k_nmr_backward_maps");
+    return 0;
+}
+
+}  // extern "C"

@@ -6,8 +6,7 @@
 
 #include "../../include/b200raster.h"
 #include "api_util.cuh"
-#include "softras_backward.cuh"
-#include "softras_forward.cuh"
+#include "softras_launch.cuh"
 #include "softras_setup.cuh"
 
 using namespace b200r;
@@ -16,8 +15,11 @@ namespace {
 
 std::atomic<int> g_fwd_variant{1};     // 0: warp-uniform face loop, 1: per-lane face lists
 std::atomic<int> g_fwd_persistent{1};  // 0: one CTA per tile, 1: persistent grid + atomic tile queue
+std::atomic<int> g_bwd_variant{1};     // 0: warp union walk + scalar atomics, 1: per-lane walk + 16-byte vector atomics
+std::atomic<int> g_fwd_warps{1};       // warps per forward CTA: 8 (16x16 tile), 2 (16x4), 1 (8x4, warp-autonomous; default)
+}  // namespace
 
-int sm_count() {
+int b200r_sm_count() {
     static int n = 0;
     if (n == 0) {
         int dev = 0;
@@ -27,7 +29,7 @@ int sm_count() {
     return n;
 }
 
-int gcd_i(long long a, long long b) { while (b) { long long t = a % b; a = b; b = t; } return (int)a; }
+namespace {
 
 int validate(const char* fn, int B, int nf, int T, int is, int K, int dist, int rgb, int alpha, int tex,
              float sigma, float gamma) {
@@ -53,78 +55,14 @@ SoftRasParams make_params(int B, int nf, int T, int is, int K, float near_, floa
     P.near_ = near_; P.far_ = far_; P.eps = eps; P.sigma = sigma; P.gamma = gamma; P.dist_eps = dist_eps;
     P.dist_func = dist; P.rgb_func = rgb; P.alpha_func = alpha; P.tex_type = tex; P.double_side = double_side ? 1 : 0;
     b200r_geometry(is, &P.ntx, &P.coarse_px, &P.ncs);
-    const long long total = (long long)P.ntx * P.ntx * B;
-    long long stride = (long long)(total * 0.6180339887) | 1;
-    while (stride > 1 && gcd_i(stride, total) != 1) stride += 2;
-    P.tile_stride = (int)(stride % total == 0 ? 1 : stride);
+    const int nw = g_fwd_warps.load();
+    P.ftw = nw == 1 ? 8 : 16;
+    P.fth = nw == 8 ? 16 : 4;
+    P.fntx = (is + P.ftw - 1) / P.ftw;
+    P.fnty = (is + P.fth - 1) / P.fth;
+    P.tile_stride = 1;
     return P;
 }
-
-template <int DIST, int RGB, int VARIANT>
-cudaError_t launch_forward_v(const SoftRasParams& P, const SoftRasWorkspace& W, const float* textures,
-                             float* soft_colors, float* aggrs_info, int32_t* ids, cudaStream_t st) {
-    size_t smem = sizeof(FwdSmem) + (size_t)P.K * B200R_TILE_THREADS * 8;
-    if (VARIANT == 1) smem += (size_t)B200R_CHUNK * B200R_TILE_THREADS;
-    cudaError_t e = cudaFuncSetAttribute(k_softras_forward<DIST, RGB, VARIANT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    const int tiles = P.ntx * P.ntx;
-    const bool persistent = g_fwd_persistent.load() != 0;
-    int* counter = nullptr;
-    dim3 grid(tiles, P.B);
-    if (persistent) {
-        counter = W.counters;
-        int occ = 1;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_softras_forward<DIST, RGB, VARIANT>, B200R_TILE_THREADS, smem);
-        if (occ < 1) occ = 1;
-        const long long total = (long long)tiles * P.B;
-        const long long slots = (long long)sm_count() * occ;
-        grid = dim3((unsigned)(total < slots ? total : slots), 1);
-    }
-    {
-        B200rProfScope prof(B200R_K_SOFTRAS_FWD, st);
-        k_softras_forward<DIST, RGB, VARIANT><<<grid, B200R_TILE_THREADS, smem, st>>>(
-            P, W.recs, W.rects, W.coarse_cnt, W.coarse_ids, textures, soft_colors, aggrs_info, ids, counter, W.tile_order);
-    }
-    return cudaGetLastError();
-}
-
-template <int DIST, int RGB>
-cudaError_t launch_forward(const SoftRasParams& P, const SoftRasWorkspace& W, const float* textures,
-                           float* soft_colors, float* aggrs_info, int32_t* ids, cudaStream_t st) {
-    if (g_fwd_variant.load() == 0) return launch_forward_v<DIST, RGB, 0>(P, W, textures, soft_colors, aggrs_info, ids, st);
-    return launch_forward_v<DIST, RGB, 1>(P, W, textures, soft_colors, aggrs_info, ids, st);
-}
-
-template <int DIST, int RGB>
-cudaError_t launch_backward(const SoftRasParams& P, const SoftRasWorkspace& W, const float* textures,
-                            const float* soft_colors, const float* aggrs_info, const int32_t* ids,
-                            const float* grad_soft_colors, float* grad_faces, float* grad_textures, cudaStream_t st) {
-    const size_t smem = (size_t)P.K * B200R_TILE_THREADS * 4 + 8 * sizeof(FaceRec);
-    cudaError_t e = cudaFuncSetAttribute(k_softras_backward<DIST, RGB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    dim3 grid(P.ntx * P.ntx, P.B);
-    {
-        B200rProfScope prof(B200R_K_SOFTRAS_BWD, st);
-        k_softras_backward<DIST, RGB><<<grid, B200R_TILE_THREADS, smem, st>>>(P, W.recs, textures, soft_colors, aggrs_info, ids,
-                                                                               grad_soft_colors, grad_faces, grad_textures);
-    }
-    return cudaGetLastError();
-}
-
-#define DISPATCH(FN, ...)                                                                   \
-    do {                                                                                    \
-        switch (P.dist_func * 3 + P.rgb_func) {                                             \
-            case 0: e = FN<0, 0>(__VA_ARGS__); break;                                       \
-            case 1: e = FN<0, 1>(__VA_ARGS__); break;                                       \
-            case 2: e = FN<0, 2>(__VA_ARGS__); break;                                       \
-            case 3: e = FN<1, 0>(__VA_ARGS__); break;                                       \
-            case 4: e = FN<1, 1>(__VA_ARGS__); break;                                       \
-            case 5: e = FN<1, 2>(__VA_ARGS__); break;                                       \
-            case 6: e = FN<2, 0>(__VA_ARGS__); break;                                       \
-            case 7: e = FN<2, 1>(__VA_ARGS__); break;                                       \
-            default: e = FN<2, 2>(__VA_ARGS__); break;                                      \
-        }                                                                                   \
-    } while (0)
 
 }  // namespace
 
@@ -136,6 +74,12 @@ int b200r_set_option(const char* name, int value) {
     if (!name) return b200r_fail(B200R_EINVAL, "b200r_set_option: NULL name");
     if (!strcmp(name, "softras_fwd_variant")) { g_fwd_variant.store(value ? 1 : 0); return 0; }
     if (!strcmp(name, "softras_fwd_persistent")) { g_fwd_persistent.store(value ? 1 : 0); return 0; }
+    if (!strcmp(name, "softras_bwd_variant")) { g_bwd_variant.store(value ? 1 : 0); return 0; }
+    if (!strcmp(name, "softras_fwd_warps")) {
+        if (value != 1 && value != 2 && value != 8) return b200r_fail(B200R_EINVAL, "softras_fwd_warps must be 1, 2 or 8");
+        g_fwd_warps.store(value);
+        return 0;
+    }
     return b200r_fail(B200R_EINVAL, "b200r_set_option: unknown option '%s'", name);
 }
 
@@ -174,25 +118,31 @@ int b200r_softras_forward(const float* face_vertices, const float* textures, flo
     {
         B200rProfScope prof(B200R_K_COARSE_BIN, st);
         k_coarse_bin<<<dim3(P.ncs * P.ncs, B), 256, 0, st>>>(W.rects, W.coarse_cnt, W.coarse_ids, W.tile_cost, W.counters + 64,
-                                                             nf, is, P.coarse_px, P.ncs, P.ntx);
+                                                             nf, is, P.coarse_px, P.ncs, P.ftw, P.fth, P.fntx, P.fnty);
     }
     e = cudaGetLastError();
     if (e != cudaSuccess) return b200r_cuda_fail(e, "k_coarse_bin");
     {
-        const int total_tiles = P.ntx * P.ntx * B;
+        const int total_tiles = P.fntx * P.fnty * B;
         B200rProfScope prof(B200R_K_TILE_ORDER, st);
         k_tile_order<<<(total_tiles + 255) / 256, 256, 0, st>>>(W.tile_cost, W.counters + 64, W.counters + 128, W.tile_order, total_tiles);
     }
     e = cudaGetLastError();
     if (e != cudaSuccess) return b200r_cuda_fail(e, "k_tile_order");
 
-    DISPATCH(launch_forward, P, W, textures, soft_colors, aggrs_info, faces_id_buffer, st);
+    {
+        const int variant = g_fwd_variant.load(), persistent = g_fwd_persistent.load();
+        const int nw = g_fwd_warps.load();
+        if (nw == 1) e = b200r_launch_forward_nw1(P, W, textures, soft_colors, aggrs_info, faces_id_buffer, variant, persistent, st);
+        else if (nw == 2) e = b200r_launch_forward_nw2(P, W, textures, soft_colors, aggrs_info, faces_id_buffer, variant, persistent, st);
+        else e = b200r_launch_forward_nw8(P, W, textures, soft_colors, aggrs_info, faces_id_buffer, variant, persistent, st);
+    }
     if (e != cudaSuccess) return b200r_cuda_fail(e, "k_softras_forward");
     return 0;
 }
 
 int b200r_softras_backward(const float* face_vertices, const float* textures, const float* soft_colors,
-                           const float* aggrs_info, const int32_t* faces_id_buffer, const void* workspace,
+                           const float* aggrs_info, const int32_t* faces_id_buffer, void* workspace,
                            size_t workspace_bytes, const float* grad_soft_colors, float* grad_face_vertices,
                            float* grad_textures, int B, int nf, int T, int is, int K, float near_, float far_,
                            float eps, float sigma_val, float gamma_val, float dist_eps_logit, int dist_func,
@@ -202,18 +152,14 @@ int b200r_softras_backward(const float* face_vertices, const float* textures, co
     if (!face_vertices || !textures || !soft_colors || !aggrs_info || !faces_id_buffer || !workspace ||
         !grad_soft_colors || !grad_face_vertices || !grad_textures)
         return b200r_fail(B200R_EINVAL, "b200r_softras_backward: NULL pointer argument");
-    const SoftRasWorkspace W = b200r_carve(const_cast<void*>(workspace), B, nf, is);
+    const SoftRasWorkspace W = b200r_carve(workspace, B, nf, is);
     if (workspace_bytes < W.bytes)
         return b200r_fail(B200R_EWORKSPACE, "b200r_softras_backward: workspace %zu < required %zu bytes", workspace_bytes, W.bytes);
     const SoftRasParams P = make_params(B, nf, T, is, K, near_, far_, eps, sigma_val, gamma_val, dist_eps_logit,
                                         dist_func, rgb_func, alpha_func, texture_type, double_side);
     cudaStream_t st = (cudaStream_t)stream;
-    cudaError_t e = cudaMemsetAsync(grad_face_vertices, 0, sizeof(float) * 9 * (size_t)B * nf, st);  // :1374
-    if (e != cudaSuccess) return b200r_cuda_fail(e, "memset grad_faces");
-    e = cudaMemsetAsync(grad_textures, 0, sizeof(float) * 3 * (size_t)T * B * nf, st);  // :1375
-    if (e != cudaSuccess) return b200r_cuda_fail(e, "memset grad_textures");
-    DISPATCH(launch_backward, P, W, textures, soft_colors, aggrs_info, faces_id_buffer, grad_soft_colors,
-             grad_face_vertices, grad_textures, st);
+    cudaError_t e = b200r_launch_backward(P, W, textures, soft_colors, aggrs_info, faces_id_buffer, grad_soft_colors,
+                                          grad_face_vertices, grad_textures, g_bwd_variant.load(), st);
     if (e != cudaSuccess) return b200r_cuda_fail(e, "k_softras_backward");
     return 0;
 }

@@ -1,12 +1,22 @@
 // softras_backward.cuh -- SoftRas top-K backward (replaces K6 of the reference:
 // backward_soft_rasterize_cuda_kernel, cuda/soft_rasterize.py:1177-1360).
 //
-// The reference issues 9 + 3T global atomicAdd per (pixel, face) pair.  Here a warp owns
-// an 8x4 pixel block; every lane sorts its <=K saved face ids ascending, and the warp then
-// walks the UNION of its lanes' ids in ascending order (redux.sync min picks the next
-// face).  Lanes that hold the face compute its gradient contribution, the 12 values are
-// reduced across the warp with shuffles, and one lane issues the atomics: global atomics
-// drop from one set per (pixel, face) to one set per (warp, face).
+// The reference issues 9 + 3T scalar global atomicAdd per (pixel, face) pair.  Two variants:
+//
+//  VARIANT 1 (default) "per-lane + vector atomics": every lane walks its own <=K saved ids, so
+//    all lanes of a covered warp work (the union walk below keeps ~48 % of the lanes busy), reads
+//    the face record straight from the L1-resident record array, and adds its 12 gradient
+//    values (9 vertex + 3 colour for T == 1) with THREE 16-byte REDG.E.ADD.F32x4 into a padded
+//    accumulator [B*nf][12]; k_softras_bwd_finalize then unpacks it into grad_face_vertices
+//    [.,9] and grad_textures [.,1,3] (36-byte rows cannot take 16-byte atomics directly).
+//    Atomic packets drop 4x against the reference and no zero-fill of the outputs is needed.
+//  VARIANT 0 "warp union walk": every lane sorts its ids ascending and the warp walks the UNION
+//    of its lanes' ids (redux.sync min picks the next face); holders compute, a shuffle tree
+//    sums the 12 values and one lane issues scalar atomics: one set per (warp, face).
+//
+// Both evaluate the same per-pair arithmetic (pair_gradient) in the reference's order; only
+// the floating-point summation order of the atomics differs (as it does run to run in the
+// reference).
 #pragma once
 #include "softras_math.cuh"
 
@@ -18,6 +28,238 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+// Per-pixel constants of the backward.
+struct BwdPixel {
+    float xp, yp;
+    float g[4], oc[4];           // upstream gradient, forward output RGBA
+    float softmax_sum, softmax_max;
+    float r_ssum; bool s_ssum;   // reciprocal of softmax_sum
+    double d_galpha, d_one_minus_alpha;
+};
+
+// Gradient contribution of one (pixel, face) pair: gv[k*3+l] = d/d vertex k coord l; gt = texture
+// gradient (T == 1 surface: gt[0..2]; vertex: gt[j*3+k]).  For surface textures with T > 1 the hit
+// texel index is returned in texel_out and gt[0..2] holds its gradient.  (:1240-1358)
+template <int DIST, int RGB>
+__device__ __forceinline__ void pair_gradient(const FaceRec* rec, int fn, const BwdPixel& px, const SoftRasParams& P,
+                                              const DivConst& dc, float nmf, float r_nmf, bool s_nmf,
+                                              const float* __restrict__ tex, float gv[9], float gt[9], int& texel_out) {
+    const float* f = rec->v;
+    const float xp = px.xp, yp = px.yp;
+    const int T = P.T;
+    float w[3], t[3] = {0.f, 0.f, 0.f};
+    float dis = 0.f, dis_x = 0.f, dis_y = 0.f, sign = 0.f, soft_fragment;
+    texel_out = 0;
+    barycentric_coordinate(w, xp, yp, rec->inv);
+    if (DIST == 0) {
+        soft_fragment = 1.f;  // :1259
+    } else if (DIST == 1) {
+        dis = barycentric_p2f_distance(w);
+        t[0] = w[0]; t[1] = w[1]; t[2] = w[2];
+        soft_fragment = sigmoid_from_negarg(dc.by_sigma(-dis));
+    } else {
+        sign = euclidean_p2f_distance(dis_x, dis_y, t, w, rec, xp, yp);
+        dis = dis_x * dis_x + dis_y * dis_y;
+        soft_fragment = sigmoid_from_negarg(dc.by_sigma(-sign * dis));
+    }
+
+    float C_grad_xy = 0.f;
+    float C_grad_xy_alpha = px.g[3];
+    if (P.alpha_func == 1) {
+        C_grad_xy_alpha = C_grad_xy_alpha / (float)P.nf;
+    } else if (P.alpha_func == 2) {
+        // (float)((double)g_a * ((double)(1 - alpha_out) / max((double)(1 - D), 1e-6)))  (:1289)
+        const float omd = 1.f - soft_fragment;
+        const double den = fmax(midrange(omd) ? f2d_mid(omd) : (double)omd, 1e-6);
+        const double prod = px.d_galpha * (px.d_one_minus_alpha / den);
+        C_grad_xy_alpha = d_midrange(prod) ? d2f_mid(prod) : (float)prod;
+    }
+    C_grad_xy += C_grad_xy_alpha;
+
+    const float w0[3] = {w[0], w[1], w[2]};
+    barycentric_clip(w);
+    const float zp = interp_z(w, rec);
+
+    if (RGB == 0) {
+        if ((float)fn == px.softmax_max) {  // :1300 (int vs float compare, Q10)
+            if (P.tex_type == 0) {
+                texel_out = surface_texel(w, P.R);
+                gt[0] = px.g[0]; gt[1] = px.g[1]; gt[2] = px.g[2];
+            } else {
+#pragma unroll
+                for (int j = 0; j < 3; j++)
+#pragma unroll
+                    for (int k = 0; k < 3; k++) gt[j * 3 + k] = w[j] * px.g[k];
+            }
+        }
+    } else if (RGB == 1) {
+        float C_grad_xyz_rgb = 0.f;
+        const float zp_norm = dc.by_span(P.far_ - zp);
+        const float zp_softmax = fast_div(soft_fragment * expf(dc.by_gamma(zp_norm - px.softmax_max)), px.softmax_sum,
+                                          px.r_ssum, px.s_ssum);
+        float col[3];
+        if (P.tex_type == 0) {
+            const int j = surface_texel(w, P.R);
+            texel_out = j;
+            if (T == 1) { col[0] = rec->col[0]; col[1] = rec->col[1]; col[2] = rec->col[2]; }
+            else {
+#pragma unroll
+                for (int k = 0; k < 3; k++) col[k] = __ldg(tex + j * 3 + k);
+            }
+#pragma unroll
+            for (int k = 0; k < 3; k++) gt[k] = zp_softmax * px.g[k];
+        } else {
+#pragma unroll
+            for (int k = 0; k < 3; k++)
+                col[k] = w[0] * __ldg(tex + k) + w[1] * __ldg(tex + 3 + k) + w[2] * __ldg(tex + 6 + k);
+#pragma unroll
+            for (int j = 0; j < 3; j++)
+#pragma unroll
+                for (int k = 0; k < 3; k++) gt[j * 3 + k] = zp_softmax * (w[j] * px.g[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < 3; k++) C_grad_xyz_rgb += px.g[k] * (col[k] - px.oc[k]);
+        C_grad_xyz_rgb *= zp_softmax;
+        C_grad_xy += C_grad_xyz_rgb / soft_fragment;
+
+        const float C_grad_z_rgb = fast_div(dc.by_gamma(C_grad_xyz_rgb), nmf, r_nmf, s_nmf) * zp * zp;
+        const uint32_t fl = rec->flags;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const bool sz = (fl & (16u << k)) != 0;
+            const float z = f[3 * k + 2], rz = rec->rz[k];
+            gv[k * 3 + 2] = fast_div(fast_div(C_grad_z_rgb * w[k], z, rz, sz), z, rz, sz);
+        }
+    }
+
+    C_grad_xy *= dc.by_sigma(soft_fragment * (1.f - soft_fragment));  // :1336
+    if (DIST == 1) {  // backward_barycentric_p2f_distance (:1118-1132), w := t (unclipped)
+        const int pm = t[0] > t[1] ? (t[1] > t[2] ? 2 : 1) : (t[0] > t[2] ? 2 : 0);
+        const float* inv = rec->inv;
+        const float scale2 = dis > 0.f ? sqrtf(dis) : sqrtf(-dis);
+#pragma unroll
+        for (int l = 0; l < 2; l++)
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                float grad_kl = 0.f;
+                const float a = -inv[3 * pm + l];
+                grad_kl += a * inv[3 * k + 0] * xp;
+                grad_kl += a * inv[3 * k + 1] * yp;
+                grad_kl += a * inv[3 * k + 2] * 1.f;
+                float v = grad_kl * C_grad_xy;
+                v = (float)((double)v * (2.0 * (double)scale2));
+                gv[k * 3 + l] = v;
+            }
+    } else if (DIST == 2) {  // :1341-1347
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            gv[k * 3 + 0] = 2.f * sign * C_grad_xy * (t[k] + w0[k]) * dis_x;
+            gv[k * 3 + 1] = 2.f * sign * C_grad_xy * (t[k] + w0[k]) * dis_y;
+        }
+    }
+}
+
+__device__ __forceinline__ void load_pixel(BwdPixel& px, const float* __restrict__ soft_colors,
+                                           const float* __restrict__ aggrs_info, const float* __restrict__ grad_soft_colors,
+                                           int b, size_t pn, size_t npix, bool valid) {
+#pragma unroll
+    for (int k = 0; k < 4; k++) { px.g[k] = 0.f; px.oc[k] = 0.f; }
+    px.softmax_sum = 1.f;
+    px.softmax_max = 0.f;
+    if (valid) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            px.g[k] = __ldg(grad_soft_colors + ((size_t)b * 4 + k) * npix + pn);
+            px.oc[k] = __ldg(soft_colors + ((size_t)b * 4 + k) * npix + pn);
+        }
+        px.softmax_sum = __ldg(aggrs_info + ((size_t)b * 2 + 0) * npix + pn);
+        px.softmax_max = __ldg(aggrs_info + ((size_t)b * 2 + 1) * npix + pn);
+    }
+    px.r_ssum = rcp_refined(px.softmax_sum);
+    px.s_ssum = midrange(px.softmax_sum);
+    px.d_galpha = (double)px.g[3];
+    px.d_one_minus_alpha = (double)(1.f - px.oc[3]);
+}
+
+// ---------------------------------------------------------------- VARIANT 1: per-lane walk + vector atomics
+template <int DIST, int RGB>
+__global__ void __launch_bounds__(B200R_TILE_THREADS, 2)
+k_softras_backward_lane(const SoftRasParams P, const FaceRec* __restrict__ recs, const float* __restrict__ textures,
+                        const float* __restrict__ soft_colors, const float* __restrict__ aggrs_info,
+                        const int* __restrict__ ids_in, const float* __restrict__ grad_soft_colors,
+                        float* __restrict__ gacc /*[B*nf][12]*/, float* __restrict__ grad_textures) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int is = P.is, nf = P.nf, K = P.K, T = P.T;
+    const int b = blockIdx.y;
+    const int tx = blockIdx.x % P.ntx, ty = blockIdx.x / P.ntx;
+    const int pxi = tx * B200R_TILE + (warp & 1) * 8 + (lane & 7);
+    const int row = ty * B200R_TILE + (warp >> 1) * 4 + (lane >> 3);
+    const bool valid = pxi < is && row < is;
+    const size_t npix = (size_t)is * is;
+    const size_t pn = (size_t)row * is + pxi;
+    const int* src = ids_in + (size_t)b * K * npix + pn;
+    int fn = valid ? __ldg(src) : -1;
+    if (fn < 0) return;  // list ends at the first -1 (:1236)
+
+    DivConst dc;
+    dc.init(P);
+    BwdPixel px;
+    px.xp = b200r_pix_coord(pxi, is);
+    px.yp = b200r_pix_coord(is - 1 - row, is);
+    load_pixel(px, soft_colors, aggrs_info, grad_soft_colors, b, pn, npix, true);
+    const float nmf = P.near_ - P.far_;
+    const float r_nmf = rcp_refined(nmf);
+    const bool s_nmf = midrange(nmf);
+    const FaceRec* brecs = recs + (size_t)b * nf;
+    const float* btex = textures + (size_t)b * nf * T * 3;
+    float* bacc = gacc + (size_t)b * nf * 12;
+    float* bgt = grad_textures + (size_t)b * nf * T * 3;
+    const bool tex_in_acc = (P.tex_type == 0 && T == 1);
+
+    for (int m = 0; m < K && fn >= 0; m++) {
+        const int fn_next = (m + 1 < K) ? __ldg(src + (size_t)(m + 1) * npix) : -1;  // prefetch
+        const FaceRec* rec = brecs + fn;
+        float gv[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        float gt[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        int texel;
+        pair_gradient<DIST, RGB>(rec, fn, px, P, dc, nmf, r_nmf, s_nmf, btex + (size_t)fn * T * 3, gv, gt, texel);
+        float4* a = reinterpret_cast<float4*>(bacc + (size_t)fn * 12);
+        atomicAdd(a + 0, make_float4(gv[0], gv[1], gv[2], gv[3]));
+        atomicAdd(a + 1, make_float4(gv[4], gv[5], gv[6], gv[7]));
+        atomicAdd(a + 2, make_float4(gv[8], tex_in_acc ? gt[0] : 0.f, tex_in_acc ? gt[1] : 0.f, tex_in_acc ? gt[2] : 0.f));
+        if (RGB != 2 && !tex_in_acc) {
+            if (P.tex_type == 0) {
+#pragma unroll
+                for (int k = 0; k < 3; k++) atomicAdd(bgt + ((size_t)fn * T + texel) * 3 + k, gt[k]);
+            } else {
+#pragma unroll
+                for (int c = 0; c < 9; c++) atomicAdd(bgt + (size_t)fn * 9 + c, gt[c]);
+            }
+        }
+        fn = fn_next;
+    }
+}
+
+// Unpacks the padded accumulator: grad_face_vertices[i][0..8] and, for T == 1 surface textures,
+// grad_textures[i][0..2].
+__global__ void __launch_bounds__(256)
+k_softras_bwd_finalize(const float* __restrict__ gacc, float* __restrict__ grad_faces, float* __restrict__ grad_textures,
+                       int total_faces, int tex_in_acc) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total_faces) return;
+    const float4* a = reinterpret_cast<const float4*>(gacc + (size_t)i * 12);
+    const float4 v0 = a[0], v1 = a[1], v2 = a[2];
+    float* g = grad_faces + (size_t)i * 9;
+    g[0] = v0.x; g[1] = v0.y; g[2] = v0.z; g[3] = v0.w;
+    g[4] = v1.x; g[5] = v1.y; g[6] = v1.z; g[7] = v1.w;
+    g[8] = v2.x;
+    if (tex_in_acc) {
+        float* t = grad_textures + (size_t)i * 3;
+        t[0] = v2.y; t[1] = v2.z; t[2] = v2.w;
+    }
+}
+
+// ---------------------------------------------------------------- VARIANT 0: warp union walk
 template <int DIST, int RGB>
 __global__ void __launch_bounds__(B200R_TILE_THREADS, 2)
 k_softras_backward(const SoftRasParams P, const FaceRec* __restrict__ recs, const float* __restrict__ textures,
@@ -32,13 +274,11 @@ k_softras_backward(const SoftRasParams P, const FaceRec* __restrict__ recs, cons
     const int is = P.is, nf = P.nf, K = P.K, T = P.T;
     const int b = blockIdx.y;
     const int tx = blockIdx.x % P.ntx, ty = blockIdx.x / P.ntx;
-    const int px = tx * B200R_TILE + (warp & 1) * 8 + (lane & 7);
+    const int pxi = tx * B200R_TILE + (warp & 1) * 8 + (lane & 7);
     const int row = ty * B200R_TILE + (warp >> 1) * 4 + (lane >> 3);
-    const bool valid = px < is && row < is;
-    const float xp = b200r_pix_coord(px, is);
-    const float yp = b200r_pix_coord(is - 1 - row, is);
+    const bool valid = pxi < is && row < is;
     const size_t npix = (size_t)is * is;
-    const size_t pn = (size_t)row * is + px;
+    const size_t pn = (size_t)row * is + pxi;
     DivConst dc;
     dc.init(P);
 
@@ -63,23 +303,10 @@ k_softras_backward(const SoftRasParams P, const FaceRec* __restrict__ recs, cons
     // warp-uniform early out for empty blocks
     if (__ballot_sync(0xffffffffu, n > 0) == 0u) return;
 
-    float g[4] = {0.f, 0.f, 0.f, 0.f}, oc[4] = {0.f, 0.f, 0.f, 0.f};
-    float softmax_sum = 1.f, softmax_max = 0.f;
-    if (valid) {
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            g[k] = __ldg(grad_soft_colors + ((size_t)b * 4 + k) * npix + pn);
-            oc[k] = __ldg(soft_colors + ((size_t)b * 4 + k) * npix + pn);
-        }
-        softmax_sum = __ldg(aggrs_info + ((size_t)b * 2 + 0) * npix + pn);
-        softmax_max = __ldg(aggrs_info + ((size_t)b * 2 + 1) * npix + pn);
-    }
-
-    // per-pixel / per-launch denominators of the backward
-    const float r_ssum = rcp_refined(softmax_sum);
-    const bool s_ssum = midrange(softmax_sum);
-    const double d_galpha = (double)g[3];
-    const double d_one_minus_alpha = (double)(1.f - oc[3]);
+    BwdPixel px;
+    px.xp = b200r_pix_coord(pxi, is);
+    px.yp = b200r_pix_coord(is - 1 - row, is);
+    load_pixel(px, soft_colors, aggrs_info, grad_soft_colors, b, pn, npix, valid);
     const float nmf = P.near_ - P.far_;
     const float r_nmf = rcp_refined(nmf);
     const bool s_nmf = midrange(nmf);
@@ -95,7 +322,7 @@ k_softras_backward(const SoftRasParams P, const FaceRec* __restrict__ recs, cons
     while (true) {
         const int fn = __reduce_min_sync(0xffffffffu, cur);
         if (fn == 0x7fffffff) break;
-        // stage the record for the warp: one 4-byte word per lane
+        // stage the record for the warp: one 4-byte word per lane (+8)
         __syncwarp();
         reinterpret_cast<uint32_t*>(wrec)[lane] = __ldg(reinterpret_cast<const uint32_t*>(brecs + fn) + lane);
         if (lane < 8) reinterpret_cast<uint32_t*>(wrec)[32 + lane] = __ldg(reinterpret_cast<const uint32_t*>(brecs + fn) + 32 + lane);
@@ -105,124 +332,12 @@ k_softras_backward(const SoftRasParams P, const FaceRec* __restrict__ recs, cons
         float gv[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // [k*3 + l]
         float gt[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // T==1: [k]; vertex: [j*3+k]
         if (mine) {
-            const FaceRec* rec = wrec;
-            const float* f = rec->v;
-            float w[3], t[3] = {0.f, 0.f, 0.f};
-            float dis = 0.f, dis_x = 0.f, dis_y = 0.f, sign = 0.f, soft_fragment;
-            barycentric_coordinate(w, xp, yp, rec->inv);
-            if (DIST == 0) {
-                soft_fragment = 1.f;  // :1259
-            } else if (DIST == 1) {
-                dis = barycentric_p2f_distance(w);
-                t[0] = w[0]; t[1] = w[1]; t[2] = w[2];
-                soft_fragment = sigmoid_from_negarg(dc.by_sigma(-dis));
-            } else {
-                sign = euclidean_p2f_distance(dis_x, dis_y, t, w, rec, xp, yp);
-                dis = dis_x * dis_x + dis_y * dis_y;
-                soft_fragment = sigmoid_from_negarg(dc.by_sigma(-sign * dis));
-            }
-
-            float C_grad_xy = 0.f;
-            float C_grad_xy_alpha = g[3];
-            if (P.alpha_func == 1) {
-                C_grad_xy_alpha = C_grad_xy_alpha / (float)nf;
-            } else if (P.alpha_func == 2) {
-                // (float)((double)g_a * ((double)(1 - alpha_out) / max((double)(1 - D), 1e-6)))  (:1289)
-                const float omd = 1.f - soft_fragment;
-                const double den = fmax(midrange(omd) ? f2d_mid(omd) : (double)omd, 1e-6);
-                const double prod = d_galpha * (d_one_minus_alpha / den);
-                C_grad_xy_alpha = d_midrange(prod) ? d2f_mid(prod) : (float)prod;
-            }
-            C_grad_xy += C_grad_xy_alpha;
-
-            const float w0[3] = {w[0], w[1], w[2]};
-            barycentric_clip(w);
-            const float zp = interp_z(w, rec);
-
-            const float* tex = btex + (size_t)fn * T * 3;
-            if (RGB == 0) {
-                if ((float)fn == softmax_max) {  // :1300 (int vs float compare, Q10)
-                    if (P.tex_type == 0) {
-                        const int j = surface_texel(w, P.R);
-                        if (T == 1) { gt[0] = g[0]; gt[1] = g[1]; gt[2] = g[2]; }
-                        else {
+            int texel;
+            pair_gradient<DIST, RGB>(wrec, fn, px, P, dc, nmf, r_nmf, s_nmf, btex + (size_t)fn * T * 3, gv, gt, texel);
+            if (RGB != 2 && P.tex_type == 0 && T > 1) {  // per-lane texel: scalar atomics, not reduced
 #pragma unroll
-                            for (int k = 0; k < 3; k++) atomicAdd(bgt + ((size_t)fn * T + j) * 3 + k, g[k]);
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 3; j++)
-#pragma unroll
-                            for (int k = 0; k < 3; k++) gt[j * 3 + k] = w[j] * g[k];
-                    }
-                }
-            } else if (RGB == 1) {
-                float C_grad_xyz_rgb = 0.f;
-                const float zp_norm = dc.by_span(P.far_ - zp);
-                const float zp_softmax = fast_div(soft_fragment * expf(dc.by_gamma(zp_norm - softmax_max)), softmax_sum, r_ssum, s_ssum);
-                float col[3];
-                if (P.tex_type == 0) {
-                    const int j = surface_texel(w, P.R);
-                    if (T == 1) { col[0] = rec->col[0]; col[1] = rec->col[1]; col[2] = rec->col[2]; }
-                    else {
-#pragma unroll
-                        for (int k = 0; k < 3; k++) col[k] = __ldg(tex + j * 3 + k);
-                    }
-                    if (T == 1) {
-#pragma unroll
-                        for (int k = 0; k < 3; k++) gt[k] = zp_softmax * g[k];
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < 3; k++) atomicAdd(bgt + ((size_t)fn * T + j) * 3 + k, zp_softmax * g[k]);
-                    }
-                } else {
-#pragma unroll
-                    for (int k = 0; k < 3; k++)
-                        col[k] = w[0] * __ldg(tex + k) + w[1] * __ldg(tex + 3 + k) + w[2] * __ldg(tex + 6 + k);
-#pragma unroll
-                    for (int j = 0; j < 3; j++)
-#pragma unroll
-                        for (int k = 0; k < 3; k++) gt[j * 3 + k] = zp_softmax * (w[j] * g[k]);
-                }
-#pragma unroll
-                for (int k = 0; k < 3; k++) C_grad_xyz_rgb += g[k] * (col[k] - oc[k]);
-                C_grad_xyz_rgb *= zp_softmax;
-                C_grad_xy += C_grad_xyz_rgb / soft_fragment;
-
-                const float C_grad_z_rgb = fast_div(dc.by_gamma(C_grad_xyz_rgb), nmf, r_nmf, s_nmf) * zp * zp;
-                const uint32_t fl = rec->flags;
-#pragma unroll
-                for (int k = 0; k < 3; k++) {
-                    const bool sz = (fl & (16u << k)) != 0;
-                    const float z = f[3 * k + 2], rz = rec->rz[k];
-                    gv[k * 3 + 2] = fast_div(fast_div(C_grad_z_rgb * w[k], z, rz, sz), z, rz, sz);
-                }
-            }
-
-            C_grad_xy *= dc.by_sigma(soft_fragment * (1.f - soft_fragment));  // :1336
-            if (DIST == 1) {  // backward_barycentric_p2f_distance (:1118-1132), w := t (unclipped)
-                const int pm = t[0] > t[1] ? (t[1] > t[2] ? 2 : 1) : (t[0] > t[2] ? 2 : 0);
-                const float* inv = rec->inv;
-                const float scale2 = dis > 0.f ? sqrtf(dis) : sqrtf(-dis);
-#pragma unroll
-                for (int l = 0; l < 2; l++)
-#pragma unroll
-                    for (int k = 0; k < 3; k++) {
-                        float grad_kl = 0.f;
-                        const float a = -inv[3 * pm + l];
-                        grad_kl += a * inv[3 * k + 0] * xp;
-                        grad_kl += a * inv[3 * k + 1] * yp;
-                        grad_kl += a * inv[3 * k + 2] * 1.f;
-                        float v = grad_kl * C_grad_xy;
-                        v = (float)((double)v * (2.0 * (double)scale2));
-                        gv[k * 3 + l] = v;
-                    }
-            } else if (DIST == 2) {  // :1341-1347
-#pragma unroll
-                for (int k = 0; k < 3; k++) {
-                    gv[k * 3 + 0] = 2.f * sign * C_grad_xy * (t[k] + w0[k]) * dis_x;
-                    gv[k * 3 + 1] = 2.f * sign * C_grad_xy * (t[k] + w0[k]) * dis_y;
-                }
+                for (int k = 0; k < 3; k++) atomicAdd(bgt + ((size_t)fn * T + texel) * 3 + k, gt[k]);
+                gt[0] = gt[1] = gt[2] = 0.f;
             }
             ++p;
             cur = (p < n) ? s_id[p * B200R_TILE_THREADS + tid] : 0x7fffffff;

@@ -2,10 +2,14 @@
 // forward_soft_rasterize_cuda_kernel, cuda/soft_rasterize.py:243-456 and
 // cuda/soft_rasterize_coarse_to_fine.py:513-761).
 //
-// One CTA processes 16x16 pixel tiles, one thread = one pixel, warp w owns an 8x4
-// sub-rectangle.  Per tile the CTA walks its coarse bin's face list (ascending face id),
+// One CTA of WX*WY warps processes (8*WX)x(4*WY) pixel tiles, one thread = one pixel, each warp
+// owns an 8x4 sub-rectangle.  <WX,WY> = <2,4> is the classic 16x16 tile; <1,1> makes every
+// warp an autonomous 8x4 worker with no CTA-wide barrier at all, which removes the
+// intra-CTA imbalance (a warp whose block sits on a mesh pole has 10x the work of its
+// neighbours) at the price of every warp filtering the coarse list itself.
+// Per tile the CTA walks its coarse bin's face list (ascending face id),
 // keeps the faces whose check_border rectangle touches the tile (ordered ballot compaction),
-// stages their 160-byte records in shared memory in rounds of <=128, and every warp narrows
+// stages their 160-byte records in shared memory in rounds, and every warp narrows
 // the round to the faces touching its 8x4 footprint.  Then
 //   VARIANT 0: the warp walks that list in lock-step; a lane works when its pixel lies in
 //              the face's rectangle (~50 % lane utilisation on small triangles);
@@ -25,7 +29,6 @@
 
 namespace b200r {
 
-#define B200R_CHUNK 128  // staged faces per round (index fits uint8)
 
 // shared-memory copy of a record, padded to 176 B: consecutive records then start 11
 // 16-byte bank groups apart (11 is odd), so divergent per-lane record reads spread over
@@ -35,13 +38,34 @@ struct __align__(16) FaceRecS {
     uint4 pad;
 };
 
+template <int NW>
+struct FwdCfg {
+    static constexpr int NT = 32 * NW;
+    static constexpr int CHUNK = NW >= 8 ? 128 : (NW >= 2 ? 64 : 32);  // staged faces per round (index fits uint8)
+};
+
+template <int NW>
 struct FwdSmem {
-    FaceRecS rec[B200R_CHUNK];           // 22 KB (reused as the output staging area)
-    int ids[B200R_CHUNK + 256];          // pending tile-face ids, ascending
-    unsigned char wlist[8][B200R_CHUNK]; // per-warp sub-list (indices into rec[])
-    int s_warp[8];
+    FaceRecS rec[FwdCfg<NW>::CHUNK];                     // reused as the output staging area
+    int ids[FwdCfg<NW>::CHUNK + FwdCfg<NW>::NT];         // pending tile-face ids, ascending
+    unsigned char wlist[NW][FwdCfg<NW>::CHUNK];          // per-warp sub-list (indices into rec[])
+    int s_warp[NW];
     int s_tile;
 };
+
+template <int NW>
+__device__ __forceinline__ void cta_sync() {
+    if (NW == 1) __syncwarp();
+    else __syncthreads();
+}
+
+// dynamic shared memory: FwdSmem<NW> | qz [K][NT] f32 | qid [K][NT] i32 | plist [CHUNK][NT] u8 (VARIANT 1)
+template <int NW>
+static inline size_t fwd_smem_bytes(int K, int variant) {
+    size_t b = sizeof(FwdSmem<NW>) + (size_t)K * FwdCfg<NW>::NT * 8;
+    if (variant == 1) b += (size_t)FwdCfg<NW>::CHUNK * FwdCfg<NW>::NT;
+    return (b + 15) & ~(size_t)15;
+}
 
 struct PixState {
     float sc0, sc1, sc2, alpha, softmax_sum, softmax_max, depth_min, q_max_z;
@@ -50,7 +74,7 @@ struct PixState {
 
 // The reference's per-face loop body (:318-420) for one (pixel, face) pair whose pixel is
 // inside the face's check_border rectangle.
-template <int DIST, int RGB>
+template <int DIST, int RGB, int NT>
 __device__ __forceinline__ void shade_face(const FaceRec* rec, PixState& st, const SoftRasParams& P, const DivConst& dc,
                                            float xp, float yp, float threshold, float* s_qz, int* s_qid, int tid,
                                            const float* __restrict__ btex) {
@@ -91,16 +115,16 @@ __device__ __forceinline__ void shade_face(const FaceRec* rec, PixState& st, con
     const int K = P.K;
     // top-K by z, "replace the current max" policy (:367-385)
     if (st.q_size < K) {
-        s_qz[st.q_size * B200R_TILE_THREADS + tid] = zp;
-        s_qid[st.q_size * B200R_TILE_THREADS + tid] = fn;
+        s_qz[st.q_size * NT + tid] = zp;
+        s_qid[st.q_size * NT + tid] = fn;
         if (zp > st.q_max_z) { st.q_max_z = zp; st.q_max_id = st.q_size; }
         st.q_size++;
     } else if (zp < st.q_max_z) {
-        s_qz[st.q_max_id * B200R_TILE_THREADS + tid] = zp;
-        s_qid[st.q_max_id * B200R_TILE_THREADS + tid] = fn;
+        s_qz[st.q_max_id * NT + tid] = zp;
+        s_qid[st.q_max_id * NT + tid] = fn;
         st.q_max_z = -1.f;
         for (int k = 0; k < st.q_size; k++) {
-            const float z = s_qz[k * B200R_TILE_THREADS + tid];
+            const float z = s_qz[k * NT + tid];
             if (z > st.q_max_z) { st.q_max_z = z; st.q_max_id = k; }
         }
     }
@@ -139,24 +163,26 @@ __device__ __forceinline__ bool pixel_in_rect(const FaceRec* rec, int px, int ro
     return (uint32_t)(px - (int)x0) <= (rx >> 16) - x0 && (uint32_t)(row - (int)r0) <= (rr >> 16) - r0;
 }
 
-template <int DIST, int RGB, int VARIANT>
-__global__ void __launch_bounds__(B200R_TILE_THREADS, 2)
+template <int DIST, int RGB, int VARIANT, int WX, int WY>
+__global__ void __launch_bounds__(32 * WX * WY, (WX * WY >= 8) ? 2 : ((WX * WY >= 2) ? 8 : 16))
 k_softras_forward(const SoftRasParams P, const FaceRec* __restrict__ recs, const uint2* __restrict__ rects,
                   const int* __restrict__ coarse_cnt, const int* __restrict__ coarse_ids,
                   const float* __restrict__ textures, float* __restrict__ soft_colors,
                   float* __restrict__ aggrs_info, int* __restrict__ ids_out, int* tile_counter,
                   const int* __restrict__ tile_order) {
+    constexpr int NW = WX * WY, NT = 32 * NW, CHUNK = FwdCfg<NW>::CHUNK;
+    constexpr int TW = 8 * WX, TH = 4 * WY;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    FwdSmem& S = *reinterpret_cast<FwdSmem*>(smem_raw);
-    float* s_qz = reinterpret_cast<float*>(smem_raw + sizeof(FwdSmem));  // [K][256]
-    int* s_qid = reinterpret_cast<int*>(s_qz + (size_t)P.K * B200R_TILE_THREADS);
-    unsigned char* s_plist = reinterpret_cast<unsigned char*>(s_qid + (size_t)P.K * B200R_TILE_THREADS);  // VARIANT 1: [CHUNK][256]
+    FwdSmem<NW>& S = *reinterpret_cast<FwdSmem<NW>*>(smem_raw);
+    float* s_qz = reinterpret_cast<float*>(smem_raw + sizeof(FwdSmem<NW>));  // [K][NT]
+    int* s_qid = reinterpret_cast<int*>(s_qz + (size_t)P.K * NT);
+    unsigned char* s_plist = reinterpret_cast<unsigned char*>(s_qid + (size_t)P.K * NT);  // VARIANT 1: [CHUNK][NT]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int is = P.is, nf = P.nf, K = P.K;
-    const int tiles_per_image = P.ntx * P.ntx;
+    const int tiles_per_image = P.fntx * P.fnty;
     const int total_tiles = tiles_per_image * P.B;
-    const int lx = (warp & 1) * 8 + (lane & 7), ly = (warp >> 1) * 4 + (lane >> 3);
+    const int lx = (warp % WX) * 8 + (lane & 7), ly = (warp / WX) * 4 + (lane >> 3);
     const float threshold = P.dist_eps * P.sigma;  // :289
     const size_t npix = (size_t)is * is;
     DivConst dc;
@@ -170,25 +196,31 @@ k_softras_forward(const SoftRasParams P, const FaceRec* __restrict__ recs, const
             if (titer > 0) break;
             t = blockIdx.y * tiles_per_image + blockIdx.x;
         } else {
-            __syncthreads();  // previous tile fully written, S.s_tile free
-            if (tid == 0) S.s_tile = atomicAdd(tile_counter, 1);
-            __syncthreads();
-            const int q = S.s_tile;
+            cta_sync<NW>();  // previous tile fully written, S.s_tile free
+            int q = 0;
+            if (NW == 1) {
+                if (lane == 0) q = atomicAdd(tile_counter, 1);
+                q = __shfl_sync(0xffffffffu, q, 0);
+            } else {
+                if (tid == 0) S.s_tile = atomicAdd(tile_counter, 1);
+                __syncthreads();
+                q = S.s_tile;
+            }
             if (q >= total_tiles) break;
             t = __ldg(tile_order + q);  // most expensive tiles first (k_tile_order)
         }
         const int b = t / tiles_per_image;
         const int tt = t - b * tiles_per_image;
-        const int tx = tt % P.ntx, ty = tt / P.ntx;
-        const int px = tx * B200R_TILE + lx, row = ty * B200R_TILE + ly;
+        const int tx = tt % P.fntx, ty = tt / P.fntx;
+        const int px = tx * TW + lx, row = ty * TH + ly;
         const float xp = b200r_pix_coord(px, is);
         const float yp = b200r_pix_coord(is - 1 - row, is);
 
         // tile / warp footprints (inclusive pixel ranges)
-        const int tx0 = tx * B200R_TILE, tx1 = tx0 + B200R_TILE - 1;
-        const int tr0 = ty * B200R_TILE, tr1 = tr0 + B200R_TILE - 1;
-        const int wx0 = tx0 + (warp & 1) * 8, wx1 = wx0 + 7;
-        const int wr0 = tr0 + (warp >> 1) * 4, wr1 = wr0 + 3;
+        const int tx0 = tx * TW, tx1 = tx0 + TW - 1;
+        const int tr0 = ty * TH, tr1 = tr0 + TH - 1;
+        const int wx0 = tx0 + (warp % WX) * 8, wx1 = wx0 + 7;
+        const int wr0 = tr0 + (warp / WX) * 4, wr1 = wr0 + 3;
 
         // ---- per-pixel state, initialised as :291-309 (background buffer is all zero, Q1)
         PixState st;
@@ -212,8 +244,8 @@ k_softras_forward(const SoftRasParams P, const FaceRec* __restrict__ recs, const
         const float* btex = textures + (size_t)b * nf * P.T * 3;
 
         int n_pending = 0;  // uniform across the CTA
-        for (int base = 0; base < n_coarse; base += B200R_TILE_THREADS) {
-            // ---- fine filter: next 256 coarse entries -> S.ids (ordered)
+        for (int base = 0; base < n_coarse; base += NT) {
+            // ---- fine filter: next NT coarse entries -> S.ids (ordered)
             {
                 const int i = base + tid;
                 int id = -1;
@@ -223,27 +255,27 @@ k_softras_forward(const SoftRasParams P, const FaceRec* __restrict__ recs, const
                     pass = rect_overlaps(__ldg(brects + id), tx0, tx1, tr0, tr1);
                 }
                 int total;
-                const int off = n_pending + block_excl_scan_256(pass ? 1 : 0, S.s_warp, total);
+                const int off = n_pending + block_excl_scan<NW>(pass ? 1 : 0, S.s_warp, total);
                 if (pass) S.ids[off] = id;
                 n_pending += total;
             }
-            const bool last = base + B200R_TILE_THREADS >= n_coarse;
-            if (n_pending < B200R_CHUNK && !last) continue;
+            const bool last = base + NT >= n_coarse;
+            if (n_pending < CHUNK && !last) continue;
 
-            while (n_pending >= B200R_CHUNK || (last && n_pending > 0)) {
-                const int m = min(n_pending, B200R_CHUNK);
-                __syncthreads();  // S.ids complete; previous round's readers of S.rec done
+            while (n_pending >= CHUNK || (last && n_pending > 0)) {
+                const int m = min(n_pending, CHUNK);
+                cta_sync<NW>();  // S.ids complete; previous round's readers of S.rec done
                 // ---- stage m records: 10 x uint4 per face, coalesced
-                for (int j = tid; j < m * B200R_REC_UINT4; j += B200R_TILE_THREADS) {
+                for (int j = tid; j < m * B200R_REC_UINT4; j += NT) {
                     const int f = j / B200R_REC_UINT4, q = j - f * B200R_REC_UINT4;
                     reinterpret_cast<uint4*>(&S.rec[f])[q] =
                         __ldg(reinterpret_cast<const uint4*>(brecs + S.ids[f]) + q);
                 }
-                __syncthreads();
+                cta_sync<NW>();
                 // ---- shift the not-yet-staged ids to the front (through registers)
-                const int rest = n_pending - m;
+                const int rest = n_pending - m;  // < NT
                 int keep0 = 0;
-                if (tid < rest) keep0 = S.ids[m + tid];  // rest <= 255
+                if (tid < rest) keep0 = S.ids[m + tid];
                 // ---- warp sub-list
                 int wcnt = 0;
                 for (int j0 = 0; j0 < m; j0 += 32) {
@@ -261,7 +293,7 @@ k_softras_forward(const SoftRasParams P, const FaceRec* __restrict__ recs, const
                     for (int it = 0; it < wcnt; it++) {
                         const FaceRec* rec = &S.rec[S.wlist[warp][it]].r;
                         if (!pixel_in_rect(rec, px, row)) continue;
-                        shade_face<DIST, RGB>(rec, st, P, dc, xp, yp, threshold, s_qz, s_qid, tid, btex);
+                        shade_face<DIST, RGB, NT>(rec, st, P, dc, xp, yp, threshold, s_qz, s_qid, tid, btex);
                     }
                 } else {
                     // ---- each lane compacts its own list, then lanes walk private lists
@@ -269,20 +301,20 @@ k_softras_forward(const SoftRasParams P, const FaceRec* __restrict__ recs, const
                     for (int it = 0; it < wcnt; it++) {
                         const int j = S.wlist[warp][it];
                         if (pixel_in_rect(&S.rec[j].r, px, row)) {
-                            s_plist[cnt * B200R_TILE_THREADS + tid] = (unsigned char)j;
+                            s_plist[cnt * NT + tid] = (unsigned char)j;
                             cnt++;
                         }
                     }
                     const int maxcnt = __reduce_max_sync(0xffffffffu, cnt);
                     for (int i = 0; i < maxcnt; i++) {
                         if (i < cnt) {
-                            const FaceRec* rec = &S.rec[s_plist[i * B200R_TILE_THREADS + tid]].r;
-                            shade_face<DIST, RGB>(rec, st, P, dc, xp, yp, threshold, s_qz, s_qid, tid, btex);
+                            const FaceRec* rec = &S.rec[s_plist[i * NT + tid]].r;
+                            shade_face<DIST, RGB, NT>(rec, st, P, dc, xp, yp, threshold, s_qz, s_qid, tid, btex);
                         }
                     }
                 }
 
-                __syncthreads();  // everyone done reading S.ids (keep0) and S.rec
+                cta_sync<NW>();  // everyone done reading S.ids (keep0) and S.rec
                 if (tid < rest) S.ids[tid] = keep0;
                 n_pending = rest;
             }
@@ -305,31 +337,32 @@ k_softras_forward(const SoftRasParams P, const FaceRec* __restrict__ recs, const
         }
 
         // Stage the 6 output planes of the tile in shared memory and write each plane row with
-        // 16-byte stores (64 contiguous bytes per tile row).
-        __syncthreads();
-        float* s_out = reinterpret_cast<float*>(S.rec);  // 6 * 256 floats = 6 KB
-        const int tpix = ly * B200R_TILE + lx;
-        s_out[0 * 256 + tpix] = o0;
-        s_out[1 * 256 + tpix] = o1;
-        s_out[2 * 256 + tpix] = o2;
-        s_out[3 * 256 + tpix] = out_a;
-        s_out[4 * 256 + tpix] = g0;
-        s_out[5 * 256 + tpix] = g1;
-        __syncthreads();
+        // 16-byte stores (TW*4 contiguous bytes per tile row).
+        cta_sync<NW>();
+        float* s_out = reinterpret_cast<float*>(S.rec);  // 6 * NT floats
+        const int tpix = ly * TW + lx;
+        s_out[0 * NT + tpix] = o0;
+        s_out[1 * NT + tpix] = o1;
+        s_out[2 * NT + tpix] = o2;
+        s_out[3 * NT + tpix] = out_a;
+        s_out[4 * NT + tpix] = g0;
+        s_out[5 * NT + tpix] = g1;
+        cta_sync<NW>();
         if ((is & 3) == 0) {
-            for (int j = tid; j < 6 * 64; j += B200R_TILE_THREADS) {
-                const int ch = j >> 6, r = (j & 63) >> 2, q = j & 3;
+            constexpr int QPR = TW / 4;  // float4 per tile row
+            for (int j = tid; j < 6 * TH * QPR; j += NT) {
+                const int ch = j / (TH * QPR), r = (j % (TH * QPR)) / QPR, q = j % QPR;
                 const int orow = tr0 + r, ocol = tx0 + q * 4;
                 if (orow < is && ocol < is) {
-                    const float4 v = *reinterpret_cast<const float4*>(&s_out[ch * 256 + r * 16 + q * 4]);
+                    const float4 v = *reinterpret_cast<const float4*>(&s_out[ch * NT + r * TW + q * 4]);
                     float* dst = (ch < 4) ? soft_colors + ((size_t)b * 4 + ch) * npix
                                           : aggrs_info + ((size_t)b * 2 + (ch - 4)) * npix;
                     *reinterpret_cast<float4*>(dst + (size_t)orow * is + ocol) = v;
                 }
             }
         } else {
-            for (int j = tid; j < 6 * 256; j += B200R_TILE_THREADS) {
-                const int ch = j >> 8, r = (j & 255) >> 4, c = j & 15;
+            for (int j = tid; j < 6 * NT; j += NT) {
+                const int ch = j / NT, r = (j % NT) / TW, c = j % TW;
                 const int orow = tr0 + r, ocol = tx0 + c;
                 if (orow < is && ocol < is) {
                     float* dst = (ch < 4) ? soft_colors + ((size_t)b * 4 + ch) * npix
@@ -342,7 +375,7 @@ k_softras_forward(const SoftRasParams P, const FaceRec* __restrict__ recs, const
         if (px < is && row < is) {
             int* dst = ids_out + (size_t)b * K * npix + (size_t)row * is + px;
             for (int k = 0; k < K; k++)
-                dst[(size_t)k * npix] = (k < st.q_size) ? s_qid[k * B200R_TILE_THREADS + tid] : -1;
+                dst[(size_t)k * npix] = (k < st.q_size) ? s_qid[k * NT + tid] : -1;
         }
     }
 }

@@ -1,0 +1,52 @@
+// softras_fwd_nw1.cu -- forward kernel instantiations for the 1x1 warp layout (8x4 pixel tiles).
+#include <atomic>
+
+#include "api_util.cuh"
+#include "softras_forward.cuh"
+#include "softras_launch.cuh"
+
+using namespace b200r;
+
+namespace {
+template <int DIST, int RGB, int VARIANT>
+cudaError_t launch_v(const SoftRasParams& P, const SoftRasWorkspace& W, const float* textures, float* soft_colors,
+                     float* aggrs_info, int32_t* ids, int persistent, cudaStream_t st) {
+    constexpr int WX = 1, WY = 1, NW = WX * WY, NT = 32 * NW;
+    const size_t smem = fwd_smem_bytes<NW>(P.K, VARIANT);
+    // attribute + occupancy are host calls: queried once per (instantiation, smem size)
+    static std::atomic<size_t> cfg_smem{0};
+    static std::atomic<int> cfg_occ{0};
+    if (cfg_smem.load() != smem) {
+        cudaError_t e = cudaFuncSetAttribute(k_softras_forward<DIST, RGB, VARIANT, WX, WY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        int occ = 1;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_softras_forward<DIST, RGB, VARIANT, WX, WY>, NT, smem);
+        if (e != cudaSuccess) return e;
+        cfg_occ.store(occ < 1 ? 1 : occ);
+        cfg_smem.store(smem);
+    }
+    const int tiles = P.fntx * P.fnty;
+    int* counter = nullptr;
+    dim3 grid(tiles, P.B);
+    if (persistent) {
+        counter = W.counters;
+        const long long total = (long long)tiles * P.B;
+        const long long slots = (long long)b200r_sm_count() * cfg_occ.load();
+        grid = dim3((unsigned)(total < slots ? total : slots), 1);
+    }
+    {
+        B200rProfScope prof(B200R_K_SOFTRAS_FWD, st);
+        k_softras_forward<DIST, RGB, VARIANT, WX, WY><<<grid, NT, smem, st>>>(
+            P, W.recs, W.rects, W.coarse_cnt, W.coarse_ids, textures, soft_colors, aggrs_info, ids, counter, W.tile_order);
+    }
+    return cudaGetLastError();
+}
+}  // namespace
+
+cudaError_t b200r_launch_forward_nw1(const SoftRasParams& P, const SoftRasWorkspace& W, const float* textures, float* soft_colors,
+                                     float* aggrs_info, int32_t* ids, int variant, int persistent, cudaStream_t st) {
+    cudaError_t e = cudaSuccess;
+    (void)variant;  // only the per-lane-list variant is built for this layout
+    B200R_DISPATCH_DIST_RGB((e = launch_v<D, R, 1>(P, W, textures, soft_colors, aggrs_info, ids, persistent, st)))
+    return e;
+}

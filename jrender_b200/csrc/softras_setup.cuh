@@ -29,7 +29,7 @@ __device__ __forceinline__ int last_not_above(float lim, int is) {
 // One thread per (batch, face).  Computes the 160-byte record, the exact pixel rectangle
 // equivalent to check_border, and (optionally) the reference's faces_info[27].
 // Reference: forward_soft_rasterize_inv_cuda_kernel, cuda/soft_rasterize.py:176-236.
-__global__ void __launch_bounds__(256) k_face_setup(const float* __restrict__ faces, const float* __restrict__ textures,
+static __global__ void __launch_bounds__(256) k_face_setup(const float* __restrict__ faces, const float* __restrict__ textures,
                                                     FaceRec* __restrict__ recs, uint2* __restrict__ rects,
                                                     float* __restrict__ faces_info, int total_faces, int nf,
                                                     int T, int tex_type, int is, float border) {
@@ -128,8 +128,9 @@ __device__ __forceinline__ bool rect_overlaps(uint2 rc, int x0, int x1, int r0, 
 }
 
 // Block-wide ORDERED compaction step: thread `tid` contributes `cnt` items; returns the
-// exclusive prefix over the block (in thread order) and the block total.  256 threads.
-__device__ __forceinline__ int block_excl_scan_256(int cnt, int* s_warp /*[8]*/, int& total) {
+// exclusive prefix over the block (in thread order) and the block total.  NW warps per block.
+template <int NW>
+__device__ __forceinline__ int block_excl_scan(int cnt, int* s_warp /*[NW]*/, int& total) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int incl = cnt;
 #pragma unroll
@@ -137,11 +138,15 @@ __device__ __forceinline__ int block_excl_scan_256(int cnt, int* s_warp /*[8]*/,
         const int n = __shfl_up_sync(0xffffffffu, incl, d);
         if (lane >= d) incl += n;
     }
+    if (NW == 1) {
+        total = __shfl_sync(0xffffffffu, incl, 31);
+        return incl - cnt;
+    }
     if (lane == 31) s_warp[warp] = incl;
     __syncthreads();
     int base = 0, tot = 0;
 #pragma unroll
-    for (int wi = 0; wi < 8; wi++) {
+    for (int wi = 0; wi < NW; wi++) {
         const int v = s_warp[wi];
         if (wi < warp) base += v;
         tot += v;
@@ -150,6 +155,7 @@ __device__ __forceinline__ int block_excl_scan_256(int cnt, int* s_warp /*[8]*/,
     total = tot;
     return base + incl - cnt;
 }
+__device__ __forceinline__ int block_excl_scan_256(int cnt, int* s_warp, int& total) { return block_excl_scan<8>(cnt, s_warp, total); }
 
 // Coarse binning, tile-centric and deterministic: CTA (bin, b) scans the face rectangles of
 // batch element b in ascending face id and appends the overlapping ids, in order, to its
@@ -169,18 +175,19 @@ __device__ __forceinline__ int cost_bucket(int cost) {
     return bkt < B200R_COST_BUCKETS ? bkt : B200R_COST_BUCKETS - 1;
 }
 
-__global__ void __launch_bounds__(256) k_coarse_bin(const uint2* __restrict__ rects, int* __restrict__ coarse_cnt,
+static __global__ void __launch_bounds__(256) k_coarse_bin(const uint2* __restrict__ rects, int* __restrict__ coarse_cnt,
                                                     int* __restrict__ coarse_ids, int* __restrict__ tile_cost,
                                                     int* __restrict__ cost_hist, int nf, int is,
-                                                    int coarse_px, int ncs, int ntx) {
+                                                    int coarse_px, int ncs, int tw, int th, int ntx, int nty) {
     __shared__ int s_warp[8];
-    __shared__ int s_cost[B200R_MAX_COARSE_SIDE * B200R_MAX_COARSE_SIDE];  // fine tiles of this bin (<= 16x16)
+    __shared__ int s_cost[2048];  // tiles of this bin: (coarse_px/tw) * (coarse_px/th) <= 32 * 64 (8x4 tiles, 256 px bins)
     const int bin = blockIdx.x, b = blockIdx.y;
     const int bx = bin % ncs, by = bin / ncs;
     const int x0 = bx * coarse_px, x1 = min(is, x0 + coarse_px) - 1;
     const int r0 = by * coarse_px, r1 = min(is, r0 + coarse_px) - 1;
-    const int tpb = coarse_px / B200R_TILE;  // fine tiles per bin edge
-    for (int i = threadIdx.x; i < tpb * tpb; i += 256) s_cost[i] = 0;
+    const int tpbx = coarse_px / tw, tpby = coarse_px / th;  // tiles per bin along x / y
+    for (int i = threadIdx.x; i < tpbx * tpby; i += 256) s_cost[i] = 0;
+    __syncthreads();
     const uint2* rc = rects + (size_t)b * nf;
     int* out = coarse_ids + ((size_t)b * ncs * ncs + bin) * nf;
     int n_out = 0;
@@ -216,11 +223,11 @@ __global__ void __launch_bounds__(256) k_coarse_bin(const uint2* __restrict__ re
                 // cost model: (pixel, face) pairs = area of rect ∩ fine tile, for every fine tile of the bin
                 const int fx0 = max((int)(rr[u].x & 0xffffu), x0), fx1 = min((int)(rr[u].x >> 16), x1);
                 const int fr0 = max((int)(rr[u].y & 0xffffu), r0), fr1 = min((int)(rr[u].y >> 16), r1);
-                for (int ty = (fr0 - r0) / B200R_TILE; ty <= (fr1 - r0) / B200R_TILE; ty++) {
-                    const int h = min(fr1, r0 + ty * B200R_TILE + B200R_TILE - 1) - max(fr0, r0 + ty * B200R_TILE) + 1;
-                    for (int tx = (fx0 - x0) / B200R_TILE; tx <= (fx1 - x0) / B200R_TILE; tx++) {
-                        const int w = min(fx1, x0 + tx * B200R_TILE + B200R_TILE - 1) - max(fx0, x0 + tx * B200R_TILE) + 1;
-                        atomicAdd(&s_cost[ty * tpb + tx], w * h);
+                for (int ty = (fr0 - r0) / th; ty <= (fr1 - r0) / th; ty++) {
+                    const int h = min(fr1, r0 + ty * th + th - 1) - max(fr0, r0 + ty * th) + 1;
+                    for (int tx = (fx0 - x0) / tw; tx <= (fx1 - x0) / tw; tx++) {
+                        const int w = min(fx1, x0 + tx * tw + tw - 1) - max(fx0, x0 + tx * tw) + 1;
+                        atomicAdd(&s_cost[ty * tpbx + tx], w * h);
                     }
                 }
             }
@@ -228,11 +235,11 @@ __global__ void __launch_bounds__(256) k_coarse_bin(const uint2* __restrict__ re
     }
     if (threadIdx.x == 0) coarse_cnt[b * ncs * ncs + bin] = n_out;
     __syncthreads();
-    for (int i = threadIdx.x; i < tpb * tpb; i += 256) {
-        const int gtx = bx * tpb + i % tpb, gty = by * tpb + i / tpb;
-        if (gtx < ntx && gty < ntx) {
+    for (int i = threadIdx.x; i < tpbx * tpby; i += 256) {
+        const int gtx = bx * tpbx + i % tpbx, gty = by * tpby + i / tpbx;
+        if (gtx < ntx && gty < nty) {
             const int c = s_cost[i];
-            tile_cost[(size_t)b * ntx * ntx + gty * ntx + gtx] = c;
+            tile_cost[(size_t)b * ntx * nty + gty * ntx + gtx] = c;
             atomicAdd(&cost_hist[cost_bucket(c)], 1);
         }
     }
@@ -240,7 +247,7 @@ __global__ void __launch_bounds__(256) k_coarse_bin(const uint2* __restrict__ re
 
 // Orders all tiles by descending cost bucket (longest-processing-time-first for the persistent
 // raster grid).  hist[] must be complete (previous kernel); cursor[] zeroed.
-__global__ void __launch_bounds__(256) k_tile_order(const int* __restrict__ tile_cost, const int* __restrict__ hist,
+static __global__ void __launch_bounds__(256) k_tile_order(const int* __restrict__ tile_cost, const int* __restrict__ hist,
                                                     int* __restrict__ cursor, int* __restrict__ tile_order, int total) {
     __shared__ int s_start[B200R_COST_BUCKETS];
     if (threadIdx.x == 0) {

@@ -68,13 +68,16 @@ class _SoftRasterizeOp(torch.autograd.Function):
                 _ptr(faces_info) if faces_info is not None else None, _ptr(workspace), ws_bytes,
                 *scal, C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
         _lib.check(rc, "b200r_softras_forward")
-        ctx.fn = fn
         ctx.scal = scal
         ctx.ws_bytes = ws_bytes
         ctx.save_for_backward(fv, tx, soft_colors, aggrs_info, faces_id_buffer, workspace)
-        # the reference keeps these on the Function object (soft_rasterize.py:101);
-        # render2 reads save_vars[4] = aggrs_info (render2/render2.py:306)
-        fn.save_vars = (fv, tx, soft_colors, faces_info, aggrs_info, faces_id_buffer)
+        # The reference keeps these on the Function object (soft_rasterize.py:101); render2 reads
+        # save_vars[4] = aggrs_info (render2/render2.py:306).  Detached aliases only: a strong
+        # reference to the OUTPUT tensor from here would close the cycle
+        # output -> grad_fn -> ctx -> ... -> output, and ~0.9 GB per call would then wait for
+        # Python's cyclic GC instead of being freed (and re-used by the allocator) immediately.
+        fn.save_vars = (fv.detach(), tx.detach(), soft_colors.detach(), faces_info, aggrs_info.detach(),
+                        faces_id_buffer.detach())
         ctx.mark_non_differentiable(aggrs_info, faces_id_buffer)
         return soft_colors, aggrs_info, faces_id_buffer
 

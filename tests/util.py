@@ -49,3 +49,47 @@ def rel_err(a, b):
     """max |a-b| / max(|b|, tiny): scale-relative error of a whole tensor."""
     denom = max(float(np.abs(b).max()), 1e-30)
     return float(np.abs(a.astype(np.float64) - b.astype(np.float64)).max()) / denom
+
+
+def nmr_scene(num_faces=280, batch=1, ts=2, fill_back=True, seed=1):
+    """faces [B,nf(x2),3,3] and textures [B,nf(x2),ts,ts,ts,3] the way N3mrRasterizer.render_rgb builds
+    them (rasterizer.py:83-88): reversed-winding copies appended, textures permuted."""
+    from jrender_b200 import workloads as wl
+    fv, _ = wl.make_scene(num_faces, batch=batch)
+    tex = np.random.default_rng(seed).random((batch, fv.shape[1], ts, ts, ts, 3), dtype=np.float32)
+    if fill_back:
+        fv = np.concatenate([fv, fv[:, :, ::-1]], axis=1)
+        tex = np.concatenate([tex, tex.transpose(0, 1, 4, 3, 2, 5)], axis=1)
+    return np.ascontiguousarray(fv), np.ascontiguousarray(tex)
+
+
+def run_nmr_cuda(faces, textures, image_size, near=0.1, far=100.0, eps=1e-3, background_color=(0, 0, 0),
+                 flags=(True, True, True), grads=None, device="cuda:0"):
+    """Through jrender_b200.n3mr.RasterizeFunction -> ctypes -> C ABI.  grads = (g_rgb, g_alpha, g_depth)."""
+    import torch
+    from jrender_b200.n3mr import RasterizeFunction
+    dev = torch.device(device)
+    fc = torch.from_numpy(np.ascontiguousarray(faces)).to(dev).requires_grad_(grads is not None)
+    tx = torch.from_numpy(np.ascontiguousarray(textures)).to(dev).requires_grad_(grads is not None) if flags[0] else None
+    fn = RasterizeFunction(image_size, near, far, eps, background_color, *flags)
+    rgb, alpha, depth = fn(fc, tx)
+    sv = fn.save_vars
+    out = dict(face_index_map=sv[2].cpu().numpy(), weight_map=sv[3].cpu().numpy(), depth_map=sv[4].cpu().numpy())
+    if flags[0]:
+        out.update(rgb_map=rgb.detach().cpu().numpy(), sampling_index_map=sv[8].cpu().numpy(), sampling_weight_map=sv[9].cpu().numpy())
+    if flags[1]:
+        out["alpha_map"] = alpha.detach().cpu().numpy()
+    if flags[2]:
+        out["face_inv_map"] = sv[7].cpu().numpy()
+    if grads is not None:
+        outs, gs = [], []
+        for o, g, f in zip((rgb, alpha, depth), grads, flags):
+            if f:
+                outs.append(o)
+                gs.append(torch.from_numpy(np.ascontiguousarray(g)).to(dev))
+        torch.autograd.backward(outs, gs)
+        out["grad_faces"] = fc.grad.cpu().numpy()
+        if flags[0]:
+            out["grad_textures"] = tx.grad.cpu().numpy()
+    torch.cuda.synchronize()
+    return out

@@ -23,7 +23,7 @@ def kernel_times(L, nsteps, step):
     torch.cuda.synchronize()
     L.b200r_profile_enable(0)
     out = {}
-    for kid, name in [(0, "setup"), (1, "coarse"), (2, "fwd"), (3, "bwd")]:
+    for kid, name in [(0, "setup"), (1, "coarse"), (2, "fwd"), (3, "bwd"), (4, "order"), (9, "bwd_finalize")]:
         ms, n = C.c_double(0), C.c_longlong(0)
         L.b200r_profile_read(kid, C.byref(ms), C.byref(n))
         out[name] = round(ms.value / max(1, n.value), 4)
@@ -46,13 +46,20 @@ def main():
         SoftRasterizeFunction(image_size=H)(fv, tex).backward(grad)
 
     res = {"workload": desc}
-    for variant in (0, 1):
-        for persistent in (0, 1):
-            _lib.set_option("softras_fwd_variant", variant)
-            _lib.set_option("softras_fwd_persistent", persistent)
-            for _ in range(3):
-                step()
-            res["variant%d_persistent%d" % (variant, persistent)] = kernel_times(L, 10, step)
+    for warps, variant, persistent in ((8, 0, 0), (8, 1, 1), (2, 1, 1), (1, 1, 1)):
+        _lib.set_option("softras_fwd_warps", warps)
+        _lib.set_option("softras_fwd_variant", variant)
+        _lib.set_option("softras_fwd_persistent", persistent)
+        for _ in range(3):
+            step()
+        res["warps%d_variant%d_persistent%d" % (warps, variant, persistent)] = kernel_times(L, 10, step)
+    _lib.set_option("softras_fwd_warps", 1)
+    for bv in (0, 1):
+        _lib.set_option("softras_bwd_variant", bv)
+        for _ in range(3):
+            step()
+        res["bwd_variant%d" % bv] = kernel_times(L, 10, step)
+    _lib.set_option("softras_bwd_variant", 1)
     print(json.dumps(res), flush=True)
 
     from oracle import ref_gpu, softras as osr

@@ -2,8 +2,9 @@
 # One GPU session: parity tests, smoke, A/B, bench, ncu launch list + full capture of the raster kernels.
 mkdir -p gpurun_out
 nvidia-smi -L; nproc; lscpu | grep "Model name" | head -1
-timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu.log 2>&1; tail -4 gpurun_out/pytest_gpu.log
+timeout 900 python -m pytest tests -q -m gpu > gpurun_out/pytest_gpu.log 2>&1; tail -6 gpurun_out/pytest_gpu.log
 timeout 300 python __graft_entry__.py --smoke 2>&1 | tail -2
+timeout 300 python tools/diag_step.py 2>&1 | tee gpurun_out/diag.log | tail -5
 timeout 600 python tools/ab_forward.py c3 2>&1 | tee gpurun_out/ab_c3.json | tail -3
 timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_c3.json 2> gpurun_out/bench_c3.err; cat gpurun_out/bench_c3.json; tail -3 gpurun_out/bench_c3.err
 if [ "$1" != "noncu" ]; then
