@@ -34,6 +34,8 @@ WORKLOADS = {
     "c3": (39200, 1024, 4, "C3: SoftRas fwd+bwd 1024x1024, UV sphere 39200 faces, 4 images/GPU (B=32 at 8 GPUs)"),
     "c2": (3280, 1024, 8, "C2: SoftRas fwd+bwd 1024x1024, UV sphere 3280 faces, 8 images/GPU"),
     "tiny": (280, 256, 2, "tiny: SoftRas fwd+bwd 256x256, UV sphere 280 faces, 2 images/GPU (smoke only)"),
+    # BASELINE.json configs[3]: NMR (dr_type='n3mr') fwd+bwd, fill_back doubles the faces, texture_size 2
+    "c4": (39200, 1024, 16, "C4: NMR (n3mr) fwd+bwd 1024x1024, UV sphere 39200 faces (78400 with fill_back), ts=2, 16 images/GPU"),
 }
 README_39K_MS = 35.5  # Jrender SoftRas 39k faces, 1024^2, hardware/batch unstated
 
@@ -299,15 +301,15 @@ def run_ours(args, rank, world, local_rank):
     # ---- optional all-gather of the output images, reported separately
     gather_ms = None
     if world > 1:
+        from jrender_b200.distributed import all_gather_images
         img = step().detach()
-        out = torch.empty((bpg * world,) + tuple(img.shape[1:]), dtype=img.dtype, device=dev)
         for _ in range(2):
-            dist.all_gather_into_tensor(out, img)
+            out = all_gather_images(img, batch_size=bpg * world)
         barrier()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record()
         for _ in range(5):
-            dist.all_gather_into_tensor(out, img)
+            out = all_gather_images(img, batch_size=bpg * world)
         g1.record()
         barrier()
         tg = torch.tensor([g0.elapsed_time(g1) / 5], dtype=torch.float64, device=dev)
@@ -362,6 +364,74 @@ def run_ours(args, rank, world, local_rank):
     print(json.dumps(line), flush=True)
 
 
+def run_nmr(args, rank, world, local_rank):
+    """Secondary workload (not the headline metric): NMR forward + backward, BASELINE config C4."""
+    import ctypes as C
+    import torch
+    from jrender_b200 import _lib
+    from jrender_b200.n3mr import RasterizeFunction
+    from tests.util import nmr_scene
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    L = _lib.lib()
+    nf, H, bpg, desc = WORKLOADS[args.workload]
+    faces_h, tex_h = nmr_scene(nf, batch=1, ts=2)
+    # one mesh, bpg cameras: rotate the azimuth per image like build_inputs does for SoftRas
+    from jrender_b200 import workloads as wl
+    v, f = wl.sphere_by_faces(nf)
+    eyes = np.asarray([wl.get_points_from_angles(2.732, 30.0, 360.0 * (rank * bpg + b) / (bpg * world)) for b in range(bpg)], np.float32)
+    cam = wl.perspective(wl.look_at(np.repeat(v[None], bpg, 0), eyes), 30.0)
+    fv = wl.face_vertices(cam, f)
+    faces_h = np.ascontiguousarray(np.concatenate([fv, fv[:, :, ::-1]], 1))
+    tex_h = np.ascontiguousarray(np.repeat(tex_h, bpg, 0))
+    faces = torch.from_numpy(faces_h).to(dev).requires_grad_(True)
+    tex = torch.from_numpy(tex_h).to(dev).requires_grad_(True)
+    g = torch.rand((bpg, H, H, 3), device=dev) * 2 - 1
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+
+    def step():
+        faces.grad = None
+        tex.grad = None
+        rgb, _, _ = RasterizeFunction(H, 0.1, 100.0, 1e-3, (0, 0, 0), True, False, False)(faces, tex)
+        rgb.backward(g)
+    for _ in range(max(3, args.warmup)):
+        step()
+    torch.cuda.synchronize(dev)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    l0 = L.b200r_launch_count()
+    for a, b in ev:
+        flush.fill_(1.0)
+        a.record(); step(); b.record()
+    torch.cuda.synchronize(dev)
+    launches = L.b200r_launch_count() - l0
+    ms = [a.elapsed_time(b) for a, b in ev]
+    L.b200r_profile_reset(); L.b200r_profile_enable(1)
+    for _ in range(3):
+        flush.fill_(1.0); step()
+    torch.cuda.synchronize(dev); L.b200r_profile_enable(0)
+    kern = {}
+    for kid, name in [(5, "k_nmr_setup"), (1, "k_coarse_bin"), (4, "k_tile_order"), (6, "k_nmr_forward"),
+                      (7, "k_nmr_backward_pixel_map"), (8, "k_nmr_backward_maps")]:
+        t, n = C.c_double(0), C.c_longlong(0)
+        L.b200r_profile_read(kid, C.byref(t), C.byref(n))
+        kern[name] = {"avg_ms": t.value / max(1, n.value), "launches_per_step": n.value / 3}
+    if rank != 0:
+        return
+    nf2, ts, P = 2 * nf, 2, H * H
+    alg = bpg * (36 * P + 2 * (36 + 12 * ts ** 3) * nf2)   # BASELINE.md section 4
+    peak, src = peaks()
+    tot = float(np.sum(ms))
+    print(json.dumps({
+        "metric": "nmr_fwd_bwd_frames_per_s_1024px_39k_faces", "value": bpg * args.steps / (tot / 1000.0), "unit": "frames/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": tot / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc, "mode": "rgb", "texture_size": ts, "l2": "256 MiB flush between steps"},
+        "step_ms": {"min": float(np.min(ms)), "median": float(np.median(ms)), "max": float(np.max(ms))},
+        "gpu_launches": int(launches), "kernels": kern,
+        "roofline_step": {"algorithmic_bytes_per_step": int(alg), "achieved_gbs": alg / (tot / args.steps / 1000.0) / 1e9,
+                          "frac": alg / (tot / args.steps / 1000.0) / 1e9 / peak, "peak_source": src}}), flush=True)
+
+
 def main():
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -376,7 +446,10 @@ def main():
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:
-        run_ours(args, rank, world, local_rank)
+        if args.workload == "c4":
+            run_nmr(args, rank, world, local_rank)
+        else:
+            run_ours(args, rank, world, local_rank)
     finally:
         if world > 1:
             import torch.distributed as dist

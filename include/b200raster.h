@@ -134,10 +134,13 @@ B200R_API int b200r_nmr_backward(const float* faces, const int32_t* face_index_m
  * (bench.py reports the delta over the timed region as "gpu_launches"). */
 B200R_API unsigned long long b200r_launch_count(void);
 
-/* Tuning knobs (process-wide; results are identical for every setting, only speed changes):
+/* Tuning knobs (process-wide; results are identical for every setting except softras_exact_tail):
  *   "softras_fwd_variant"    0 = warp-uniform face loop, 1 = per-lane face lists (default)
  *   "softras_fwd_persistent" 0 = one CTA per tile, 1 = persistent grid + tile queue (default)
  *   "softras_fwd_warps"      warps per forward CTA: 8 (16x16 tiles), 2 (16x4), 1 (8x4, warp-autonomous)
+ *   "softras_exact_tail"     1 = the reference's double-precision sigmoid / alpha-product tails bit for bit;
+ *                            0 (default) = the same expressions in fp32 for the default euclidean+softmax
+ *                            mode (<= 1 ulp on D; all index / depth outputs are identical either way)
  *   "softras_bwd_variant"    0 = warp union walk + scalar atomics, 1 = per-lane walk + 16-byte atomics (default) */
 B200R_API int b200r_set_option(const char* name, int value);
 

@@ -46,7 +46,7 @@ struct SoftRasParams {
     int fntx, fnty; // forward tiles per image row / column
     int coarse_px;  // coarse bin edge in pixels (multiple of B200R_TILE)
     int ncs;        // coarse bins per image side
-    int tile_stride;  // persistent scheduler: odd stride coprime with the tile count
+    int queue_len;    // persistent scheduler: entries of tile_order (>= tiles; holes are -1)
 };
 
 // Workspace carve-up (all offsets 256-byte aligned).
@@ -89,7 +89,7 @@ static inline SoftRasWorkspace b200r_carve(void* base, int B, int nf, int image_
     off += b200r_align256((size_t)B * ncs * ncs * (size_t)nf * sizeof(int));
     w.counters = (int*)(p + off);
     off += b200r_align256(256 * sizeof(int));
-    const size_t max_tiles = (size_t)((image_size + 7) / 8) * ((image_size + 3) / 4);  // 8x4 is the smallest forward tile
+    const size_t max_tiles = (size_t)ntx * ntx * 8;  // queue slots: 8 forward tiles (8x4) per 16x16 cost tile
     w.tile_cost = (int*)(p + off);
     off += b200r_align256((size_t)B * max_tiles * sizeof(int));
     w.tile_order = (int*)(p + off);

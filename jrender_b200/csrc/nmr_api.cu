@@ -69,7 +69,8 @@ int b200r_nmr_forward(const float* faces, const float* textures, int32_t* face_i
     const int total_tiles = P.ntx * P.ntx * B;
     {
         B200rProfScope prof(B200R_K_TILE_ORDER, st);
-        k_tile_order<<<(total_tiles + 255) / 256, 256, 0, st>>>(W.tile_cost, W.counters + 64, W.counters + 128, W.tile_order, total_tiles);
+        k_tile_order<<<(total_tiles + 255) / 256, 256, 0, st>>>(W.tile_cost, W.counters + 64, W.counters + 128, W.tile_order,
+                                                                B, P.ntx, P.ntx, B200R_TILE, B200R_TILE, B200R_TILE, B200R_TILE, P.ntx, P.ntx, 1);
     }
     e = cudaGetLastError();
     if (e != cudaSuccess) return b200r_cuda_fail(e, "k_tile_order");

@@ -15,6 +15,7 @@ namespace {
 
 std::atomic<int> g_fwd_variant{1};     // 0: warp-uniform face loop, 1: per-lane face lists
 std::atomic<int> g_fwd_persistent{1};  // 0: one CTA per tile, 1: persistent grid + atomic tile queue
+std::atomic<int> g_exact_tail{0};      // 1: reference's double-precision sigmoid / alpha tails bit for bit; 0: fp32 tails (<= 1 ulp)
 std::atomic<int> g_bwd_variant{1};     // 0: warp union walk + scalar atomics, 1: per-lane walk + 16-byte vector atomics
 std::atomic<int> g_fwd_warps{1};       // warps per forward CTA: 8 (16x16 tile), 2 (16x4), 1 (8x4, warp-autonomous; default)
 }  // namespace
@@ -60,7 +61,7 @@ SoftRasParams make_params(int B, int nf, int T, int is, int K, float near_, floa
     P.fth = nw == 8 ? 16 : 4;
     P.fntx = (is + P.ftw - 1) / P.ftw;
     P.fnty = (is + P.fth - 1) / P.fth;
-    P.tile_stride = 1;
+    P.queue_len = P.fntx * P.fnty * B;  // cost tiles == forward tiles: no holes
     return P;
 }
 
@@ -74,6 +75,7 @@ int b200r_set_option(const char* name, int value) {
     if (!name) return b200r_fail(B200R_EINVAL, "b200r_set_option: NULL name");
     if (!strcmp(name, "softras_fwd_variant")) { g_fwd_variant.store(value ? 1 : 0); return 0; }
     if (!strcmp(name, "softras_fwd_persistent")) { g_fwd_persistent.store(value ? 1 : 0); return 0; }
+    if (!strcmp(name, "softras_exact_tail")) { g_exact_tail.store(value ? 1 : 0); return 0; }
     if (!strcmp(name, "softras_bwd_variant")) { g_bwd_variant.store(value ? 1 : 0); return 0; }
     if (!strcmp(name, "softras_fwd_warps")) {
         if (value != 1 && value != 2 && value != 8) return b200r_fail(B200R_EINVAL, "softras_fwd_warps must be 1, 2 or 8");
@@ -122,20 +124,23 @@ int b200r_softras_forward(const float* face_vertices, const float* textures, flo
     }
     e = cudaGetLastError();
     if (e != cudaSuccess) return b200r_cuda_fail(e, "k_coarse_bin");
+    e = cudaMemsetAsync(W.tile_order, 0xFF, sizeof(int) * (size_t)P.queue_len, st);  // holes (partial edge tiles) = -1
+    if (e != cudaSuccess) return b200r_cuda_fail(e, "memset tile_order");
     {
         const int total_tiles = P.fntx * P.fnty * B;
         B200rProfScope prof(B200R_K_TILE_ORDER, st);
-        k_tile_order<<<(total_tiles + 255) / 256, 256, 0, st>>>(W.tile_cost, W.counters + 64, W.counters + 128, W.tile_order, total_tiles);
+        k_tile_order<<<(total_tiles + 255) / 256, 256, 0, st>>>(W.tile_cost, W.counters + 64, W.counters + 128, W.tile_order,
+                                                                B, P.fntx, P.fnty, P.ftw, P.fth, P.ftw, P.fth, P.fntx, P.fnty, 1);
     }
     e = cudaGetLastError();
     if (e != cudaSuccess) return b200r_cuda_fail(e, "k_tile_order");
 
     {
-        const int variant = g_fwd_variant.load(), persistent = g_fwd_persistent.load();
+        const int variant = g_fwd_variant.load(), persistent = g_fwd_persistent.load(), exact = g_exact_tail.load();
         const int nw = g_fwd_warps.load();
-        if (nw == 1) e = b200r_launch_forward_nw1(P, W, textures, soft_colors, aggrs_info, faces_id_buffer, variant, persistent, st);
-        else if (nw == 2) e = b200r_launch_forward_nw2(P, W, textures, soft_colors, aggrs_info, faces_id_buffer, variant, persistent, st);
-        else e = b200r_launch_forward_nw8(P, W, textures, soft_colors, aggrs_info, faces_id_buffer, variant, persistent, st);
+        if (nw == 1) e = b200r_launch_forward_nw1(P, W, textures, soft_colors, aggrs_info, faces_id_buffer, variant, persistent, exact, st);
+        else if (nw == 2) e = b200r_launch_forward_nw2(P, W, textures, soft_colors, aggrs_info, faces_id_buffer, variant, persistent, exact, st);
+        else e = b200r_launch_forward_nw8(P, W, textures, soft_colors, aggrs_info, faces_id_buffer, variant, persistent, exact, st);
     }
     if (e != cudaSuccess) return b200r_cuda_fail(e, "k_softras_forward");
     return 0;
@@ -159,7 +164,7 @@ int b200r_softras_backward(const float* face_vertices, const float* textures, co
                                         dist_func, rgb_func, alpha_func, texture_type, double_side);
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e = b200r_launch_backward(P, W, textures, soft_colors, aggrs_info, faces_id_buffer, grad_soft_colors,
-                                          grad_face_vertices, grad_textures, g_bwd_variant.load(), st);
+                                          grad_face_vertices, grad_textures, g_bwd_variant.load(), g_exact_tail.load(), st);
     if (e != cudaSuccess) return b200r_cuda_fail(e, "k_softras_backward");
     return 0;
 }

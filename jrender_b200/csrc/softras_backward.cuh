@@ -40,7 +40,7 @@ struct BwdPixel {
 // Gradient contribution of one (pixel, face) pair: gv[k*3+l] = d/d vertex k coord l; gt = texture
 // gradient (T == 1 surface: gt[0..2]; vertex: gt[j*3+k]).  For surface textures with T > 1 the hit
 // texel index is returned in texel_out and gt[0..2] holds its gradient.  (:1240-1358)
-template <int DIST, int RGB>
+template <int DIST, int RGB, bool EXACT>
 __device__ __forceinline__ void pair_gradient(const FaceRec* rec, int fn, const BwdPixel& px, const SoftRasParams& P,
                                               const DivConst& dc, float nmf, float r_nmf, bool s_nmf,
                                               const float* __restrict__ tex, float gv[9], float gt[9], int& texel_out) {
@@ -56,11 +56,11 @@ __device__ __forceinline__ void pair_gradient(const FaceRec* rec, int fn, const 
     } else if (DIST == 1) {
         dis = barycentric_p2f_distance(w);
         t[0] = w[0]; t[1] = w[1]; t[2] = w[2];
-        soft_fragment = sigmoid_from_negarg(dc.by_sigma(-dis));
+        soft_fragment = sigmoid_from_negarg<EXACT>(dc.by_sigma(-dis));
     } else {
         sign = euclidean_p2f_distance(dis_x, dis_y, t, w, rec, xp, yp);
         dis = dis_x * dis_x + dis_y * dis_y;
-        soft_fragment = sigmoid_from_negarg(dc.by_sigma(-sign * dis));
+        soft_fragment = sigmoid_from_negarg<EXACT>(dc.by_sigma(-sign * dis));
     }
 
     float C_grad_xy = 0.f;
@@ -70,15 +70,18 @@ __device__ __forceinline__ void pair_gradient(const FaceRec* rec, int fn, const 
     } else if (P.alpha_func == 2) {
         // (float)((double)g_a * ((double)(1 - alpha_out) / max((double)(1 - D), 1e-6)))  (:1289)
         const float omd = 1.f - soft_fragment;
-        const double den = fmax(midrange(omd) ? f2d_mid(omd) : (double)omd, 1e-6);
-        const double prod = px.d_galpha * (px.d_one_minus_alpha / den);
-        C_grad_xy_alpha = d_midrange(prod) ? d2f_mid(prod) : (float)prod;
+        if (EXACT) {
+            const double den = fmax(midrange(omd) ? f2d_mid(omd) : (double)omd, 1e-6);
+            const double prod = px.d_galpha * (px.d_one_minus_alpha / den);
+            C_grad_xy_alpha = d_midrange(prod) ? d2f_mid(prod) : (float)prod;
+        } else {
+            C_grad_xy_alpha = C_grad_xy_alpha * ((1.f - px.oc[3]) / fmaxf(omd, 1e-6f));
+        }
     }
     C_grad_xy += C_grad_xy_alpha;
 
     const float w0[3] = {w[0], w[1], w[2]};
-    barycentric_clip(w);
-    const float zp = interp_z(w, rec);
+    const float zp = clip_and_z(w, rec);
 
     if (RGB == 0) {
         if ((float)fn == px.softmax_max) {  // :1300 (int vs float compare, Q10)
@@ -182,7 +185,7 @@ __device__ __forceinline__ void load_pixel(BwdPixel& px, const float* __restrict
 }
 
 // ---------------------------------------------------------------- VARIANT 1: per-lane walk + vector atomics
-template <int DIST, int RGB>
+template <int DIST, int RGB, bool EXACT>
 __global__ void __launch_bounds__(B200R_TILE_THREADS, 2)
 k_softras_backward_lane(const SoftRasParams P, const FaceRec* __restrict__ recs, const float* __restrict__ textures,
                         const float* __restrict__ soft_colors, const float* __restrict__ aggrs_info,
@@ -218,11 +221,16 @@ k_softras_backward_lane(const SoftRasParams P, const FaceRec* __restrict__ recs,
 
     for (int m = 0; m < K && fn >= 0; m++) {
         const int fn_next = (m + 1 < K) ? __ldg(src + (size_t)(m + 1) * npix) : -1;  // prefetch
+        if (fn_next >= 0) {  // pull the next face's record (two 128-byte lines) towards L1 behind this pair's math
+            const char* nr = reinterpret_cast<const char*>(brecs + fn_next);
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(nr));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(nr + 128));
+        }
         const FaceRec* rec = brecs + fn;
         float gv[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         float gt[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         int texel;
-        pair_gradient<DIST, RGB>(rec, fn, px, P, dc, nmf, r_nmf, s_nmf, btex + (size_t)fn * T * 3, gv, gt, texel);
+        pair_gradient<DIST, RGB, EXACT>(rec, fn, px, P, dc, nmf, r_nmf, s_nmf, btex + (size_t)fn * T * 3, gv, gt, texel);
         float4* a = reinterpret_cast<float4*>(bacc + (size_t)fn * 12);
         atomicAdd(a + 0, make_float4(gv[0], gv[1], gv[2], gv[3]));
         atomicAdd(a + 1, make_float4(gv[4], gv[5], gv[6], gv[7]));
@@ -333,7 +341,7 @@ k_softras_backward(const SoftRasParams P, const FaceRec* __restrict__ recs, cons
         float gt[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // T==1: [k]; vertex: [j*3+k]
         if (mine) {
             int texel;
-            pair_gradient<DIST, RGB>(wrec, fn, px, P, dc, nmf, r_nmf, s_nmf, btex + (size_t)fn * T * 3, gv, gt, texel);
+            pair_gradient<DIST, RGB, true>(wrec, fn, px, P, dc, nmf, r_nmf, s_nmf, btex + (size_t)fn * T * 3, gv, gt, texel);
             if (RGB != 2 && P.tex_type == 0 && T > 1) {  // per-lane texel: scalar atomics, not reduced
 #pragma unroll
                 for (int k = 0; k < 3; k++) atomicAdd(bgt + ((size_t)fn * T + texel) * 3 + k, gt[k]);

@@ -74,7 +74,7 @@ struct PixState {
 
 // The reference's per-face loop body (:318-420) for one (pixel, face) pair whose pixel is
 // inside the face's check_border rectangle.
-template <int DIST, int RGB, int NT>
+template <int DIST, int RGB, int NT, bool EXACT>
 __device__ __forceinline__ void shade_face(const FaceRec* rec, PixState& st, const SoftRasParams& P, const DivConst& dc,
                                            float xp, float yp, float threshold, float* s_qz, int* s_qid, int tid,
                                            const float* __restrict__ btex) {
@@ -88,13 +88,13 @@ __device__ __forceinline__ void shade_face(const FaceRec* rec, PixState& st, con
     } else if (DIST == 1) {
         const float dis = barycentric_p2f_distance(w);
         if (-dis >= threshold) return;  // :337
-        soft_fragment = sigmoid_from_negarg(dc.by_sigma(-dis));
+        soft_fragment = sigmoid_from_negarg<EXACT>(dc.by_sigma(-dis));
     } else {
         float dis_x, dis_y, t[3];
         const float sign = euclidean_p2f_distance(dis_x, dis_y, t, w, rec, xp, yp);
         const float dis = dis_x * dis_x + dis_y * dis_y;
         if (sign < 0.f && dis >= threshold) return;  // :343
-        soft_fragment = sigmoid_from_negarg(dc.by_sigma(-sign * dis));
+        soft_fragment = sigmoid_from_negarg<EXACT>(dc.by_sigma(-sign * dis));
     }
 
     // alpha aggregation, before any z test (:349-358, Q2)
@@ -103,12 +103,11 @@ __device__ __forceinline__ void shade_face(const FaceRec* rec, PixState& st, con
     } else if (P.alpha_func == 1) {
         st.alpha += soft_fragment;
     } else {
-        st.alpha = alpha_prod(st.alpha, soft_fragment);
+        st.alpha = alpha_prod_t<EXACT>(st.alpha, soft_fragment);
     }
 
     float wc[3] = {w[0], w[1], w[2]};
-    barycentric_clip(wc);
-    const float zp = interp_z(wc, rec);            // :364
+    const float zp = clip_and_z(wc, rec);          // barycentric_clip :363 + zp :364
     if (zp < P.near_ || zp > P.far_) return;       // :365
 
     const int fn = (int)rec->face_id;
@@ -163,7 +162,7 @@ __device__ __forceinline__ bool pixel_in_rect(const FaceRec* rec, int px, int ro
     return (uint32_t)(px - (int)x0) <= (rx >> 16) - x0 && (uint32_t)(row - (int)r0) <= (rr >> 16) - r0;
 }
 
-template <int DIST, int RGB, int VARIANT, int WX, int WY>
+template <int DIST, int RGB, int VARIANT, int WX, int WY, bool EXACT>
 __global__ void __launch_bounds__(32 * WX * WY, (WX * WY >= 8) ? 2 : ((WX * WY >= 2) ? 8 : 16))
 k_softras_forward(const SoftRasParams P, const FaceRec* __restrict__ recs, const uint2* __restrict__ rects,
                   const int* __restrict__ coarse_cnt, const int* __restrict__ coarse_ids,
@@ -181,7 +180,6 @@ k_softras_forward(const SoftRasParams P, const FaceRec* __restrict__ recs, const
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int is = P.is, nf = P.nf, K = P.K;
     const int tiles_per_image = P.fntx * P.fnty;
-    const int total_tiles = tiles_per_image * P.B;
     const int lx = (warp % WX) * 8 + (lane & 7), ly = (warp / WX) * 4 + (lane >> 3);
     const float threshold = P.dist_eps * P.sigma;  // :289
     const size_t npix = (size_t)is * is;
@@ -206,8 +204,9 @@ k_softras_forward(const SoftRasParams P, const FaceRec* __restrict__ recs, const
                 __syncthreads();
                 q = S.s_tile;
             }
-            if (q >= total_tiles) break;
+            if (q >= P.queue_len) break;
             t = __ldg(tile_order + q);  // most expensive tiles first (k_tile_order)
+            if (t < 0) continue;        // hole: partial cost tile at the image edge
         }
         const int b = t / tiles_per_image;
         const int tt = t - b * tiles_per_image;
@@ -293,7 +292,7 @@ k_softras_forward(const SoftRasParams P, const FaceRec* __restrict__ recs, const
                     for (int it = 0; it < wcnt; it++) {
                         const FaceRec* rec = &S.rec[S.wlist[warp][it]].r;
                         if (!pixel_in_rect(rec, px, row)) continue;
-                        shade_face<DIST, RGB, NT>(rec, st, P, dc, xp, yp, threshold, s_qz, s_qid, tid, btex);
+                        shade_face<DIST, RGB, NT, EXACT>(rec, st, P, dc, xp, yp, threshold, s_qz, s_qid, tid, btex);
                     }
                 } else {
                     // ---- each lane compacts its own list, then lanes walk private lists
@@ -309,7 +308,7 @@ k_softras_forward(const SoftRasParams P, const FaceRec* __restrict__ recs, const
                     for (int i = 0; i < maxcnt; i++) {
                         if (i < cnt) {
                             const FaceRec* rec = &S.rec[s_plist[i * NT + tid]].r;
-                            shade_face<DIST, RGB, NT>(rec, st, P, dc, xp, yp, threshold, s_qz, s_qid, tid, btex);
+                            shade_face<DIST, RGB, NT, EXACT>(rec, st, P, dc, xp, yp, threshold, s_qz, s_qid, tid, btex);
                         }
                     }
                 }

@@ -8,7 +8,7 @@
 using namespace b200r;
 
 namespace {
-template <int DIST, int RGB, int VARIANT>
+template <int DIST, int RGB, int VARIANT, bool EXACT>
 cudaError_t launch_v(const SoftRasParams& P, const SoftRasWorkspace& W, const float* textures, float* soft_colors,
                      float* aggrs_info, int32_t* ids, int persistent, cudaStream_t st) {
     constexpr int WX = 2, WY = 4, NW = WX * WY, NT = 32 * NW;
@@ -17,10 +17,10 @@ cudaError_t launch_v(const SoftRasParams& P, const SoftRasWorkspace& W, const fl
     static std::atomic<size_t> cfg_smem{0};
     static std::atomic<int> cfg_occ{0};
     if (cfg_smem.load() != smem) {
-        cudaError_t e = cudaFuncSetAttribute(k_softras_forward<DIST, RGB, VARIANT, WX, WY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(k_softras_forward<DIST, RGB, VARIANT, WX, WY, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         int occ = 1;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_softras_forward<DIST, RGB, VARIANT, WX, WY>, NT, smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_softras_forward<DIST, RGB, VARIANT, WX, WY, EXACT>, NT, smem);
         if (e != cudaSuccess) return e;
         cfg_occ.store(occ < 1 ? 1 : occ);
         cfg_smem.store(smem);
@@ -36,7 +36,7 @@ cudaError_t launch_v(const SoftRasParams& P, const SoftRasWorkspace& W, const fl
     }
     {
         B200rProfScope prof(B200R_K_SOFTRAS_FWD, st);
-        k_softras_forward<DIST, RGB, VARIANT, WX, WY><<<grid, NT, smem, st>>>(
+        k_softras_forward<DIST, RGB, VARIANT, WX, WY, EXACT><<<grid, NT, smem, st>>>(
             P, W.recs, W.rects, W.coarse_cnt, W.coarse_ids, textures, soft_colors, aggrs_info, ids, counter, W.tile_order);
     }
     return cudaGetLastError();
@@ -44,9 +44,9 @@ cudaError_t launch_v(const SoftRasParams& P, const SoftRasWorkspace& W, const fl
 }  // namespace
 
 cudaError_t b200r_launch_forward_nw8(const SoftRasParams& P, const SoftRasWorkspace& W, const float* textures, float* soft_colors,
-                                     float* aggrs_info, int32_t* ids, int variant, int persistent, cudaStream_t st) {
+                                     float* aggrs_info, int32_t* ids, int variant, int persistent, int exact, cudaStream_t st) {
     cudaError_t e = cudaSuccess;
-    if (variant == 0) { B200R_DISPATCH_DIST_RGB((e = launch_v<D, R, 0>(P, W, textures, soft_colors, aggrs_info, ids, persistent, st))) }
-    else { B200R_DISPATCH_DIST_RGB((e = launch_v<D, R, 1>(P, W, textures, soft_colors, aggrs_info, ids, persistent, st))) }
+    if (variant == 0) { B200R_DISPATCH_DIST_RGB((e = (D == 2 && R == 1 && !exact) ? launch_v<D, R, 0, (D != 2 || R != 1)>(P, W, textures, soft_colors, aggrs_info, ids, persistent, st) : launch_v<D, R, 0, true>(P, W, textures, soft_colors, aggrs_info, ids, persistent, st))) }
+    else { B200R_DISPATCH_DIST_RGB((e = (D == 2 && R == 1 && !exact) ? launch_v<D, R, 1, (D != 2 || R != 1)>(P, W, textures, soft_colors, aggrs_info, ids, persistent, st) : launch_v<D, R, 1, true>(P, W, textures, soft_colors, aggrs_info, ids, persistent, st))) }
     return e;
 }

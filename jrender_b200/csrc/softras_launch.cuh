@@ -8,15 +8,15 @@
 
 int b200r_sm_count();
 cudaError_t b200r_launch_forward_nw8(const SoftRasParams& P, const SoftRasWorkspace& W, const float* textures, float* soft_colors,
-                                     float* aggrs_info, int32_t* ids, int variant, int persistent, cudaStream_t st);
+                                     float* aggrs_info, int32_t* ids, int variant, int persistent, int exact, cudaStream_t st);
 cudaError_t b200r_launch_forward_nw2(const SoftRasParams& P, const SoftRasWorkspace& W, const float* textures, float* soft_colors,
-                                     float* aggrs_info, int32_t* ids, int variant, int persistent, cudaStream_t st);
+                                     float* aggrs_info, int32_t* ids, int variant, int persistent, int exact, cudaStream_t st);
 cudaError_t b200r_launch_forward_nw1(const SoftRasParams& P, const SoftRasWorkspace& W, const float* textures, float* soft_colors,
-                                     float* aggrs_info, int32_t* ids, int variant, int persistent, cudaStream_t st);
+                                     float* aggrs_info, int32_t* ids, int variant, int persistent, int exact, cudaStream_t st);
 cudaError_t b200r_launch_backward(const SoftRasParams& P, const SoftRasWorkspace& W, const float* textures,
                                   const float* soft_colors, const float* aggrs_info, const int32_t* ids,
                                   const float* grad_soft_colors, float* grad_faces, float* grad_textures, int variant,
-                                  cudaStream_t st);
+                                  int exact, cudaStream_t st);
 
 #define B200R_DISPATCH_DIST_RGB(CALL)                               \
     switch (P.dist_func * 3 + P.rgb_func) {                         \

@@ -41,25 +41,48 @@ __device__ __forceinline__ bool check_pixel_inside(const float w[3]) {
     return w[0] <= 1.f && w[0] >= 0.f && w[1] <= 1.f && w[1] >= 0.f && w[2] <= 1.f && w[2] >= 0.f;
 }
 
-// :49-54  (max(min(w,1.),0.) and max(sum,1e-5) are exact in fp32, see header comment)
-__device__ __forceinline__ void barycentric_clip(float w[3]) {
+// Unchecked Markstein step: correctly rounded a / b when the caller has established that
+// b is midrange and a is zero or midrange (exact_math.cuh explains the sequence).
+__device__ __forceinline__ float div_nocheck(float a, float b, float r) {
+    const float q = a * r;
+    const float rem = __fmaf_rn(q, -b, a);
+    return __fmaf_rn(r, rem, q);
+}
+
+// barycentric_clip (:49-54) followed by zp = 1. / (w0/z0 + w1/z1 + w2/z2) (:364, :1296).
+// max(min(w,1.),0.) and max(sum,1e-5) are exact in fp32 (see header comment).  The six divisions
+// share ONE range check: the clamped weights lie in [0, 1], w_sum in [1e-5, 3], so if every
+// weight is 0 or >= 2^-58 (and the face's z are midrange, flag bits 4-6) all numerators stay
+// inside fast_div's safe range before and after the normalisation; otherwise the individually
+// checked path runs.  Zero numerators are exact in the unchecked sequence because they are +0.
+__device__ __forceinline__ float clip_and_z(float w[3], const FaceRec* rec) {
 #pragma unroll
     for (int k = 0; k < 3; k++) w[k] = fmaxf(fminf(w[k], 1.f), 0.f);
     const float w_sum = fmaxf(w[0] + w[1] + w[2], 1e-5f);
-    if (w_sum != 1.f) {  // x / 1 == x exactly
+    const uint32_t fl = rec->flags;
+    const float tiny = 3.4694469519536142e-18f;  // 2^-58
+    const bool ok = ((fl & 0x70u) == 0x70u) && (w[0] == 0.f || w[0] >= tiny) && (w[1] == 0.f || w[1] >= tiny) &&
+                    (w[2] == 0.f || w[2] >= tiny);
+    if (ok) {
+        if (w_sum != 1.f) {  // x / 1 == x exactly
+            const float r = rcp_refined(w_sum);
+#pragma unroll
+            for (int k = 0; k < 3; k++) w[k] = div_nocheck(w[k], w_sum, r);
+        }
+        const float a = div_nocheck(w[0], rec->v[2], rec->rz[0]);
+        const float b = div_nocheck(w[1], rec->v[5], rec->rz[1]);
+        const float c = div_nocheck(w[2], rec->v[8], rec->rz[2]);
+        return 1.f / (a + b + c);
+    }
+    if (w_sum != 1.f) {
         const float r = rcp_refined(w_sum);
         const bool safe = midrange(w_sum);
 #pragma unroll
         for (int k = 0; k < 3; k++) w[k] = fast_div(w[k], w_sum, r, safe);
     }
-}
-
-// zp = 1. / (w0/z0 + w1/z1 + w2/z2)   (:364, :1296)
-__device__ __forceinline__ float interp_z(const float wc[3], const FaceRec* rec) {
-    const uint32_t fl = rec->flags;
-    const float a = fast_div(wc[0], rec->v[2], rec->rz[0], (fl & 16u) != 0);
-    const float b = fast_div(wc[1], rec->v[5], rec->rz[1], (fl & 32u) != 0);
-    const float c = fast_div(wc[2], rec->v[8], rec->rz[2], (fl & 64u) != 0);
+    const float a = fast_div(w[0], rec->v[2], rec->rz[0], (fl & 16u) != 0);
+    const float b = fast_div(w[1], rec->v[5], rec->rz[1], (fl & 32u) != 0);
+    const float c = fast_div(w[2], rec->v[8], rec->rz[2], (fl & 64u) != 0);
     return 1.f / (a + b + c);
 }
 
@@ -146,8 +169,23 @@ __device__ __forceinline__ float barycentric_p2f_distance(const float w[3]) {
     return dis;
 }
 
-// `1. / (1. + exp(x))` with x already = -sign*dis/sigma  (:338, :344)
-__device__ __forceinline__ float sigmoid_from_negarg(float x) { return sigmoid_tail(expf(x)); }
+// `1. / (1. + exp(x))` with x already = -sign*dis/sigma  (:338, :344).
+// EXACT: the reference's double-precision tail, bit for bit.  !EXACT: the same expression in fp32
+// (two roundings instead of one: <= 1 ulp from the exact tail, 6e-8 relative) -- about 20 fewer
+// instructions per (pixel, face) pair and no FP64 pipe.  D feeds no discrete decision except the
+// `D > 0.5` of hard alpha, so every index / depth output stays bit-identical either way.
+template <bool EXACT>
+__device__ __forceinline__ float sigmoid_from_negarg(float x) {
+    if (EXACT) return sigmoid_tail(expf(x));
+    return 1.f / (1.f + expf(x));
+}
+
+// alpha "prod" aggregation  alpha *= 1. - D  (:357); see sigmoid_from_negarg for EXACT.
+template <bool EXACT>
+__device__ __forceinline__ float alpha_prod_t(float alpha, float D) {
+    if (EXACT) return alpha_prod(alpha, D);
+    return alpha * (1.f - D);
+}
 
 // surface texel index of forward_sample_texture / backward_sample_texture (:159-166, :1157-1168).
 // R == 1: both branches of the reference give texel 0 (w is clipped to >= 0).

@@ -245,20 +245,39 @@ static __global__ void __launch_bounds__(256) k_coarse_bin(const uint2* __restri
     }
 }
 
-// Orders all tiles by descending cost bucket (longest-processing-time-first for the persistent
-// raster grid).  hist[] must be complete (previous kernel); cursor[] zeroed.
+// Orders all forward tiles by descending cost bucket (longest-processing-time-first for the
+// persistent raster grid).  Costs are kept per (ctw x cth) "cost tile" (k_coarse_bin); a forward
+// tile of (tw x th) pixels inherits the bucket of the cost tile that contains it.  hist[] counts
+// COST tiles per bucket (complete after k_coarse_bin); `per` = forward tiles per cost tile (1 when
+// the two tilings coincide, which is how the SoftRas forward runs: a silhouette tile whose only
+// busy 8x4 block is long-running must not hide behind its cheap 16x16 parent).  Block-aggregated
+// reservation: one global atomic per (CTA, bucket) instead of one per tile.
 static __global__ void __launch_bounds__(256) k_tile_order(const int* __restrict__ tile_cost, const int* __restrict__ hist,
-                                                    int* __restrict__ cursor, int* __restrict__ tile_order, int total) {
+                                                           int* __restrict__ cursor, int* __restrict__ tile_order,
+                                                           int B, int fntx, int fnty, int tw, int th, int ctw, int cth, int cntx, int cnty, int per) {
     __shared__ int s_start[B200R_COST_BUCKETS];
+    __shared__ int s_cnt[B200R_COST_BUCKETS];
+    __shared__ int s_base[B200R_COST_BUCKETS];
+    if (threadIdx.x < B200R_COST_BUCKETS) s_cnt[threadIdx.x] = 0;
     if (threadIdx.x == 0) {
         int acc = 0;
-        for (int k = B200R_COST_BUCKETS - 1; k >= 0; k--) { s_start[k] = acc; acc += hist[k]; }
+        for (int k = B200R_COST_BUCKETS - 1; k >= 0; k--) { s_start[k] = acc; acc += hist[k] * per; }
     }
     __syncthreads();
+    const int total = B * fntx * fnty;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= total) return;
-    const int bkt = cost_bucket(tile_cost[t]);
-    tile_order[s_start[bkt] + atomicAdd(&cursor[bkt], 1)] = t;
+    int bkt = 0, lrank = 0;
+    if (t < total) {
+        const int b = t / (fntx * fnty), tt = t % (fntx * fnty);
+        const int cx = (tt % fntx) * tw / ctw, cy = (tt / fntx) * th / cth;
+        bkt = cost_bucket(tile_cost[(size_t)b * cntx * cnty + cy * cntx + cx]);
+        lrank = atomicAdd(&s_cnt[bkt], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x < B200R_COST_BUCKETS && s_cnt[threadIdx.x] > 0)
+        s_base[threadIdx.x] = atomicAdd(&cursor[threadIdx.x], s_cnt[threadIdx.x]);
+    __syncthreads();
+    if (t < total) tile_order[s_start[bkt] + s_base[bkt] + lrank] = t;
 }
 
 }  // namespace b200r

@@ -247,3 +247,24 @@ def test_backward_variants_agree_with_oracle(cuda_device, mode):
             check(fv5, tex5, osr.Params(image_size=64, aggr_func_rgb=mode.get("aggr_func_rgb", "softmax")))
     finally:
         _lib.set_option("softras_bwd_variant", 1)
+
+
+def test_exact_tail_option(cuda_device):
+    """softras_exact_tail=1 evaluates the sigmoid / alpha-product tails in double like the reference;
+    the default fp32 tails may move D by <= 1 ulp.  Index / depth outputs must be identical, colours
+    agree to a few 1e-7, and both settings satisfy the oracle tolerances."""
+    from jrender_b200 import _lib
+    fv, tex = wl.make_scene(3280, batch=1)
+    P = osr.Params(image_size=192)
+    g = np.random.default_rng(2).uniform(-1, 1, (1, 4, 192, 192)).astype(np.float32)
+    try:
+        _lib.set_option("softras_exact_tail", 1)
+        _, exact = check(fv, tex, P)
+        _lib.set_option("softras_exact_tail", 0)
+        _, fast = check(fv, tex, P)
+    finally:
+        _lib.set_option("softras_exact_tail", 0)
+    assert np.array_equal(exact["faces_id_buffer"], fast["faces_id_buffer"])
+    assert np.array_equal(exact["aggrs_info"][:, 1], fast["aggrs_info"][:, 1])
+    assert np.abs(exact["soft_colors"] - fast["soft_colors"]).max() <= 5e-7
+    assert np.abs(exact["grad_faces"] - fast["grad_faces"]).max() <= GRAD_RTOL * np.abs(exact["grad_faces"]).max()
