@@ -120,13 +120,17 @@ B200R_API int b200r_nmr_forward(const float* faces, const float* textures, int32
                                 const float* background_rgb, int return_rgb, int return_alpha,
                                 int return_depth, void* stream);
 /* grad_faces [B,nf,3,3] and grad_textures [B,nf,ts,ts,ts,3] are overwritten.  Sub-ops follow
- * n3mr.py:29-67: pixel-map gradient (x,y) -> texture gradient -> depth gradient accumulated in place. */
+ * n3mr.py:29-67: pixel-map gradient (x,y) -> texture gradient -> depth gradient accumulated in place.
+ * `scratch` (b200r_nmr_backward_scratch_bytes) holds the packed row-/column-major pixel records the
+ * pixel-map gradient scans; it is only needed when return_rgb or return_alpha. */
+B200R_API size_t b200r_nmr_backward_scratch_bytes(int batch_size, int image_size);
 B200R_API int b200r_nmr_backward(const float* faces, const int32_t* face_index_map, const float* weight_map,
                                  const float* depth_map, const float* rgb_map, const float* alpha_map,
                                  const int32_t* sampling_index_map, const float* sampling_weight_map,
                                  const float* face_inv_map, const float* grad_rgb_map,
                                  const float* grad_alpha_map, const float* grad_depth_map, float* grad_faces,
-                                 float* grad_textures, int batch_size, int num_faces, int texture_size,
+                                 float* grad_textures, void* scratch, size_t scratch_bytes,
+                                 int batch_size, int num_faces, int texture_size,
                                  int image_size, float eps, int return_rgb, int return_alpha,
                                  int return_depth, void* stream);
 
@@ -149,7 +153,7 @@ B200R_API int b200r_set_option(const char* name, int value);
  * dominant kernel; b200r_profile_read synchronises the outstanding events. */
 enum { B200R_K_FACE_SETUP = 0, B200R_K_COARSE_BIN = 1, B200R_K_SOFTRAS_FWD = 2, B200R_K_SOFTRAS_BWD = 3,
        B200R_K_TILE_ORDER = 4, B200R_K_NMR_SETUP = 5, B200R_K_NMR_FWD = 6, B200R_K_NMR_BWD_PIXEL = 7,
-       B200R_K_NMR_BWD_MAPS = 8, B200R_K_SOFTRAS_BWD_FINALIZE = 9 };
+       B200R_K_NMR_BWD_MAPS = 8, B200R_K_SOFTRAS_BWD_FINALIZE = 9, B200R_K_NMR_PACK = 10 };
 B200R_API void b200r_profile_enable(int on);
 B200R_API void b200r_profile_reset(void);
 B200R_API int b200r_profile_read(int kernel, double* total_ms, long long* launches);

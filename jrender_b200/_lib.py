@@ -56,7 +56,9 @@ def lib():
     L.b200r_nmr_forward.restype = _I
     L.b200r_nmr_forward.argtypes = [_P] * 11 + [C.c_size_t, _I, _I, _I, _I, _F, _F, _F, _P, _I, _I, _I, _P]
     L.b200r_nmr_backward.restype = _I
-    L.b200r_nmr_backward.argtypes = [_P] * 14 + [_I, _I, _I, _I, _F, _I, _I, _I, _P]
+    L.b200r_nmr_backward.argtypes = [_P] * 15 + [C.c_size_t, _I, _I, _I, _I, _F, _I, _I, _I, _P]
+    L.b200r_nmr_backward_scratch_bytes.restype = C.c_size_t
+    L.b200r_nmr_backward_scratch_bytes.argtypes = [_I, _I]
     L.b200r_set_option.restype = _I
     L.b200r_set_option.argtypes = [C.c_char_p, _I]
     _lib = L

@@ -91,13 +91,18 @@ int b200r_nmr_forward(const float* faces, const float* textures, int32_t* face_i
     return 0;
 }
 
+size_t b200r_nmr_backward_scratch_bytes(int batch_size, int image_size) {
+    if (batch_size <= 0 || image_size <= 0) return 0;
+    return 2 * (size_t)batch_size * image_size * image_size * 32;  // row-major + column-major packed pixel records
+}
+
 int b200r_nmr_backward(const float* faces, const int32_t* face_index_map, const float* weight_map,
                        const float* depth_map, const float* rgb_map, const float* alpha_map,
                        const int32_t* sampling_index_map, const float* sampling_weight_map,
                        const float* face_inv_map, const float* grad_rgb_map, const float* grad_alpha_map,
-                       const float* grad_depth_map, float* grad_faces, float* grad_textures, int B, int nf,
-                       int texture_size, int is, float eps, int return_rgb, int return_alpha, int return_depth,
-                       void* stream) {
+                       const float* grad_depth_map, float* grad_faces, float* grad_textures, void* scratch,
+                       size_t scratch_bytes, int B, int nf, int texture_size, int is, float eps, int return_rgb,
+                       int return_alpha, int return_depth, void* stream) {
     if (B <= 0 || nf <= 0 || is <= 0) return b200r_fail(B200R_EINVAL, "b200r_nmr_backward: non-positive size");
     if (!faces || !face_index_map || !grad_faces) return b200r_fail(B200R_EINVAL, "b200r_nmr_backward: NULL pointer argument");
     if (return_rgb && (!rgb_map || !grad_rgb_map || !sampling_index_map || !sampling_weight_map || !grad_textures || texture_size <= 0))
@@ -113,10 +118,22 @@ int b200r_nmr_backward(const float* faces, const int32_t* face_index_map, const 
         if (e != cudaSuccess) return b200r_cuda_fail(e, "memset grad_textures");
     }
     if (return_rgb || return_alpha) {  // n3mr.py:150-154
+        const size_t need = b200r_nmr_backward_scratch_bytes(B, is);
+        if (!scratch || scratch_bytes < need)
+            return b200r_fail(B200R_EWORKSPACE, "b200r_nmr_backward: scratch %zu < required %zu bytes", scratch_bytes, need);
+        float4* ph = reinterpret_cast<float4*>(scratch);
+        float4* pv = ph + (size_t)B * is * is * 2;
+        {
+            B200rProfScope prof(B200R_K_NMR_PACK, st);
+            k_nmr_pack<<<dim3((is + 31) / 32, (is + 31) / 32, B), 256, 0, st>>>(rgb_map, alpha_map, grad_rgb_map, grad_alpha_map, ph, pv, is,
+                                                                              return_rgb ? 1 : 0, return_alpha ? 1 : 0);
+        }
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return b200r_cuda_fail(e, "k_nmr_pack");
         const long warps = (long)B * nf;
         B200rProfScope prof(B200R_K_NMR_BWD_PIXEL, st);
         k_nmr_backward_pixel_map<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(faces, face_index_map, rgb_map, alpha_map, grad_rgb_map,
-                                                                             grad_alpha_map, grad_faces, B, nf, is, eps,
+                                                                             grad_alpha_map, ph, pv, grad_faces, B, nf, is, eps,
                                                                              return_rgb ? 1 : 0, return_alpha ? 1 : 0);
     }
     e = cudaGetLastError();

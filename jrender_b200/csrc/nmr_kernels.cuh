@@ -307,6 +307,48 @@ k_nmr_forward(const NmrParams P, const NmrRec* __restrict__ recs, const uint2* _
     }
 }
 
+// ---------------------------------------------------------------- K9 prologue: packed pixel records
+// K9's scans read (rgb, grad_rgb, alpha, grad_alpha) of long pixel runs: along x for axis 1 and
+// along y for axis 0.  Reading four separate maps, and columns with a stride of a whole image
+// row, made the first version of the backward 20x slower than its instruction count warrants.
+// This kernel gathers the 8 floats of every pixel into one 32-byte record and writes them twice:
+// row-major (ph[b][y][x]) and column-major (pv[b][x][y]), so that both scan directions read
+// consecutive 32-byte sectors.  32x32 tile transpose through shared memory.
+__global__ void __launch_bounds__(256)
+k_nmr_pack(const float* __restrict__ rgb_map, const float* __restrict__ alpha_map, const float* __restrict__ grad_rgb_map,
+           const float* __restrict__ grad_alpha_map, float4* __restrict__ ph, float4* __restrict__ pv, int is,
+           int return_rgb, int return_alpha) {
+    __shared__ float4 s[32][33][2];
+    const int b = blockIdx.z, x0 = blockIdx.x * 32, y0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const size_t img = (size_t)b * is * is;
+    for (int r = ty; r < 32; r += 8) {
+        const int x = x0 + tx, y = y0 + r;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), c = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (x < is && y < is) {
+            const size_t i = img + (size_t)y * is + x;
+            if (return_rgb) {
+                a.x = __ldg(rgb_map + i * 3 + 0); a.y = __ldg(rgb_map + i * 3 + 1); a.z = __ldg(rgb_map + i * 3 + 2);
+                a.w = __ldg(grad_rgb_map + i * 3 + 0); c.x = __ldg(grad_rgb_map + i * 3 + 1); c.y = __ldg(grad_rgb_map + i * 3 + 2);
+            }
+            if (return_alpha) { c.z = __ldg(alpha_map + i); c.w = __ldg(grad_alpha_map + i); }
+            ph[i * 2] = a;
+            ph[i * 2 + 1] = c;
+        }
+        s[r][tx][0] = a;
+        s[r][tx][1] = c;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int x = x0 + r, y = y0 + tx;   // pv[b][x][y] <- pixel (y, x) = s[y - y0][x - x0]
+        if (x < is && y < is) {
+            const size_t j = img + (size_t)x * is + y;
+            pv[j * 2] = s[tx][r][0];
+            pv[j * 2 + 1] = s[tx][r][1];
+        }
+    }
+}
+
 // ---------------------------------------------------------------- K9: warp per (batch, face)
 __device__ __forceinline__ float warp_sum_f(float v) {
 #pragma unroll
@@ -318,6 +360,7 @@ __global__ void __launch_bounds__(256)
 k_nmr_backward_pixel_map(const float* __restrict__ faces, const int* __restrict__ face_index_map,
                          const float* __restrict__ rgb_map, const float* __restrict__ alpha_map,
                          const float* __restrict__ grad_rgb_map, const float* __restrict__ grad_alpha_map,
+                         const float4* __restrict__ ph, const float4* __restrict__ pv,
                          float* __restrict__ grad_faces, int batch_size, int num_faces, int is, float eps,
                          int return_rgb, int return_alpha) {
     const int lane = threadIdx.x & 31;
@@ -363,12 +406,15 @@ k_nmr_backward_pixel_map(const float* __restrict__ faces, const int* __restrict_
                 if (d1_in < 0 || is <= d1_in) continue;
                 if (d1_out < 0 || is <= d1_out) continue;
                 const long map_index_in = (axis == 0) ? img + (long)d1_in * is + d0 : img + (long)d0 * is + d1_in;
-                const long map_index_out = (axis == 0) ? img + (long)d1_out * is + d0 : img + (long)d0 * is + d1_out;
-                float alpha_in = 0.f, alpha_out = 0.f, rin[3] = {0.f, 0.f, 0.f}, rout[3] = {0.f, 0.f, 0.f};
-                if (return_alpha) { alpha_in = __ldg(alpha_map + map_index_in); alpha_out = __ldg(alpha_map + map_index_out); }
-                if (return_rgb) {
-#pragma unroll
-                    for (int k = 0; k < 3; k++) { rin[k] = __ldg(rgb_map + map_index_in * 3 + k); rout[k] = __ldg(rgb_map + map_index_out * 3 + k); }
+                // packed records: axis 1 scans rows of ph, axis 0 scans rows of pv; in both the
+                // record of (d0, d1) sits at img + d0 * is + d1
+                const float4* __restrict__ pk = (axis == 0) ? pv : ph;
+                float alpha_in, alpha_out, rin[3], rout[3];
+                {
+                    const float4 ia = __ldg(pk + (img + (long)d0 * is + d1_in) * 2), ic = __ldg(pk + (img + (long)d0 * is + d1_in) * 2 + 1);
+                    const float4 oa = __ldg(pk + (img + (long)d0 * is + d1_out) * 2), oc = __ldg(pk + (img + (long)d0 * is + d1_out) * 2 + 1);
+                    rin[0] = ia.x; rin[1] = ia.y; rin[2] = ia.z; alpha_in = ic.z;
+                    rout[0] = oa.x; rout[1] = oa.y; rout[2] = oa.z; alpha_out = oc.z;
                 }
                 const bool has0 = p[1][0] != d0, has1 = p[0][0] != d0;
                 const float q0 = (p[1][0] - p[0][0]) / (p[1][0] - d0);
@@ -379,12 +425,13 @@ k_nmr_backward_pixel_map(const float* __restrict__ faces, const int* __restrict_
                     const int d1_from = max(min(d1_out, d1_limit), 0);
                     const int d1_to = min(max(d1_out, d1_limit), is - 1);
                     for (int d1 = d1_from + lane; d1 <= d1_to; d1 += 32) {
-                        const long idx = (axis == 0) ? img + (long)d1 * is + d0 : img + (long)d0 * is + d1;
+                        const float4 qa = __ldg(pk + (img + (long)d0 * is + d1) * 2), qc = __ldg(pk + (img + (long)d0 * is + d1) * 2 + 1);
                         float diff_grad = 0.f;
-                        if (return_alpha) diff_grad += (__ldg(alpha_map + idx) - alpha_in) * __ldg(grad_alpha_map + idx);
+                        if (return_alpha) diff_grad += (qc.z - alpha_in) * qc.w;
                         if (return_rgb) {
-#pragma unroll
-                            for (int k = 0; k < 3; k++) diff_grad += (__ldg(rgb_map + idx * 3 + k) - rin[k]) * __ldg(grad_rgb_map + idx * 3 + k);
+                            diff_grad += (qa.x - rin[0]) * qa.w;
+                            diff_grad += (qa.y - rin[1]) * qc.x;
+                            diff_grad += (qa.z - rin[2]) * qc.y;
                         }
                         if (diff_grad <= 0.f) continue;
                         if (has0) {
@@ -412,11 +459,13 @@ k_nmr_backward_pixel_map(const float* __restrict__ faces, const int* __restrict_
                     for (int d1 = d1_from + lane; d1 <= d1_to; d1 += 32) {
                         const long idx = (axis == 0) ? img + (long)d1 * is + d0 : img + (long)d0 * is + d1;
                         if (__ldg(face_index_map + idx) != fn) continue;
+                        const float4 qa = __ldg(pk + (img + (long)d0 * is + d1) * 2), qc = __ldg(pk + (img + (long)d0 * is + d1) * 2 + 1);
                         float diff_grad = 0.f;
-                        if (return_alpha) diff_grad += (__ldg(alpha_map + idx) - alpha_out) * __ldg(grad_alpha_map + idx);
+                        if (return_alpha) diff_grad += (qc.z - alpha_out) * qc.w;
                         if (return_rgb) {
-#pragma unroll
-                            for (int k = 0; k < 3; k++) diff_grad += (__ldg(rgb_map + idx * 3 + k) - rout[k]) * __ldg(grad_rgb_map + idx * 3 + k);
+                            diff_grad += (qa.x - rout[0]) * qa.w;
+                            diff_grad += (qa.y - rout[1]) * qc.x;
+                            diff_grad += (qa.z - rout[2]) * qc.y;
                         }
                         if (diff_grad <= 0.f) continue;
                         if (has0) {

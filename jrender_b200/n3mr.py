@@ -108,10 +108,12 @@ class _RasterizeOp(torch.autograd.Function):
             g_d = prep(grad_depth_map, depth_map) if depth_req else None
             grad_faces = torch.empty_like(fc)
             grad_textures = torch.empty_like(tx) if rgb else None
+            sc_bytes = L.b200r_nmr_backward_scratch_bytes(B, H) if (rgb or alpha) else 0
+            scratch = torch.empty((sc_bytes,), dtype=torch.uint8, device=dev) if sc_bytes else None
             rc = L.b200r_nmr_backward(
                 _ptr(fc), _ptr(face_index_map), _ptr(weight_map), _ptr(depth_map), _ptr(rgb_map), _ptr(alpha_map),
                 _ptr(sidx), _ptr(swgt), _ptr(face_inv_map), _ptr(g_rgb), _ptr(g_a), _ptr(g_d),
-                _ptr(grad_faces), _ptr(grad_textures), B, nf, ts, H, ctx.eps,
+                _ptr(grad_faces), _ptr(grad_textures), _ptr(scratch), sc_bytes, B, nf, ts, H, ctx.eps,
                 int(rgb), int(alpha), int(depth_req), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
         _lib.check(rc, "b200r_nmr_backward")
         return grad_faces, grad_textures, None
