@@ -186,7 +186,7 @@ __device__ __forceinline__ void load_pixel(BwdPixel& px, const float* __restrict
 
 // ---------------------------------------------------------------- VARIANT 1: per-lane walk + vector atomics
 template <int DIST, int RGB, bool EXACT>
-__global__ void __launch_bounds__(B200R_TILE_THREADS, 2)
+__global__ void __launch_bounds__(B200R_TILE_THREADS, 3)
 k_softras_backward_lane(const SoftRasParams P, const FaceRec* __restrict__ recs, const float* __restrict__ textures,
                         const float* __restrict__ soft_colors, const float* __restrict__ aggrs_info,
                         const int* __restrict__ ids_in, const float* __restrict__ grad_soft_colors,
