@@ -42,12 +42,13 @@ template <int NW>
 struct FwdCfg {
     static constexpr int NT = 32 * NW;
     static constexpr int CHUNK = NW >= 8 ? 128 : (NW >= 2 ? 64 : 32);  // staged faces per round (index fits uint8)
+    static constexpr int UNR = NW >= 8 ? 1 : (NW >= 2 ? 2 : 4);         // coarse entries filtered per thread per pass
 };
 
 template <int NW>
 struct FwdSmem {
     FaceRecS rec[FwdCfg<NW>::CHUNK];                     // reused as the output staging area
-    int ids[FwdCfg<NW>::CHUNK + FwdCfg<NW>::NT];         // pending tile-face ids, ascending
+    int ids[FwdCfg<NW>::CHUNK + FwdCfg<NW>::UNR * FwdCfg<NW>::NT];  // pending tile-face ids, ascending
     unsigned char wlist[NW][FwdCfg<NW>::CHUNK];          // per-warp sub-list (indices into rec[])
     int s_warp[NW];
     int s_tile;
@@ -163,13 +164,13 @@ __device__ __forceinline__ bool pixel_in_rect(const FaceRec* rec, int px, int ro
 }
 
 template <int DIST, int RGB, int VARIANT, int WX, int WY, bool EXACT>
-__global__ void __launch_bounds__(32 * WX * WY, (WX * WY >= 8) ? 2 : ((WX * WY >= 2) ? 8 : 16))
+__global__ void __launch_bounds__(32 * WX * WY, (WX * WY >= 8) ? 2 : ((WX * WY >= 2) ? 8 : 20))
 k_softras_forward(const SoftRasParams P, const FaceRec* __restrict__ recs, const uint2* __restrict__ rects,
                   const int* __restrict__ coarse_cnt, const int* __restrict__ coarse_ids,
                   const float* __restrict__ textures, float* __restrict__ soft_colors,
                   float* __restrict__ aggrs_info, int* __restrict__ ids_out, int* tile_counter,
                   const int* __restrict__ tile_order) {
-    constexpr int NW = WX * WY, NT = 32 * NW, CHUNK = FwdCfg<NW>::CHUNK;
+    constexpr int NW = WX * WY, NT = 32 * NW, CHUNK = FwdCfg<NW>::CHUNK, UNR = FwdCfg<NW>::UNR;
     constexpr int TW = 8 * WX, TH = 4 * WY;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FwdSmem<NW>& S = *reinterpret_cast<FwdSmem<NW>*>(smem_raw);
@@ -242,55 +243,84 @@ k_softras_forward(const SoftRasParams P, const FaceRec* __restrict__ recs, const
         const FaceRec* brecs = recs + (size_t)b * nf;
         const float* btex = textures + (size_t)b * nf * P.T * 3;
 
-        int n_pending = 0;  // uniform across the CTA
-        for (int base = 0; base < n_coarse; base += NT) {
-            // ---- fine filter: next NT coarse entries -> S.ids (ordered)
-            {
-                const int i = base + tid;
-                int id = -1;
-                bool pass = false;
-                if (i < n_coarse) {
-                    id = __ldg(clist + i);
-                    pass = rect_overlaps(__ldg(brects + id), tx0, tx1, tr0, tr1);
-                }
-                int total;
-                const int off = n_pending + block_excl_scan<NW>(pass ? 1 : 0, S.s_warp, total);
-                if (pass) S.ids[off] = id;
-                n_pending += total;
+        int n_pending = 0, head = 0;  // pending ids live in S.ids[head, head + n_pending); uniform across the CTA
+        for (int base = 0; base < n_coarse; base += NT * UNR) {
+            // ---- leftover of the previous pass (< CHUNK <= NT entries) back to the front
+            if (head > 0) {
+                int keep = 0;
+                if (tid < n_pending) keep = S.ids[head + tid];
+                cta_sync<NW>();
+                if (tid < n_pending) S.ids[tid] = keep;
+                head = 0;
             }
-            const bool last = base + NT >= n_coarse;
-            if (n_pending < CHUNK && !last) continue;
+            // ---- fine filter: next UNR*NT coarse entries -> S.ids (ordered).  All id loads are
+            // issued before the dependent rectangle gathers so one pass costs two memory
+            // latencies, not 2*UNR.
+            {
+                int id[UNR];
+                uint2 rc[UNR];
+#pragma unroll
+                for (int u = 0; u < UNR; u++) {
+                    const int i = base + u * NT + tid;
+                    id[u] = (i < n_coarse) ? __ldg(clist + i) : -1;
+                }
+#pragma unroll
+                for (int u = 0; u < UNR; u++) rc[u] = (id[u] >= 0) ? __ldg(brects + id[u]) : make_uint2(1u, 1u);
+#pragma unroll
+                for (int u = 0; u < UNR; u++) {
+                    const bool pass = id[u] >= 0 && rect_overlaps(rc[u], tx0, tx1, tr0, tr1);
+                    int total;
+                    const int off = n_pending + block_excl_scan_flag<NW>(pass, S.s_warp, total);
+                    if (pass) S.ids[off] = id[u];
+                    n_pending += total;
+                }
+            }
+            const bool last = base + NT * UNR >= n_coarse;
 
             while (n_pending >= CHUNK || (last && n_pending > 0)) {
                 const int m = min(n_pending, CHUNK);
                 cta_sync<NW>();  // S.ids complete; previous round's readers of S.rec done
-                // ---- stage m records: 10 x uint4 per face, coalesced
-                for (int j = tid; j < m * B200R_REC_UINT4; j += NT) {
-                    const int f = j / B200R_REC_UINT4, q = j - f * B200R_REC_UINT4;
-                    reinterpret_cast<uint4*>(&S.rec[f])[q] =
-                        __ldg(reinterpret_cast<const uint4*>(brecs + S.ids[f]) + q);
+                // ---- stage m records: 10 x uint4 per face, coalesced, 5 loads in flight per thread
+                for (int j0 = 0; j0 < m * B200R_REC_UINT4; j0 += NT * 5) {
+                    uint4 v[5];
+#pragma unroll
+                    for (int u = 0; u < 5; u++) {
+                        const int j = j0 + u * NT + tid;
+                        if (j < m * B200R_REC_UINT4) {
+                            const int f = j / B200R_REC_UINT4, q = j - f * B200R_REC_UINT4;
+                            v[u] = __ldg(reinterpret_cast<const uint4*>(brecs + S.ids[head + f]) + q);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 5; u++) {
+                        const int j = j0 + u * NT + tid;
+                        if (j < m * B200R_REC_UINT4) {
+                            const int f = j / B200R_REC_UINT4, q = j - f * B200R_REC_UINT4;
+                            reinterpret_cast<uint4*>(&S.rec[f])[q] = v[u];
+                        }
+                    }
                 }
                 cta_sync<NW>();
-                // ---- shift the not-yet-staged ids to the front (through registers)
-                const int rest = n_pending - m;  // < NT
-                int keep0 = 0;
-                if (tid < rest) keep0 = S.ids[m + tid];
-                // ---- warp sub-list
+                // ---- warp sub-list (the whole round when the warp is the CTA)
                 int wcnt = 0;
-                for (int j0 = 0; j0 < m; j0 += 32) {
-                    const int j = j0 + lane;
-                    bool pass = false;
-                    if (j < m) pass = rect_overlaps(make_uint2(S.rec[j].r.rect_x, S.rec[j].r.rect_r), wx0, wx1, wr0, wr1);
-                    const unsigned bal = __ballot_sync(0xffffffffu, pass);
-                    if (pass) S.wlist[warp][wcnt + __popc(bal & ((1u << lane) - 1u))] = (unsigned char)j;
-                    wcnt += __popc(bal);
+                if (NW > 1) {
+                    for (int j0 = 0; j0 < m; j0 += 32) {
+                        const int j = j0 + lane;
+                        bool pass = false;
+                        if (j < m) pass = rect_overlaps(make_uint2(S.rec[j].r.rect_x, S.rec[j].r.rect_r), wx0, wx1, wr0, wr1);
+                        const unsigned bal = __ballot_sync(0xffffffffu, pass);
+                        if (pass) S.wlist[warp][wcnt + __popc(bal & ((1u << lane) - 1u))] = (unsigned char)j;
+                        wcnt += __popc(bal);
+                    }
+                    __syncwarp();
+                } else {
+                    wcnt = m;
                 }
-                __syncwarp();
 
                 if (VARIANT == 0) {
                     // ---- warp walks its list in lock-step
                     for (int it = 0; it < wcnt; it++) {
-                        const FaceRec* rec = &S.rec[S.wlist[warp][it]].r;
+                        const FaceRec* rec = &S.rec[NW > 1 ? (int)S.wlist[warp][it] : it].r;
                         if (!pixel_in_rect(rec, px, row)) continue;
                         shade_face<DIST, RGB, NT, EXACT>(rec, st, P, dc, xp, yp, threshold, s_qz, s_qid, tid, btex);
                     }
@@ -298,7 +328,7 @@ k_softras_forward(const SoftRasParams P, const FaceRec* __restrict__ recs, const
                     // ---- each lane compacts its own list, then lanes walk private lists
                     int cnt = 0;
                     for (int it = 0; it < wcnt; it++) {
-                        const int j = S.wlist[warp][it];
+                        const int j = NW > 1 ? (int)S.wlist[warp][it] : it;
                         if (pixel_in_rect(&S.rec[j].r, px, row)) {
                             s_plist[cnt * NT + tid] = (unsigned char)j;
                             cnt++;
@@ -312,10 +342,8 @@ k_softras_forward(const SoftRasParams P, const FaceRec* __restrict__ recs, const
                         }
                     }
                 }
-
-                cta_sync<NW>();  // everyone done reading S.ids (keep0) and S.rec
-                if (tid < rest) S.ids[tid] = keep0;
-                n_pending = rest;
+                head += m;
+                n_pending -= m;
             }
         }
 

@@ -155,6 +155,29 @@ __device__ __forceinline__ int block_excl_scan(int cnt, int* s_warp /*[NW]*/, in
     total = tot;
     return base + incl - cnt;
 }
+// Same for a 0/1 contribution: one ballot instead of a 5-step shuffle scan.
+template <int NW>
+__device__ __forceinline__ int block_excl_scan_flag(bool flag, int* s_warp /*[NW]*/, int& total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned bal = __ballot_sync(0xffffffffu, flag);
+    const int excl = __popc(bal & ((1u << lane) - 1u));
+    if (NW == 1) {
+        total = __popc(bal);
+        return excl;
+    }
+    if (lane == 0) s_warp[warp] = __popc(bal);
+    __syncthreads();
+    int base = 0, tot = 0;
+#pragma unroll
+    for (int wi = 0; wi < NW; wi++) {
+        const int v = s_warp[wi];
+        if (wi < warp) base += v;
+        tot += v;
+    }
+    __syncthreads();
+    total = tot;
+    return base + excl;
+}
 __device__ __forceinline__ int block_excl_scan_256(int cnt, int* s_warp, int& total) { return block_excl_scan<8>(cnt, s_warp, total); }
 
 // Coarse binning, tile-centric and deterministic: CTA (bin, b) scans the face rectangles of
