@@ -48,6 +48,8 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--option", action="append", default=[], metavar="NAME=VALUE",
+                    help="b200r_set_option() knob for A/B runs, e.g. --option nmr_bwd_unroll=2")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU-baseline sample time")
     return ap.parse_args()
 
@@ -445,6 +447,10 @@ def main():
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    for kv in args.option:
+        from jrender_b200 import _lib
+        name, value = kv.split("=")
+        _lib.set_option(name, int(value))
     try:
         if args.workload == "c4":
             run_nmr(args, rank, world, local_rank)

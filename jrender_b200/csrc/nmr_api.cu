@@ -132,9 +132,16 @@ int b200r_nmr_backward(const float* faces, const int32_t* face_index_map, const 
         if (e != cudaSuccess) return b200r_cuda_fail(e, "k_nmr_pack");
         const long warps = (long)B * nf;
         B200rProfScope prof(B200R_K_NMR_BWD_PIXEL, st);
-        k_nmr_backward_pixel_map<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(faces, face_index_map, rgb_map, alpha_map, grad_rgb_map,
-                                                                             grad_alpha_map, ph, pv, grad_faces, B, nf, is, eps,
-                                                                             return_rgb ? 1 : 0, return_alpha ? 1 : 0);
+#define B200R_LAUNCH_K9(U)                                                                                              \
+    k_nmr_backward_pixel_map<U><<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(faces, face_index_map, rgb_map, alpha_map, \
+                                                                            grad_rgb_map, grad_alpha_map, ph, pv,      \
+                                                                            grad_faces, B, nf, is, eps,                \
+                                                                            return_rgb ? 1 : 0, return_alpha ? 1 : 0)
+        const int unroll = b200r_option_nmr_bwd_unroll();
+        if (unroll >= 4) B200R_LAUNCH_K9(4);
+        else if (unroll >= 2) B200R_LAUNCH_K9(2);
+        else B200R_LAUNCH_K9(1);
+#undef B200R_LAUNCH_K9
     }
     e = cudaGetLastError();
     if (e != cudaSuccess) return b200r_cuda_fail(e, "k_nmr_backward_pixel_map");

@@ -356,6 +356,39 @@ __device__ __forceinline__ float warp_sum_f(float v) {
     return v;
 }
 
+// (float)((double)x * 2. / is), the pixel -> NDC scaling of the reference's distance terms
+// (n3mr/cuda/rasterize.py:497-512, 578-593), without the FP64 multiply / divide.  x is a
+// 24-bit float and `is` an integer <= 4096, so 2x/is is either exactly representable in a
+// double or at least 2^-37 (relative) away from every fp32 rounding boundary; the 2^-53
+// error of the double division can therefore never move the final float: the correctly
+// rounded fp32 quotient fl(2x / is) is the same number (Markstein sequence on the hoisted
+// refined reciprocal of `is`, as fast_div).  Out-of-range x takes the plain path, out of line.
+static __device__ __noinline__ float nmr_pixel_to_ndc_slow(float x, int is) { return (float)((double)x * 2. / is); }
+
+__device__ __forceinline__ float nmr_pixel_to_ndc(float x, int is, float is_f, float r_is) {
+    if (midrange(x)) {  // |x| in [2^-60, 2^61): no intermediate over/underflows
+        const float a = 2.f * x;
+        const float q = a * r_is;
+        const float rem = __fmaf_rn(q, -is_f, a);
+        return __fmaf_rn(r_is, rem, q);
+    }
+    return nmr_pixel_to_ndc_slow(x, is);
+}
+
+// 1 / x to 1 ulp (MUFU.RCP).  The edge-scan sums below run in a different order from the
+// reference's serial per-face loop anyway (lanes, then a warp reduction), so the terms
+// diff_grad / dist are formed with this reciprocal and one FMA instead of an IEEE division:
+// <= 1.5 ulp per term, against the 2e-5 relative tolerance of the gradient parity tests.
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// One (edge, axis) pass of the reference's per-face loop (:386-608).  The six passes of a face
+// run as a real loop (not unrolled): the body is long and six copies of it thrash the
+// instruction cache.
+template <int U>
 __global__ void __launch_bounds__(256)
 k_nmr_backward_pixel_map(const float* __restrict__ faces, const int* __restrict__ face_index_map,
                          const float* __restrict__ rgb_map, const float* __restrict__ alpha_map,
@@ -368,122 +401,119 @@ k_nmr_backward_pixel_map(const float* __restrict__ faces, const int* __restrict_
     if (i >= (long)batch_size * num_faces) return;
     const int bn = (int)(i / num_faces);
     const int fn = (int)(i % num_faces);
-    float face[9];
-#pragma unroll
-    for (int k = 0; k < 9; k++) face[k] = __ldg(faces + i * 9 + k);
-    if ((face[7] - face[1]) * (face[3] - face[0]) < (face[4] - face[1]) * (face[6] - face[0])) return;  // :377 (zeros stay)
+    const float* __restrict__ face = faces + i * 9;
+    {
+        const float x0 = __ldg(face + 0), y0 = __ldg(face + 1), x1 = __ldg(face + 3), y1 = __ldg(face + 4);
+        const float x2 = __ldg(face + 6), y2 = __ldg(face + 7);
+        if ((y2 - y0) * (x1 - x0) < (y1 - y0) * (x2 - x0)) return;  // :377 (zeros stay)
+    }
 
     float gacc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // [vertex*2 + (0:x, 1:y)]
+    const float is_f = (float)is, r_is = rcp_refined(is_f);
+    // power-of-two image sizes: x * (2 / is) is an exact scaling, identical to the double expression
+    const float pow2_scale = ((is & (is - 1)) == 0) ? 2.f / is_f : 0.f;
     const long img = (long)bn * is * is;
 
-#pragma unroll
-    for (int edge_num = 0; edge_num < 3; edge_num++) {
-        const int pi0 = edge_num, pi1 = (edge_num + 1) % 3, pi2 = (edge_num + 2) % 3;
-        float pp[3][2];
-        const int pis[3] = {pi0, pi1, pi2};
-#pragma unroll
-        for (int num = 0; num < 3; num++)
-#pragma unroll
-            for (int dim = 0; dim < 2; dim++) pp[num][dim] = 0.5f * (face[3 * pis[num] + dim] * is + is - 1);
-#pragma unroll
-        for (int axis = 0; axis < 2; axis++) {
-            float p[3][2];
-#pragma unroll
-            for (int num = 0; num < 3; num++)
-#pragma unroll
-                for (int dim = 0; dim < 2; dim++) p[num][dim] = pp[num][(dim + axis) % 2];
-            int direction;
-            if (axis == 0) direction = (p[0][0] < p[1][0]) ? -1 : 1;
-            else direction = (p[0][0] < p[1][0]) ? 1 : -1;
-            const int d0_from = (int)fmax((double)ceilf(fminf(p[0][0], p[1][0])), 0.);
-            const int d0_to = (int)fmin((double)fmaxf(p[0][0], p[1][0]), is - 1.);
-            const long map_offset = (axis == 0) ? is : 1;
-            float acc0 = 0.f, acc1 = 0.f;  // contributions to vertex pi0 / pi1, coordinate (1 - axis)
-            for (int d0 = d0_from; d0 <= d0_to; d0++) {
-                const float d1_cross = (p[1][1] - p[0][1]) / (p[1][0] - p[0][0]) * (d0 - p[0][0]) + p[0][1];
-                const int d1_in = (0 < direction) ? (int)floorf(d1_cross) : (int)ceilf(d1_cross);
-                const int d1_out = d1_in + direction;
-                if (d1_in < 0 || is <= d1_in) continue;
-                if (d1_out < 0 || is <= d1_out) continue;
-                const long map_index_in = (axis == 0) ? img + (long)d1_in * is + d0 : img + (long)d0 * is + d1_in;
-                // packed records: axis 1 scans rows of ph, axis 0 scans rows of pv; in both the
-                // record of (d0, d1) sits at img + d0 * is + d1
-                const float4* __restrict__ pk = (axis == 0) ? pv : ph;
-                float alpha_in, alpha_out, rin[3], rout[3];
-                {
-                    const float4 ia = __ldg(pk + (img + (long)d0 * is + d1_in) * 2), ic = __ldg(pk + (img + (long)d0 * is + d1_in) * 2 + 1);
-                    const float4 oa = __ldg(pk + (img + (long)d0 * is + d1_out) * 2), oc = __ldg(pk + (img + (long)d0 * is + d1_out) * 2 + 1);
-                    rin[0] = ia.x; rin[1] = ia.y; rin[2] = ia.z; alpha_in = ic.z;
-                    rout[0] = oa.x; rout[1] = oa.y; rout[2] = oa.z; alpha_out = oc.z;
+#pragma unroll 1
+    for (int pass = 0; pass < 6; pass++) {
+        const int edge_num = pass >> 1, axis = pass & 1;
+        const int pi0 = edge_num, pi1 = (edge_num == 2) ? 0 : edge_num + 1, pi2 = (edge_num == 0) ? 2 : edge_num - 1;
+        // p[num][dim] = 0.5 * (face[3 * pi_num + (dim + axis) % 2] * is + is - 1)   (:389-399)
+        const float p00 = 0.5f * (__ldg(face + 3 * pi0 + axis) * is + is - 1), p01 = 0.5f * (__ldg(face + 3 * pi0 + (axis ^ 1)) * is + is - 1);
+        const float p10 = 0.5f * (__ldg(face + 3 * pi1 + axis) * is + is - 1), p11 = 0.5f * (__ldg(face + 3 * pi1 + (axis ^ 1)) * is + is - 1);
+        const float p20 = 0.5f * (__ldg(face + 3 * pi2 + axis) * is + is - 1), p21 = 0.5f * (__ldg(face + 3 * pi2 + (axis ^ 1)) * is + is - 1);
+        int direction;
+        if (axis == 0) direction = (p00 < p10) ? -1 : 1;
+        else direction = (p00 < p10) ? 1 : -1;
+        const int d0_from = (int)fmax((double)ceilf(fminf(p00, p10)), 0.);
+        const int d0_to = (int)fmin((double)fmaxf(p00, p10), is - 1.);
+        // packed records: axis 1 scans rows of ph, axis 0 scans rows of pv; in both the record
+        // of (d0, d1) sits at img + d0 * is + d1
+        const float4* __restrict__ pk = ((axis == 0) ? pv : ph) + img * 2;
+        float acc0 = 0.f, acc1 = 0.f;  // contributions to vertex pi0 / pi1, coordinate (1 - axis)
+        for (int d0 = d0_from; d0 <= d0_to; d0++) {
+            const float d1_cross = (p11 - p01) / (p10 - p00) * (d0 - p00) + p01;
+            const int d1_in = (0 < direction) ? (int)floorf(d1_cross) : (int)ceilf(d1_cross);
+            const int d1_out = d1_in + direction;
+            if (d1_in < 0 || is <= d1_in) continue;
+            if (d1_out < 0 || is <= d1_out) continue;
+            const float4* __restrict__ prow = pk + (long)d0 * is * 2;
+            const float4 ia = __ldg(prow + d1_in * 2), ic = __ldg(prow + d1_in * 2 + 1);
+            const float4 oa = __ldg(prow + d1_out * 2), oc = __ldg(prow + d1_out * 2 + 1);
+            const bool has0 = p10 != d0, has1 = p00 != d0;
+            const float q0 = (p10 - p00) / (p10 - d0);
+            const float q1 = (p10 - p00) / (d0 - p00);
+            const long map_index_in = (axis == 0) ? img + (long)d1_in * is + d0 : img + (long)d0 * is + d1_in;
+            const bool visible = __ldg(face_index_map + map_index_in) == fn;
+            float d0_cross2;
+            if ((d0 - p00) * (d0 - p20) < 0.f) d0_cross2 = (p21 - p01) / (p20 - p00) * (d0 - p00) + p01;
+            else d0_cross2 = (p11 - p21) / (p10 - p20) * (d0 - p20) + p21;
+            const int in_limit = (0 < direction) ? (int)ceilf(d0_cross2) : (int)floorf(d0_cross2);
+            const long fim_base = (axis == 0) ? img + d0 : img + (long)d0 * is;
+            const long fim_stride = (axis == 0) ? is : 1;
+
+#pragma unroll 1
+            for (int scan = 0; scan < 2; scan++) {
+                // scan 0: outwards from the edge (:461-521), only if the face owns the inside pixel;
+                // scan 1: inwards up to the opposite edge (:523-602), pixels owned by the face
+                int lim, start;
+                float r0, r1, r2, ra;
+                if (scan == 0) {
+                    if (!visible) continue;
+                    lim = (0 < direction) ? is - 1 : 0;
+                    start = d1_out;
+                    r0 = ia.x; r1 = ia.y; r2 = ia.z; ra = ic.z;
+                } else {
+                    lim = in_limit;
+                    start = d1_in;
+                    r0 = oa.x; r1 = oa.y; r2 = oa.z; ra = oc.z;
                 }
-                const bool has0 = p[1][0] != d0, has1 = p[0][0] != d0;
-                const float q0 = (p[1][0] - p[0][0]) / (p[1][0] - d0);
-                const float q1 = (p[1][0] - p[0][0]) / (d0 - p[0][0]);
-                // ---- out scan (:461-521)
-                if (__ldg(face_index_map + map_index_in) == fn) {
-                    const int d1_limit = (0 < direction) ? is - 1 : 0;
-                    const int d1_from = max(min(d1_out, d1_limit), 0);
-                    const int d1_to = min(max(d1_out, d1_limit), is - 1);
-                    for (int d1 = d1_from + lane; d1 <= d1_to; d1 += 32) {
-                        const float4 qa = __ldg(pk + (img + (long)d0 * is + d1) * 2), qc = __ldg(pk + (img + (long)d0 * is + d1) * 2 + 1);
-                        float diff_grad = 0.f;
-                        if (return_alpha) diff_grad += (qc.z - alpha_in) * qc.w;
-                        if (return_rgb) {
-                            diff_grad += (qa.x - rin[0]) * qa.w;
-                            diff_grad += (qa.y - rin[1]) * qc.x;
-                            diff_grad += (qa.z - rin[2]) * qc.y;
-                        }
-                        if (diff_grad <= 0.f) continue;
-                        if (has0) {
-                            float dist = (float)((double)(q0 * (d1 - d1_cross)) * 2. / is);
-                            dist = (0.f < dist) ? dist + eps : dist - eps;
-                            acc0 -= diff_grad / dist;
-                        }
-                        if (has1) {
-                            float dist = (float)((double)(q1 * (d1 - d1_cross)) * 2. / is);
-                            dist = (0.f < dist) ? dist + eps : dist - eps;
-                            acc1 -= diff_grad / dist;
-                        }
+                const int d1_from = max(min(start, lim), 0);
+                const int d1_to = min(max(start, lim), is - 1);
+                // U pixels per lane per trip, every load issued before the first use: the scan is
+                // latency-bound (one dependent L1/L2 round trip per trip), not bandwidth-bound
+                for (int d1b = d1_from + lane; d1b <= d1_to; d1b += 32 * U) {
+                    float4 qa[U], qc[U];
+                    int owner[U];
+#pragma unroll
+                    for (int u = 0; u < U; u++) {
+                        const int d1 = min(d1b + 32 * u, d1_to);  // clamped: always a valid address
+                        owner[u] = (scan == 1) ? __ldg(face_index_map + fim_base + (long)d1 * fim_stride) : fn;
+                        qa[u] = __ldg(prow + d1 * 2);
+                        qc[u] = __ldg(prow + d1 * 2 + 1);
                     }
-                }
-                // ---- in scan (:523-602)
-                {
-                    float d0_cross2;
-                    if ((d0 - p[0][0]) * (d0 - p[2][0]) < 0.f)
-                        d0_cross2 = (p[2][1] - p[0][1]) / (p[2][0] - p[0][0]) * (d0 - p[0][0]) + p[0][1];
-                    else
-                        d0_cross2 = (p[1][1] - p[2][1]) / (p[1][0] - p[2][0]) * (d0 - p[2][0]) + p[2][1];
-                    const int d1_limit = (0 < direction) ? (int)ceilf(d0_cross2) : (int)floorf(d0_cross2);
-                    const int d1_from = max(min(d1_in, d1_limit), 0);
-                    const int d1_to = min(max(d1_in, d1_limit), is - 1);
-                    for (int d1 = d1_from + lane; d1 <= d1_to; d1 += 32) {
-                        const long idx = (axis == 0) ? img + (long)d1 * is + d0 : img + (long)d0 * is + d1;
-                        if (__ldg(face_index_map + idx) != fn) continue;
-                        const float4 qa = __ldg(pk + (img + (long)d0 * is + d1) * 2), qc = __ldg(pk + (img + (long)d0 * is + d1) * 2 + 1);
+#pragma unroll
+                    for (int u = 0; u < U; u++) {
+                        const int d1 = d1b + 32 * u;
+                        if (d1 > d1_to || owner[u] != fn) continue;
                         float diff_grad = 0.f;
-                        if (return_alpha) diff_grad += (qc.z - alpha_out) * qc.w;
+                        if (return_alpha) diff_grad += (qc[u].z - ra) * qc[u].w;
                         if (return_rgb) {
-                            diff_grad += (qa.x - rout[0]) * qa.w;
-                            diff_grad += (qa.y - rout[1]) * qc.x;
-                            diff_grad += (qa.z - rout[2]) * qc.y;
+                            diff_grad += (qa[u].x - r0) * qa[u].w;
+                            diff_grad += (qa[u].y - r1) * qc[u].x;
+                            diff_grad += (qa[u].z - r2) * qc[u].y;
                         }
                         if (diff_grad <= 0.f) continue;
+                        const float delta = (float)d1 - d1_cross;
                         if (has0) {
-                            float dist = (float)((double)(q0 * (d1 - d1_cross)) * 2. / is);
+                            float dist = pow2_scale != 0.f ? (q0 * delta) * pow2_scale : nmr_pixel_to_ndc(q0 * delta, is, is_f, r_is);
                             dist = (0.f < dist) ? dist + eps : dist - eps;
-                            acc0 -= diff_grad / dist;
+                            acc0 = __fmaf_rn(-diff_grad, rcp_approx(dist), acc0);
                         }
                         if (has1) {
-                            float dist = (float)((double)(q1 * (d1 - d1_cross)) * 2. / is);
+                            float dist = pow2_scale != 0.f ? (q1 * delta) * pow2_scale : nmr_pixel_to_ndc(q1 * delta, is, is_f, r_is);
                             dist = (0.f < dist) ? dist + eps : dist - eps;
-                            acc1 -= diff_grad / dist;
+                            acc1 = __fmaf_rn(-diff_grad, rcp_approx(dist), acc1);
                         }
                     }
                 }
             }
-            (void)map_offset;
-            gacc[pi0 * 2 + (1 - axis)] += acc0;
-            gacc[pi1 * 2 + (1 - axis)] += acc1;
+        }
+        const int k0 = pi0 * 2 + (1 - axis), k1 = pi1 * 2 + (1 - axis);
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+            if (k == k0) gacc[k] += acc0;
+            if (k == k1) gacc[k] += acc1;
         }
     }
 #pragma unroll
