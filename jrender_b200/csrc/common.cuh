@@ -53,6 +53,7 @@ struct SoftRasParams {
 struct SoftRasWorkspace {
     FaceRec* recs;       // [B*nf]
     uint2* rects;        // [B*nf]  (rect_x, rect_r) copy for the binning scans
+    uint2* chunk_rects;  // [B*ceil(nf/256)] union rectangle of each run of 256 consecutive faces
     int* coarse_cnt;     // [B*ncs*ncs]
     int* coarse_ids;     // [B*ncs*ncs][nf]
     int* counters;       // [256] scheduler state, zeroed per launch: [0] queue head, [64..127] cost histogram, [128..191] scatter cursors
@@ -83,6 +84,8 @@ static inline SoftRasWorkspace b200r_carve(void* base, int B, int nf, int image_
     off += b200r_align256((size_t)B * nf * sizeof(FaceRec));
     w.rects = (uint2*)(p + off);
     off += b200r_align256((size_t)B * nf * sizeof(uint2));
+    w.chunk_rects = (uint2*)(p + off);
+    off += b200r_align256((size_t)B * ((nf + 255) / 256) * sizeof(uint2));
     w.coarse_cnt = (int*)(p + off);
     off += b200r_align256((size_t)B * ncs * ncs * sizeof(int));
     w.coarse_ids = (int*)(p + off);

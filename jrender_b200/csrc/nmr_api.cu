@@ -61,7 +61,8 @@ int b200r_nmr_forward(const float* faces, const float* textures, int32_t* face_i
     if (e != cudaSuccess) return b200r_cuda_fail(e, "memset counters");
     {
         B200rProfScope prof(B200R_K_COARSE_BIN, st);
-        k_coarse_bin<<<dim3(P.ncs * P.ncs, B), 256, 0, st>>>(W.rects, W.coarse_cnt, W.coarse_ids, W.tile_cost, W.counters + 64,
+        k_chunk_rects<<<dim3((nf + 255) / 256, B), 256, 0, st>>>(W.rects, W.chunk_rects, nf);
+        k_coarse_bin<<<dim3(P.ncs * P.ncs, B), 256, 0, st>>>(W.rects, W.chunk_rects, W.coarse_cnt, W.coarse_ids, W.tile_cost, W.counters + 64,
                                                              nf, is, P.coarse_px, P.ncs, B200R_TILE, B200R_TILE, P.ntx, P.ntx);
     }
     e = cudaGetLastError();

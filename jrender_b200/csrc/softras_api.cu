@@ -127,13 +127,13 @@ int b200r_softras_forward(const float* face_vertices, const float* textures, flo
     if (e != cudaSuccess) return b200r_cuda_fail(e, "memset counters");
     {
         B200rProfScope prof(B200R_K_COARSE_BIN, st);
-        k_coarse_bin<<<dim3(P.ncs * P.ncs, B), 256, 0, st>>>(W.rects, W.coarse_cnt, W.coarse_ids, W.tile_cost, W.counters + 64,
+        k_chunk_rects<<<dim3((nf + 255) / 256, B), 256, 0, st>>>(W.rects, W.chunk_rects, nf);
+        k_coarse_bin<<<dim3(P.ncs * P.ncs, B), 256, 0, st>>>(W.rects, W.chunk_rects, W.coarse_cnt, W.coarse_ids, W.tile_cost, W.counters + 64,
                                                              nf, is, P.coarse_px, P.ncs, P.ftw, P.fth, P.fntx, P.fnty);
     }
     e = cudaGetLastError();
     if (e != cudaSuccess) return b200r_cuda_fail(e, "k_coarse_bin");
-    e = cudaMemsetAsync(W.tile_order, 0xFF, sizeof(int) * (size_t)P.queue_len, st);  // holes (partial edge tiles) = -1
-    if (e != cudaSuccess) return b200r_cuda_fail(e, "memset tile_order");
+    // cost tiles == forward tiles: k_tile_order writes a permutation of all queue_len slots, no holes to pre-fill
     {
         const int total_tiles = P.fntx * P.fnty * B;
         B200rProfScope prof(B200R_K_TILE_ORDER, st);

@@ -38,10 +38,17 @@ struct __align__(16) FaceRecS {
     uint4 pad;
 };
 
+#ifndef B200R_FWD_CHUNK1
+#define B200R_FWD_CHUNK1 16   // records staged per round by a 1-warp CTA
+#endif
+#ifndef B200R_FWD_MINB1
+#define B200R_FWD_MINB1 24    // resident 1-warp CTAs per SM the register allocation must allow
+#endif
+
 template <int NW>
 struct FwdCfg {
     static constexpr int NT = 32 * NW;
-    static constexpr int CHUNK = NW >= 8 ? 128 : (NW >= 2 ? 64 : 32);  // staged faces per round (index fits uint8)
+    static constexpr int CHUNK = NW >= 8 ? 128 : (NW >= 2 ? 64 : B200R_FWD_CHUNK1);  // staged faces per round (index fits uint8)
     static constexpr int UNR = NW >= 8 ? 1 : (NW >= 2 ? 2 : 4);         // coarse entries filtered per thread per pass
 };
 
@@ -164,7 +171,7 @@ __device__ __forceinline__ bool pixel_in_rect(const FaceRec* rec, int px, int ro
 }
 
 template <int DIST, int RGB, int VARIANT, int WX, int WY, bool EXACT>
-__global__ void __launch_bounds__(32 * WX * WY, (WX * WY >= 8) ? 2 : ((WX * WY >= 2) ? 8 : 20))
+__global__ void __launch_bounds__(32 * WX * WY, (WX * WY >= 8) ? 2 : ((WX * WY >= 2) ? 8 : B200R_FWD_MINB1))
 k_softras_forward(const SoftRasParams P, const FaceRec* __restrict__ recs, const uint2* __restrict__ rects,
                   const int* __restrict__ coarse_cnt, const int* __restrict__ coarse_ids,
                   const float* __restrict__ textures, float* __restrict__ soft_colors,

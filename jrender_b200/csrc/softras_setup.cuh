@@ -198,11 +198,41 @@ __device__ __forceinline__ int cost_bucket(int cost) {
     return bkt < B200R_COST_BUCKETS ? bkt : B200R_COST_BUCKETS - 1;
 }
 
-static __global__ void __launch_bounds__(256) k_coarse_bin(const uint2* __restrict__ rects, int* __restrict__ coarse_cnt,
+// Union rectangle of every run of 256 consecutive faces (CTA (chunk, b)).  Mesh faces that are
+// close in index are close on screen, so k_coarse_bin can discard most runs against its bin
+// with one test instead of scanning them.  An empty union is stored as (1, 0) like an empty rect.
+static __global__ void __launch_bounds__(256) k_chunk_rects(const uint2* __restrict__ rects, uint2* __restrict__ chunk_rects, int nf) {
+    __shared__ int s_red[4][8];
+    const int f = blockIdx.x * 256 + threadIdx.x, b = blockIdx.y;
+    int x0 = 0xffff, x1 = -1, r0 = 0xffff, r1 = -1;
+    if (f < nf) {
+        const uint2 rc = __ldg(rects + (size_t)b * nf + f);
+        const int fx0 = (int)(rc.x & 0xffffu), fx1 = (int)(rc.x >> 16), fr0 = (int)(rc.y & 0xffffu), fr1 = (int)(rc.y >> 16);
+        if (fx0 <= fx1 && fr0 <= fr1) { x0 = fx0; x1 = fx1; r0 = fr0; r1 = fr1; }
+    }
+    x0 = __reduce_min_sync(0xffffffffu, x0); x1 = __reduce_max_sync(0xffffffffu, x1);
+    r0 = __reduce_min_sync(0xffffffffu, r0); r1 = __reduce_max_sync(0xffffffffu, r1);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { s_red[0][warp] = x0; s_red[1][warp] = x1; s_red[2][warp] = r0; s_red[3][warp] = r1; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; w++) {
+            x0 = min(x0, s_red[0][w]); x1 = max(x1, s_red[1][w]);
+            r0 = min(r0, s_red[2][w]); r1 = max(r1, s_red[3][w]);
+        }
+        uint2 out = make_uint2(1u, 1u);  // empty: x0 = 1 > x1 = 0
+        if (x0 <= x1 && r0 <= r1) out = make_uint2((uint32_t)x0 | ((uint32_t)x1 << 16), (uint32_t)r0 | ((uint32_t)r1 << 16));
+        chunk_rects[(size_t)b * gridDim.x + blockIdx.x] = out;
+    }
+}
+
+static __global__ void __launch_bounds__(256) k_coarse_bin(const uint2* __restrict__ rects, const uint2* __restrict__ chunk_rects,
+                                                    int* __restrict__ coarse_cnt,
                                                     int* __restrict__ coarse_ids, int* __restrict__ tile_cost,
                                                     int* __restrict__ cost_hist, int nf, int is,
                                                     int coarse_px, int ncs, int tw, int th, int ntx, int nty) {
     __shared__ int s_warp[8];
+    __shared__ int s_hist[B200R_COST_BUCKETS];
     __shared__ int s_cost[2048];  // tiles of this bin: (coarse_px/tw) * (coarse_px/th) <= 32 * 64 (8x4 tiles, 256 px bins)
     const int bin = blockIdx.x, b = blockIdx.y;
     const int bx = bin % ncs, by = bin / ncs;
@@ -215,7 +245,18 @@ static __global__ void __launch_bounds__(256) k_coarse_bin(const uint2* __restri
     int* out = coarse_ids + ((size_t)b * ncs * ncs + bin) * nf;
     int n_out = 0;
     const bool vec_ok = (reinterpret_cast<uintptr_t>(rc) & 15) == 0;  // (b*nf) even
+    const int n_chunks = (nf + 255) / 256;
+    const uint2* crc = chunk_rects + (size_t)b * n_chunks;
     for (int base = 0; base < nf; base += 256 * B200R_COARSE_PER_THREAD) {
+        {   // whole pass (4 runs of 256 faces) outside the bin: skip it, uniformly for the CTA
+            bool any = false;
+#pragma unroll
+            for (int u = 0; u < B200R_COARSE_PER_THREAD; u++) {
+                const int c = base / 256 + u;
+                if (c < n_chunks && rect_overlaps(__ldg(crc + c), x0, x1, r0, r1)) any = true;
+            }
+            if (!any) continue;
+        }
         const int first = base + threadIdx.x * B200R_COARSE_PER_THREAD;
         uint32_t mask = 0;
         uint2 rr[B200R_COARSE_PER_THREAD];
@@ -241,31 +282,51 @@ static __global__ void __launch_bounds__(256) k_coarse_bin(const uint2* __restri
         int off = n_out + block_excl_scan_256(__popc(mask), s_warp, total);
 #pragma unroll
         for (int u = 0; u < B200R_COARSE_PER_THREAD; u++)
-            if (mask & (1u << u)) {
-                out[off++] = first + u;
-                // cost model: (pixel, face) pairs = area of rect ∩ fine tile, for every fine tile of the bin
-                const int fx0 = max((int)(rr[u].x & 0xffffu), x0), fx1 = min((int)(rr[u].x >> 16), x1);
-                const int fr0 = max((int)(rr[u].y & 0xffffu), r0), fr1 = min((int)(rr[u].y >> 16), r1);
-                for (int ty = (fr0 - r0) / th; ty <= (fr1 - r0) / th; ty++) {
-                    const int h = min(fr1, r0 + ty * th + th - 1) - max(fr0, r0 + ty * th) + 1;
-                    for (int tx = (fx0 - x0) / tw; tx <= (fx1 - x0) / tw; tx++) {
-                        const int w = min(fx1, x0 + tx * tw + tw - 1) - max(fx0, x0 + tx * tw) + 1;
-                        atomicAdd(&s_cost[ty * tpbx + tx], w * h);
-                    }
-                }
-            }
+            if (mask & (1u << u)) out[off++] = first + u;
         n_out += total;
     }
+    // cost model: faces listed per fine tile of the bin (x tile pixels), as a 2-D difference
+    // array -- 4 shared-memory atomics per listed face at the corners of its tile range --
+    // followed by row and column prefix sums.  (Adding the clipped area to every overlapped
+    // tile costs ~12 atomics per face, and consecutive faces hit the same tiles: 32-way
+    // conflicts made that pass half of the kernel.)
+    __syncthreads();  // out[] written by other threads of this CTA
+    for (int j = threadIdx.x; j < n_out; j += 256) {
+        const uint2 rr = __ldg(rc + out[j]);
+        const int fx0 = max((int)(rr.x & 0xffffu), x0), fx1 = min((int)(rr.x >> 16), x1);
+        const int fr0 = max((int)(rr.y & 0xffffu), r0), fr1 = min((int)(rr.y >> 16), r1);
+        const int ty_first = (fr0 - r0) / th, ty_end = (fr1 - r0) / th + 1;
+        const int tx_first = (fx0 - x0) / tw, tx_end = (fx1 - x0) / tw + 1;
+        atomicAdd(&s_cost[ty_first * tpbx + tx_first], 1);
+        if (tx_end < tpbx) atomicAdd(&s_cost[ty_first * tpbx + tx_end], -1);
+        if (ty_end < tpby) {
+            atomicAdd(&s_cost[ty_end * tpbx + tx_first], -1);
+            if (tx_end < tpbx) atomicAdd(&s_cost[ty_end * tpbx + tx_end], 1);
+        }
+    }
+    __syncthreads();
+    for (int ty = threadIdx.x; ty < tpby; ty += 256) {  // along x
+        int acc = 0;
+        for (int tx = 0; tx < tpbx; tx++) { acc += s_cost[ty * tpbx + tx]; s_cost[ty * tpbx + tx] = acc; }
+    }
+    __syncthreads();
+    for (int tx = threadIdx.x; tx < tpbx; tx += 256) {  // along y
+        int acc = 0;
+        for (int ty = 0; ty < tpby; ty++) { acc += s_cost[ty * tpbx + tx]; s_cost[ty * tpbx + tx] = acc; }
+    }
     if (threadIdx.x == 0) coarse_cnt[b * ncs * ncs + bin] = n_out;
+    if (threadIdx.x < B200R_COST_BUCKETS) s_hist[threadIdx.x] = 0;
     __syncthreads();
     for (int i = threadIdx.x; i < tpbx * tpby; i += 256) {
         const int gtx = bx * tpbx + i % tpbx, gty = by * tpby + i / tpbx;
         if (gtx < ntx && gty < nty) {
-            const int c = s_cost[i];
+            const int c = s_cost[i] * tw * th;  // ~ (pixel, face) pairs
             tile_cost[(size_t)b * ntx * nty + gty * ntx + gtx] = c;
-            atomicAdd(&cost_hist[cost_bucket(c)], 1);
+            atomicAdd(&s_hist[cost_bucket(c)], 1);
         }
     }
+    __syncthreads();  // one global atomic per (CTA, non-empty bucket), not one per tile
+    if (threadIdx.x < B200R_COST_BUCKETS && s_hist[threadIdx.x] > 0) atomicAdd(&cost_hist[threadIdx.x], s_hist[threadIdx.x]);
 }
 
 // Orders all forward tiles by descending cost bucket (longest-processing-time-first for the
