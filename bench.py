@@ -140,7 +140,7 @@ def time_oracle(workload, target_s, nthreads=0, want_steps=1):
     stride0 = max(1, H // 4)
     t0 = time.perf_counter()
     out = osr.forward(fv, tex, P, row_stride=stride0, nthreads=nthreads)
-    osr.backward(fv, tex, out, g, P, row_stride=stride0)
+    osr.backward(fv, tex, out, g, P, row_stride=stride0, nthreads=cores)
     per_row = (time.perf_counter() - t0) / max(1, len(range(0, H, stride0)))
     rows = int(min(H, max(2, target_s / max(per_row, 1e-9))))
     stride = max(1, H // rows)
@@ -150,7 +150,7 @@ def time_oracle(workload, target_s, nthreads=0, want_steps=1):
         t0 = time.perf_counter()
         out = osr.forward(fv, tex, P, row_stride=stride, nthreads=nthreads)
         t1 = time.perf_counter()
-        osr.backward(fv, tex, out, g, P, row_stride=stride)
+        osr.backward(fv, tex, out, g, P, row_stride=stride, nthreads=cores)
         t2 = time.perf_counter()
         times.append((t1 - t0, t2 - t1))
     return n_rows, H, cores, times
@@ -175,7 +175,7 @@ def run_reference(args, rank, world):
     timed = times[args.warmup:] if len(times) > args.warmup else times
     v = cpu_frames_per_s(n_rows, H, timed)
     nf, _, bpg, desc = WORKLOADS[args.workload]
-    sample = "fwd+bwd of %d evenly spaced rows of one %dx%d image (%d faces), extrapolated x%.1f to a full image; fwd OpenMP %d threads, bwd 1 thread" % (
+    sample = "fwd+bwd of %d evenly spaced rows of one %dx%d image (%d faces), extrapolated x%.1f to a full image; fwd and bwd OpenMP %d threads" % (
         n_rows, H, H, nf, H / n_rows, cores)
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": "frames/s", "n_gpus": args.gpus,
@@ -361,7 +361,7 @@ def run_ours(args, rank, world, local_rank):
         v = cpu_frames_per_s(n_rows, HH, times)
         line["cpu_baseline"] = {
             "value": v, "unit": "frames/s", "cores": cores, "kind": "port",
-            "sample": "oracle fwd+bwd on %d evenly spaced rows of one %dx%d image (%d faces), x%.1f extrapolated; fwd OpenMP %d threads, bwd 1 thread"
+            "sample": "oracle fwd+bwd on %d evenly spaced rows of one %dx%d image (%d faces), x%.1f extrapolated; fwd and bwd OpenMP %d threads"
                       % (n_rows, HH, HH, nf, HH / n_rows, cores)}
     print(json.dumps(line), flush=True)
 

@@ -37,6 +37,12 @@ def lib():
             C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
             C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_float, C.c_float,
             C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+        _lib.softras_oracle_backward_mt.restype = None
+        _lib.softras_oracle_backward_mt.argtypes = [
+            f32p, f32p, f32p, f32p, f32p, i32p, f32p, f32p, f32p,
+            C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+            C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, C.c_float, C.c_float,
+            C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
         _lib.softras_oracle_max_threads.restype = C.c_int
     return _lib
 
@@ -91,8 +97,10 @@ def forward(face_vertices, textures, params, rows=None, nthreads=0, row_stride=1
     return dict(soft_colors=soft_colors, faces_info=faces_info, aggrs_info=aggrs_info, faces_id_buffer=ids)
 
 
-def backward(face_vertices, textures, fwd, grad_soft_colors, params, accumulate_double=True, rows=None, row_stride=1):
-    """Top-K backward (K6).  `fwd` is the dict returned by forward().  -> (grad_faces, grad_textures)."""
+def backward(face_vertices, textures, fwd, grad_soft_colors, params, accumulate_double=True, rows=None, row_stride=1,
+             nthreads=1):
+    """Top-K backward (K6).  `fwd` is the dict returned by forward().  -> (grad_faces, grad_textures).
+    nthreads > 1 (CPU-baseline timing only): rows are dealt to threads with private double accumulators."""
     fv = np.ascontiguousarray(face_vertices, dtype=np.float32)
     tx = np.ascontiguousarray(textures, dtype=np.float32)
     g = np.ascontiguousarray(grad_soft_colors, dtype=np.float32)
@@ -103,6 +111,13 @@ def backward(face_vertices, textures, fwd, grad_soft_colors, params, accumulate_
     gf = np.zeros((B, nf, 3, 3), np.float32)
     gt = np.zeros((B, nf, T, 3), np.float32)
     r0, r1 = (0, H) if rows is None else rows
+    if nthreads > 1:
+        lib().softras_oracle_backward_mt(
+            _p(fv, C.c_float), _p(tx, C.c_float), _p(np.ascontiguousarray(fwd["soft_colors"]), C.c_float),
+            _p(np.ascontiguousarray(fwd["faces_info"]), C.c_float), _p(np.ascontiguousarray(fwd["aggrs_info"]), C.c_float),
+            _p(np.ascontiguousarray(fwd["faces_id_buffer"]), C.c_int32), _p(g, C.c_float),
+            _p(gf, C.c_float), _p(gt, C.c_float), B, nf, T, H, K, *params.scalars(), r0, r1, int(row_stride), int(nthreads))
+        return gf, gt
     lib().softras_oracle_backward(
         _p(fv, C.c_float), _p(tx, C.c_float), _p(np.ascontiguousarray(fwd["soft_colors"]), C.c_float),
         _p(np.ascontiguousarray(fwd["faces_info"]), C.c_float), _p(np.ascontiguousarray(fwd["aggrs_info"]), C.c_float),

@@ -631,6 +631,49 @@ void softras_oracle_backward(const float *faces, const float *textures, const fl
     free(gt);
 }
 
+/* Multi-threaded timing variant for the CPU baseline (bench.py): thread t runs the sequential
+ * restatement above on rows row_begin + t*stride, + nthreads*stride, ... into private
+ * gradient buffers (double accumulation), which are then summed -- SURVEY.md 8(d)'s
+ * "per-thread private grad buffers reduced at the end".  Not used by the parity tests. */
+void softras_oracle_backward_mt(const float *faces, const float *textures, const float *soft_colors,
+                                const float *faces_info, const float *aggrs_info,
+                                const int32_t *faces_id_buffer, const float *grad_soft_colors,
+                                float *grad_faces, float *grad_textures, int batch_size,
+                                int num_faces, int texture_size, int image_size, int max_faces_id,
+                                float near, float far, float eps, float sigma_val, int func_id_dist,
+                                float dist_eps, float gamma_val, int func_id_rgb, int func_id_alpha,
+                                int texture_sample_type, int double_side,
+                                int row_begin, int row_end, int row_stride, int nthreads) {
+    const size_t ngf = (size_t)batch_size * num_faces * 9;
+    const size_t ngt = (size_t)batch_size * num_faces * texture_size * 3;
+    if (row_stride < 1) row_stride = 1;
+    if (nthreads < 1) nthreads = 1;
+    float *pf = (float *)calloc(ngf * nthreads, sizeof(float));
+    float *pt = (float *)calloc(ngt * nthreads, sizeof(float));
+#pragma omp parallel for schedule(static, 1) num_threads(nthreads)
+    for (int t = 0; t < nthreads; t++)
+        softras_oracle_backward(faces, textures, soft_colors, faces_info, aggrs_info, faces_id_buffer,
+                                grad_soft_colors, pf + ngf * t, pt + ngt * t, batch_size, num_faces,
+                                texture_size, image_size, max_faces_id, near, far, eps, sigma_val,
+                                func_id_dist, dist_eps, gamma_val, func_id_rgb, func_id_alpha,
+                                texture_sample_type, double_side, 1, row_begin + t * row_stride, row_end,
+                                row_stride * nthreads);
+#pragma omp parallel for schedule(static) num_threads(nthreads)
+    for (long i = 0; i < (long)ngf; i++) {
+        double a = 0;
+        for (int t = 0; t < nthreads; t++) a += pf[ngf * t + i];
+        grad_faces[i] = (float)a;
+    }
+#pragma omp parallel for schedule(static) num_threads(nthreads)
+    for (long i = 0; i < (long)ngt; i++) {
+        double a = 0;
+        for (int t = 0; t < nthreads; t++) a += pt[ngt * t + i];
+        grad_textures[i] = (float)a;
+    }
+    free(pf);
+    free(pt);
+}
+
 int softras_oracle_max_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -95,6 +95,18 @@ def test_float_vs_double_accumulation_close(scene):
     assert np.abs(gt64 - gt32).max() <= 1e-5 * np.abs(gt64).max()
 
 
+def test_threaded_backward_matches_sequential(scene):
+    # the CPU-baseline timing variant (rows dealt to threads, private accumulators) computes the same sums
+    fv, tex = scene
+    P = osr.Params(image_size=48)
+    out = osr.forward(fv, tex, P)
+    g = np.random.default_rng(3).uniform(-1, 1, out["soft_colors"].shape).astype(np.float32)
+    gf1, gt1 = osr.backward(fv, tex, out, g, P, accumulate_double=True)
+    gf3, gt3 = osr.backward(fv, tex, out, g, P, nthreads=3)
+    assert np.abs(gf1 - gf3).max() <= 2e-6 * np.abs(gf1).max()
+    assert np.abs(gt1 - gt3).max() <= 2e-6 * np.abs(gt1).max()
+
+
 def test_texture_gradient_is_the_softmax_weight_for_T1(scene):
     """With T=1, d out_k / d tex_k at a pixel is the face's softmax weight, so summing the texture
     gradient over faces for upstream g=(1,1,1,0) gives sum_pixels sum_topK weights (<= #pixels)."""
