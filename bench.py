@@ -135,7 +135,9 @@ def time_oracle(workload, target_s, nthreads=0, want_steps=1):
     fv, tex = wl.make_scene(nf, batch=1)
     P = osr.Params(image_size=H)
     g = np.random.default_rng(2).uniform(-1.0, 1.0, (1, 4, H, H)).astype(np.float32)
-    cores = osr.max_threads() if nthreads <= 0 else nthreads
+    # every core this process may run on; torchrun exports OMP_NUM_THREADS=1, which must not shrink the CPU baseline
+    cores = nthreads if nthreads > 0 else len(os.sched_getaffinity(0))
+    nthreads = cores
     # calibrate on 4 rows
     stride0 = max(1, H // 4)
     t0 = time.perf_counter()
