@@ -56,11 +56,11 @@ __device__ __forceinline__ void pair_gradient(const FaceRec* rec, int fn, const 
     } else if (DIST == 1) {
         dis = barycentric_p2f_distance(w);
         t[0] = w[0]; t[1] = w[1]; t[2] = w[2];
-        soft_fragment = sigmoid_from_negarg<EXACT>(dc.by_sigma(-dis));
+        soft_fragment = sigmoid_from_negarg<EXACT>(dc.template by_sigma_t<EXACT>(-dis));
     } else {
         sign = euclidean_p2f_distance(dis_x, dis_y, t, w, rec, xp, yp);
         dis = dis_x * dis_x + dis_y * dis_y;
-        soft_fragment = sigmoid_from_negarg<EXACT>(dc.by_sigma(-sign * dis));
+        soft_fragment = sigmoid_from_negarg<EXACT>(dc.template by_sigma_t<EXACT>(-sign * dis));
     }
 
     float C_grad_xy = 0.f;
@@ -97,9 +97,9 @@ __device__ __forceinline__ void pair_gradient(const FaceRec* rec, int fn, const 
         }
     } else if (RGB == 1) {
         float C_grad_xyz_rgb = 0.f;
-        const float zp_norm = dc.by_span(P.far_ - zp);
-        const float zp_softmax = fast_div(soft_fragment * expf(dc.by_gamma(zp_norm - px.softmax_max)), px.softmax_sum,
-                                          px.r_ssum, px.s_ssum);
+        const float zp_norm = dc.template by_span_t<EXACT>(P.far_ - zp);
+        const float zp_softmax = div_t<EXACT>(soft_fragment * expf(dc.template by_gamma_t<EXACT>(zp_norm - px.softmax_max)),
+                                              px.softmax_sum, px.r_ssum, px.s_ssum);
         float col[3];
         if (P.tex_type == 0) {
             const int j = surface_texel(w, P.R);
@@ -125,17 +125,17 @@ __device__ __forceinline__ void pair_gradient(const FaceRec* rec, int fn, const 
         C_grad_xyz_rgb *= zp_softmax;
         C_grad_xy += C_grad_xyz_rgb / soft_fragment;
 
-        const float C_grad_z_rgb = fast_div(dc.by_gamma(C_grad_xyz_rgb), nmf, r_nmf, s_nmf) * zp * zp;
+        const float C_grad_z_rgb = div_t<EXACT>(dc.template by_gamma_t<EXACT>(C_grad_xyz_rgb), nmf, r_nmf, s_nmf) * zp * zp;
         const uint32_t fl = rec->flags;
 #pragma unroll
         for (int k = 0; k < 3; k++) {
             const bool sz = (fl & (16u << k)) != 0;
             const float z = f[3 * k + 2], rz = rec->rz[k];
-            gv[k * 3 + 2] = fast_div(fast_div(C_grad_z_rgb * w[k], z, rz, sz), z, rz, sz);
+            gv[k * 3 + 2] = div_t<EXACT>(div_t<EXACT>(C_grad_z_rgb * w[k], z, rz, sz), z, rz, sz);
         }
     }
 
-    C_grad_xy *= dc.by_sigma(soft_fragment * (1.f - soft_fragment));  // :1336
+    C_grad_xy *= dc.template by_sigma_t<EXACT>(soft_fragment * (1.f - soft_fragment));  // :1336
     if (DIST == 1) {  // backward_barycentric_p2f_distance (:1118-1132), w := t (unclipped)
         const int pm = t[0] > t[1] ? (t[1] > t[2] ? 2 : 1) : (t[0] > t[2] ? 2 : 0);
         const float* inv = rec->inv;

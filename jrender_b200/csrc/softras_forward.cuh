@@ -96,13 +96,13 @@ __device__ __forceinline__ void shade_face(const FaceRec* rec, PixState& st, con
     } else if (DIST == 1) {
         const float dis = barycentric_p2f_distance(w);
         if (-dis >= threshold) return;  // :337
-        soft_fragment = sigmoid_from_negarg<EXACT>(dc.by_sigma(-dis));
+        soft_fragment = sigmoid_from_negarg<EXACT>(dc.template by_sigma_t<EXACT>(-dis));
     } else {
         float dis_x, dis_y, t[3];
         const float sign = euclidean_p2f_distance(dis_x, dis_y, t, w, rec, xp, yp);
         const float dis = dis_x * dis_x + dis_y * dis_y;
         if (sign < 0.f && dis >= threshold) return;  // :343
-        soft_fragment = sigmoid_from_negarg<EXACT>(dc.by_sigma(-sign * dis));
+        soft_fragment = sigmoid_from_negarg<EXACT>(dc.template by_sigma_t<EXACT>(-sign * dis));
     }
 
     // alpha aggregation, before any z test (:349-358, Q2)
@@ -147,13 +147,13 @@ __device__ __forceinline__ void shade_face(const FaceRec* rec, PixState& st, con
         }
     } else if (RGB == 1) {  // :399-419
         if (front || P.double_side) {
-            const float zp_norm = dc.by_span(P.far_ - zp);
+            const float zp_norm = dc.template by_span_t<EXACT>(P.far_ - zp);
             float exp_delta_zp = 1.f;
             if (zp_norm > st.softmax_max) {
-                exp_delta_zp = expf(dc.by_gamma(st.softmax_max - zp_norm));
+                exp_delta_zp = expf(dc.template by_gamma_t<EXACT>(st.softmax_max - zp_norm));
                 st.softmax_max = zp_norm;
             }
-            const float exp_z = expf(dc.by_gamma(zp_norm - st.softmax_max));
+            const float exp_z = expf(dc.template by_gamma_t<EXACT>(zp_norm - st.softmax_max));
             st.softmax_sum = exp_delta_zp * st.softmax_sum + exp_z * soft_fragment;
             float col[3];
             sample_texture_fwd(col, btex + (size_t)fn * P.T * 3, wc, P.R, P.tex_type, rec, zp);

@@ -27,6 +27,10 @@ struct DivConst {
     __device__ __forceinline__ float by_sigma(float a) const { return fast_div(a, sigma, r_sigma, s_sigma); }
     __device__ __forceinline__ float by_gamma(float a) const { return fast_div(a, gamma, r_gamma, s_gamma); }
     __device__ __forceinline__ float by_span(float a) const { return fast_div(a, span, r_span, s_span); }
+    // EXACT = false: relaxed_div (arguments of exp() and gradient terms only)
+    template <bool EXACT> __device__ __forceinline__ float by_sigma_t(float a) const { return div_t<EXACT>(a, sigma, r_sigma, s_sigma); }
+    template <bool EXACT> __device__ __forceinline__ float by_gamma_t(float a) const { return div_t<EXACT>(a, gamma, r_gamma, s_gamma); }
+    template <bool EXACT> __device__ __forceinline__ float by_span_t(float a) const { return div_t<EXACT>(a, span, r_span, s_span); }
 };
 
 // :20-25
