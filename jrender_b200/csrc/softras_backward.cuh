@@ -58,7 +58,7 @@ __device__ __forceinline__ void pair_gradient(const FaceRec* rec, int fn, const 
         t[0] = w[0]; t[1] = w[1]; t[2] = w[2];
         soft_fragment = sigmoid_from_negarg<EXACT>(dc.template by_sigma_t<EXACT>(-dis));
     } else {
-        sign = euclidean_p2f_distance(dis_x, dis_y, t, w, rec, xp, yp);
+        sign = euclidean_p2f_distance<EXACT>(dis_x, dis_y, t, w, rec, xp, yp);
         dis = dis_x * dis_x + dis_y * dis_y;
         soft_fragment = sigmoid_from_negarg<EXACT>(dc.template by_sigma_t<EXACT>(-sign * dis));
     }
@@ -75,13 +75,13 @@ __device__ __forceinline__ void pair_gradient(const FaceRec* rec, int fn, const 
             const double prod = px.d_galpha * (px.d_one_minus_alpha / den);
             C_grad_xy_alpha = d_midrange(prod) ? d2f_mid(prod) : (float)prod;
         } else {
-            C_grad_xy_alpha = C_grad_xy_alpha * ((1.f - px.oc[3]) / fmaxf(omd, 1e-6f));
+            C_grad_xy_alpha = C_grad_xy_alpha * div_var_t<EXACT>(1.f - px.oc[3], fmaxf(omd, 1e-6f));
         }
     }
     C_grad_xy += C_grad_xy_alpha;
 
     const float w0[3] = {w[0], w[1], w[2]};
-    const float zp = clip_and_z(w, rec);
+    const float zp = clip_and_z<EXACT>(w, rec);
 
     if (RGB == 0) {
         if ((float)fn == px.softmax_max) {  // :1300 (int vs float compare, Q10)
@@ -123,7 +123,7 @@ __device__ __forceinline__ void pair_gradient(const FaceRec* rec, int fn, const 
 #pragma unroll
         for (int k = 0; k < 3; k++) C_grad_xyz_rgb += px.g[k] * (col[k] - px.oc[k]);
         C_grad_xyz_rgb *= zp_softmax;
-        C_grad_xy += C_grad_xyz_rgb / soft_fragment;
+        C_grad_xy += div_var_t<EXACT>(C_grad_xyz_rgb, soft_fragment);
 
         const float C_grad_z_rgb = div_t<EXACT>(dc.template by_gamma_t<EXACT>(C_grad_xyz_rgb), nmf, r_nmf, s_nmf) * zp * zp;
         const uint32_t fl = rec->flags;
@@ -219,8 +219,11 @@ k_softras_backward_lane(const SoftRasParams P, const FaceRec* __restrict__ recs,
     float* bgt = grad_textures + (size_t)b * nf * T * 3;
     const bool tex_in_acc = (P.tex_type == 0 && T == 1);
 
+    // ids are fetched two slots ahead, so the id of the NEXT face is already in a register when
+    // its record is prefetched (waiting for a just-issued id load here stalled every iteration)
+    int fn_next = (1 < K) ? __ldg(src + npix) : -1;
     for (int m = 0; m < K && fn >= 0; m++) {
-        const int fn_next = (m + 1 < K) ? __ldg(src + (size_t)(m + 1) * npix) : -1;  // prefetch
+        const int fn_next2 = (m + 2 < K) ? __ldg(src + (size_t)(m + 2) * npix) : -1;
         if (fn_next >= 0) {  // pull the next face's record (two 128-byte lines) towards L1 behind this pair's math
             const char* nr = reinterpret_cast<const char*>(brecs + fn_next);
             asm volatile("prefetch.global.L1 [%0];" ::"l"(nr));
@@ -245,6 +248,7 @@ k_softras_backward_lane(const SoftRasParams P, const FaceRec* __restrict__ recs,
             }
         }
         fn = fn_next;
+        fn_next = fn_next2;
     }
 }
 

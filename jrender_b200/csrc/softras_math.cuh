@@ -59,14 +59,17 @@ __device__ __forceinline__ float div_nocheck(float a, float b, float r) {
 // weight is 0 or >= 2^-58 (and the face's z are midrange, flag bits 4-6) all numerators stay
 // inside fast_div's safe range before and after the normalisation; otherwise the individually
 // checked path runs.  Zero numerators are exact in the unchecked sequence because they are +0.
+// STRICT = false (backward, where zp only scales gradient terms): weights below 2^-58 are not
+// diverted to the checked path (relaxed_div's argument applies).
+template <bool STRICT = true>
 __device__ __forceinline__ float clip_and_z(float w[3], const FaceRec* rec) {
 #pragma unroll
     for (int k = 0; k < 3; k++) w[k] = fmaxf(fminf(w[k], 1.f), 0.f);
     const float w_sum = fmaxf(w[0] + w[1] + w[2], 1e-5f);
     const uint32_t fl = rec->flags;
     const float tiny = 3.4694469519536142e-18f;  // 2^-58
-    const bool ok = ((fl & 0x70u) == 0x70u) && (w[0] == 0.f || w[0] >= tiny) && (w[1] == 0.f || w[1] >= tiny) &&
-                    (w[2] == 0.f || w[2] >= tiny);
+    const bool ok = ((fl & 0x70u) == 0x70u) &&
+                    (!STRICT || ((w[0] == 0.f || w[0] >= tiny) && (w[1] == 0.f || w[1] >= tiny) && (w[2] == 0.f || w[2] >= tiny)));
     if (ok) {
         if (w_sum != 1.f) {  // x / 1 == x exactly
             const float r = rcp_refined(w_sum);
@@ -94,6 +97,7 @@ __device__ __forceinline__ float sel3(int i, float a, float b, float c) { return
 
 // :57-147.  rec->a0 holds the pre-subtracted Gram-matrix rows.  Returns sign; writes
 // dis_x, dis_y and (for the backward) t[3].
+template <bool STRICT = true>
 __device__ __forceinline__ float euclidean_p2f_distance(float& dis_x, float& dis_y, float t[3],
                                                         const float w[3], const FaceRec* rec,
                                                         float xp, float yp) {
@@ -108,8 +112,8 @@ __device__ __forceinline__ float euclidean_p2f_distance(float& dis_x, float& dis
             const int v0 = k, v1 = (k + 1) % 3, v2 = (k + 2) % 3;
             const float* a = rec->a0 + 3 * k;
             float t0[3];
-            t0[v0] = fast_div(w[0] * a[0] + w[1] * a[1] + w[2] * a[2] - a[v1], a[v0] - a[v1], rec->rden[k],
-                              (fl & (128u << k)) != 0);
+            t0[v0] = div_t<STRICT>(w[0] * a[0] + w[1] * a[1] + w[2] * a[2] - a[v1], a[v0] - a[v1], rec->rden[k],
+                                   (fl & (128u << k)) != 0);
             t0[v1] = 1.f - t0[v0];
             t0[v2] = 0.f;
             t0[0] -= w[0];
@@ -150,8 +154,8 @@ __device__ __forceinline__ float euclidean_p2f_distance(float& dis_x, float& dis
         const float a_0 = a[0], a_1 = a[1], a_2 = a[2];
         const float a_v0 = sel3(v0, a_0, a_1, a_2);
         const float a_v1 = sel3(v1, a_0, a_1, a_2);
-        const float tv0 = fast_div(w[0] * a_0 + w[1] * a_1 + w[2] * a_2 - a_v1, a_v0 - a_v1, rec->rden[v0],
-                                   (fl & (128u << v0)) != 0);
+        const float tv0 = div_t<STRICT>(w[0] * a_0 + w[1] * a_1 + w[2] * a_2 - a_v1, a_v0 - a_v1, rec->rden[v0],
+                                        (fl & (128u << v0)) != 0);
         const float tv1 = 1.f - tv0;
         const float c0 = fminf(fmaxf(tv0, 0.f), 1.f);
         const float c1 = fminf(fmaxf(tv1, 0.f), 1.f);
