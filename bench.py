@@ -275,27 +275,60 @@ def run_ours(args, rank, world, local_rank):
     gt_p = torch.empty_like(tex_p).pin_memory()
     target = torch.zeros((bpg, 4, H, H), dtype=torch.float32, device=dev)
 
-    def e2e_step():
-        a = fv_p.to(dev, non_blocking=True).requires_grad_(True)
-        t = tex_p.to(dev, non_blocking=True).requires_grad_(True)
-        img = SoftRasterizeFunction(image_size=H)(a, t)
-        loss = ((img - target) ** 2).mean()      # loss gradient is produced on the device
-        loss.backward()
-        gf_p.copy_(a.grad, non_blocking=True)
-        gt_p.copy_(t.grad, non_blocking=True)
-        return float(loss.item())                # D2H read of the step's result; also syncs
+    # Software pipeline over three streams, as a training loop would run it: the H2D copy of step
+    # i+1 (copy stream) and the D2H copy of step i-1's gradients and loss (second copy stream)
+    # overlap the raster kernels of step i.  Every step's copies are inside the timed region;
+    # the host blocks once at the end, when the last step's results have landed in pinned memory.
+    s_in, s_out, s_main = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.current_stream(dev)
+    d_fv = [torch.empty_like(fv_p, device=dev) for _ in range(2)]
+    d_tex = [torch.empty_like(tex_p, device=dev) for _ in range(2)]
+    loss_p = torch.zeros(64, dtype=torch.float32).pin_memory()
+    ev_in = [torch.cuda.Event() for _ in range(2)]      # inputs of slot landed on the device
+    ev_free = [torch.cuda.Event() for _ in range(2)]    # compute of the step that used the slot is done
+    ev_done = [torch.cuda.Event() for _ in range(2)]
 
-    for _ in range(3):
-        e2e_step()
+    def e2e_run(n):
+        for i in range(n):
+            k = i & 1
+            with torch.cuda.stream(s_in):
+                if i >= 2:
+                    s_in.wait_event(ev_free[k])
+                d_fv[k].copy_(fv_p, non_blocking=True)
+                d_tex[k].copy_(tex_p, non_blocking=True)
+                ev_in[k].record(s_in)
+            s_main.wait_event(ev_in[k])
+            a = d_fv[k].detach().requires_grad_(True)
+            t = d_tex[k].detach().requires_grad_(True)
+            img = SoftRasterizeFunction(image_size=H)(a, t)
+            loss = ((img - target) ** 2).mean()      # loss gradient is produced on the device
+            loss.backward()
+            ev_free[k].record(s_main)
+            ev_done[k].record(s_main)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_done[k])
+                for g in (a.grad, t.grad, loss):
+                    g.record_stream(s_out)
+                gf_p.copy_(a.grad, non_blocking=True)
+                gt_p.copy_(t.grad, non_blocking=True)
+                loss_p[i % 64].copy_(loss.detach(), non_blocking=True)   # D2H read of the step's result
+        s_out.synchronize()
+        s_main.synchronize()
+        return float(loss_p[(n - 1) % 64])
+
+    e2e_run(3)
     barrier()
     e2e_steps = max(3, min(args.steps, 10))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_host0 = time.perf_counter()
     e0.record()
-    for _ in range(e2e_steps):
-        e2e_step()
+    e2e_run(e2e_steps)
     e1.record()
+    e1.synchronize()
+    t_host = (time.perf_counter() - t_host0) * 1000.0
     barrier()
-    t_e2e = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    # device events on the main stream bracket the loop; the host wall clock (which also covers the
+    # tail of the D2H stream) is taken as the e2e time when it is longer
+    t_e2e = torch.tensor([max(e0.elapsed_time(e1), t_host)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     e2e_value = bpg * world * e2e_steps / (float(t_e2e.item()) / 1000.0)
@@ -331,6 +364,12 @@ def run_ours(args, rank, world, local_rank):
     dom = max(alg, key=lambda k: kern[k]["avg_ms"])
     peak, peak_src = peaks()
     achieved = alg[dom] / (kern[dom]["avg_ms"] / 1000.0) / 1e9
+    traffic = None   # measured DRAM bytes per launch of the dominant kernel, from the committed ncu capture
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_traffic.json")) as f:
+            traffic = json.load(f).get(args.workload, {}).get(dom)
+    except OSError:
+        pass
     step_alg = bpg * (48 * P + 3 * (36 + 12 * T) * nf)
     line = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
@@ -345,11 +384,11 @@ def run_ours(args, rank, world, local_rank):
         "step_ms": {"min": float(np.min(step_ms)), "median": float(np.median(step_ms)), "max": float(np.max(step_ms))},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "what": "pinned host face_vertices+textures -> H2D -> forward -> on-device MSE loss -> backward -> D2H grads + loss scalar"},
+                "what": "public API, per step: pinned host face_vertices+textures -> H2D -> forward -> on-device MSE loss -> backward -> D2H grads + loss scalar; copies of neighbouring steps overlap the kernels on two copy streams, host waits once at the end"},
         "gpu_launches": int(launches),
         "kernels": kern,
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": int(alg[dom]),
                      "note": "SIMT fp32 rasterization is issue-bound, not HBM-bound (SURVEY.md F9); see profiles/"},
         "roofline_step": {"algorithmic_bytes_per_step": int(step_alg),
