@@ -356,40 +356,24 @@ __device__ __forceinline__ float warp_sum_f(float v) {
     return v;
 }
 
-// (float)((double)x * 2. / is), the pixel -> NDC scaling of the reference's distance terms
-// (n3mr/cuda/rasterize.py:497-512, 578-593), without the FP64 multiply / divide.  x is a
-// 24-bit float and `is` an integer <= 4096, so 2x/is is either exactly representable in a
-// double or at least 2^-37 (relative) away from every fp32 rounding boundary; the 2^-53
-// error of the double division can therefore never move the final float: the correctly
-// rounded fp32 quotient fl(2x / is) is the same number (Markstein sequence on the hoisted
-// refined reciprocal of `is`, as fast_div).  Out-of-range x takes the plain path, out of line.
-static __device__ __noinline__ float nmr_pixel_to_ndc_slow(float x, int is) { return (float)((double)x * 2. / is); }
-
-__device__ __forceinline__ float nmr_pixel_to_ndc(float x, int is, float is_f, float r_is) {
-    if (midrange(x)) {  // |x| in [2^-60, 2^61): no intermediate over/underflows
-        const float a = 2.f * x;
-        const float q = a * r_is;
-        const float rem = __fmaf_rn(q, -is_f, a);
-        return __fmaf_rn(r_is, rem, q);
-    }
-    return nmr_pixel_to_ndc_slow(x, is);
-}
-
 // 1 / x to 1 ulp (MUFU.RCP).  The edge-scan sums below run in a different order from the
 // reference's serial per-face loop anyway (lanes, then a warp reduction), so the terms
 // diff_grad / dist are formed with this reciprocal and one FMA instead of an IEEE division:
 // <= 1.5 ulp per term, against the 2e-5 relative tolerance of the gradient parity tests.
 __device__ __forceinline__ float rcp_approx(float x) {
     float r;
-    asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));  // |x| >= eps: never denormal
     return r;
 }
 
 // One (edge, axis) pass of the reference's per-face loop (:386-608).  The six passes of a face
 // run as a real loop (not unrolled): the body is long and six copies of it thrash the
 // instruction cache.
+#ifndef B200R_K9_MINB
+#define B200R_K9_MINB 6   // resident 256-thread CTAs per SM for the single-pixel-per-trip scan (40 registers; measured best of 4/5/6/8)
+#endif
 template <int U>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, U == 1 ? B200R_K9_MINB : 1)
 k_nmr_backward_pixel_map(const float* __restrict__ faces, const int* __restrict__ face_index_map,
                          const float* __restrict__ rgb_map, const float* __restrict__ alpha_map,
                          const float* __restrict__ grad_rgb_map, const float* __restrict__ grad_alpha_map,
@@ -409,9 +393,7 @@ k_nmr_backward_pixel_map(const float* __restrict__ faces, const int* __restrict_
     }
 
     float gacc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // [vertex*2 + (0:x, 1:y)]
-    const float is_f = (float)is, r_is = rcp_refined(is_f);
-    // power-of-two image sizes: x * (2 / is) is an exact scaling, identical to the double expression
-    const float pow2_scale = ((is & (is - 1)) == 0) ? 2.f / is_f : 0.f;
+    const float ndc_scale = 2.f / (float)is;
     const long img = (long)bn * is * is;
 
 #pragma unroll 1
@@ -443,6 +425,10 @@ k_nmr_backward_pixel_map(const float* __restrict__ faces, const int* __restrict_
             const bool has0 = p10 != d0, has1 = p00 != d0;
             const float q0 = (p10 - p00) / (p10 - d0);
             const float q1 = (p10 - p00) / (d0 - p00);
+            // pixel -> NDC: the reference's (float)((double)(q * delta) * 2. / is) is formed as
+            // delta * (q * (2 / is)) -- a few ulp on a quantity that is then offset by eps and
+            // inverted approximately (see rcp_approx); the sign test `0 < dist` is unaffected
+            const float k0 = q0 * ndc_scale, k1 = q1 * ndc_scale;
             const long map_index_in = (axis == 0) ? img + (long)d1_in * is + d0 : img + (long)d0 * is + d1_in;
             const bool visible = __ldg(face_index_map + map_index_in) == fn;
             float d0_cross2;
@@ -472,7 +458,8 @@ k_nmr_backward_pixel_map(const float* __restrict__ faces, const int* __restrict_
                 const int d1_to = min(max(start, lim), is - 1);
                 // U pixels per lane per trip, every load issued before the first use: the scan is
                 // latency-bound (one dependent L1/L2 round trip per trip), not bandwidth-bound
-                for (int d1b = d1_from + lane; d1b <= d1_to; d1b += 32 * U) {
+                float d1f = (float)(d1_from + lane);  // exact below 2^24
+                for (int d1b = d1_from + lane; d1b <= d1_to; d1b += 32 * U, d1f += 32.f * U) {
                     float4 qa[U], qc[U];
                     int owner[U];
 #pragma unroll
@@ -494,14 +481,14 @@ k_nmr_backward_pixel_map(const float* __restrict__ faces, const int* __restrict_
                             diff_grad += (qa[u].z - r2) * qc[u].y;
                         }
                         if (diff_grad <= 0.f) continue;
-                        const float delta = (float)d1 - d1_cross;
+                        const float delta = (d1f + 32.f * u) - d1_cross;
                         if (has0) {
-                            float dist = pow2_scale != 0.f ? (q0 * delta) * pow2_scale : nmr_pixel_to_ndc(q0 * delta, is, is_f, r_is);
+                            float dist = delta * k0;
                             dist = (0.f < dist) ? dist + eps : dist - eps;
                             acc0 = __fmaf_rn(-diff_grad, rcp_approx(dist), acc0);
                         }
                         if (has1) {
-                            float dist = pow2_scale != 0.f ? (q1 * delta) * pow2_scale : nmr_pixel_to_ndc(q1 * delta, is, is_f, r_is);
+                            float dist = delta * k1;
                             dist = (0.f < dist) ? dist + eps : dist - eps;
                             acc1 = __fmaf_rn(-diff_grad, rcp_approx(dist), acc1);
                         }
@@ -509,11 +496,11 @@ k_nmr_backward_pixel_map(const float* __restrict__ faces, const int* __restrict_
                 }
             }
         }
-        const int k0 = pi0 * 2 + (1 - axis), k1 = pi1 * 2 + (1 - axis);
+        const int g0 = pi0 * 2 + (1 - axis), g1 = pi1 * 2 + (1 - axis);
 #pragma unroll
         for (int k = 0; k < 6; k++) {
-            if (k == k0) gacc[k] += acc0;
-            if (k == k1) gacc[k] += acc1;
+            if (k == g0) gacc[k] += acc0;
+            if (k == g1) gacc[k] += acc1;
         }
     }
 #pragma unroll

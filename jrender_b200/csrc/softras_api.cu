@@ -18,7 +18,7 @@ std::atomic<int> g_fwd_persistent{1};  // 0: one CTA per tile, 1: persistent gri
 std::atomic<int> g_exact_tail{0};      // 1: reference's double-precision sigmoid / alpha tails bit for bit; 0: fp32 tails (<= 1 ulp)
 std::atomic<int> g_bwd_variant{1};     // 0: warp union walk + scalar atomics, 1: per-lane walk + 16-byte vector atomics
 std::atomic<int> g_fwd_warps{1};       // warps per forward CTA: 8 (16x16 tile), 2 (16x4), 1 (8x4, warp-autonomous; default)
-std::atomic<int> g_nmr_bwd_unroll{2};  // pixels per lane per trip in the NMR edge scans (1, 2 or 4)
+std::atomic<int> g_nmr_bwd_unroll{1};  // pixels per lane per trip in the NMR edge scans (1, 2 or 4)
 }  // namespace
 
 int b200r_option_nmr_bwd_unroll() { return g_nmr_bwd_unroll.load(); }
