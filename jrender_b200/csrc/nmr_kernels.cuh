@@ -278,9 +278,15 @@ k_nmr_forward(const NmrParams P, const NmrRec* __restrict__ recs, const uint2* _
                             else { w *= tif[k] - base_i; tii[k] = base_i + 1; }
                         }
                         const int isc = tii[0] * ts * ts + tii[1] * ts + tii[2];
-                        np0 += w * __ldg(texture + isc * 3 + 0);
-                        np1 += w * __ldg(texture + isc * 3 + 1);
-                        np2 += w * __ldg(texture + isc * 3 + 2);
+                        // texture_size 1: ts - 1 - eps < 0 and the "+1" taps leave the face's block; the
+                        // reference reads whatever follows (next faces' texels; past the tensor for the
+                        // last faces).  Taps inside the tensor are read likewise, taps past it give 0.
+                        const size_t tap = ((size_t)b * nf + best) * ts * ts * ts + (size_t)isc;
+                        if (isc >= 0 && tap < (size_t)P.B * nf * ts * ts * ts) {
+                            np0 += w * __ldg(texture + isc * 3 + 0);
+                            np1 += w * __ldg(texture + isc * 3 + 1);
+                            np2 += w * __ldg(texture + isc * 3 + 2);
+                        }
                         sidx[pn] = isc;
                         sw[pn] = w;
                     }
@@ -534,6 +540,8 @@ k_nmr_backward_maps(const float* __restrict__ faces, const int* __restrict__ fac
         for (int pn = 0; pn < 8; pn++) {
             const float w = __ldg(sampling_weight_map + i * 8 + pn);
             const int isc = __ldg(sampling_index_map + i * 8 + pn);
+            const size_t tap = ((size_t)bn * nf + fn) * ts * ts * ts + (size_t)isc;
+            if (isc < 0 || tap >= (size_t)batch_size * nf * ts * ts * ts) continue;  // tap past the tensor (ts == 1, see K8)
             atomicAdd(gt + isc * 3 + 0, w * g0);
             atomicAdd(gt + isc * 3 + 1, w * g1);
             atomicAdd(gt + isc * 3 + 2, w * g2);

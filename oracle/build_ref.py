@@ -151,6 +151,127 @@ extern "C" int ref_softras_forward_c2f(const float* faces, const float* textures
 '''
 
 
+# ---------------------------------------------------------------- NMR (dr_type='n3mr')
+# Launchers restating the cuda_src blocks of jrender/renderer/dr/n3mr/cuda/rasterize.py:
+# :163-217 (K7: fills, thread mapping by power-of-two face count, lock buffer), :299-339 (K8),
+# :614-647 (K9), :696-726 (K10), :790-823 (K11).  K7 takes image_size and the three return flags as
+# template arguments (the reference bakes them into the JIT source), so a fixed set is instantiated.
+LAUNCH_NMR_K7 = r'''
+namespace {
+__global__ void ref_fill_f32(float* p, size_t n, float v) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+template <int IS, int RGB, int A, int D>
+void launch_k7(const float* faces, float* faces_inv, int32_t* fim, float* wm, float* dm, float* finv, int B, int nf,
+               float near_, float far_, int nbits, int32_t* lock) {
+    const int threads = 256;
+    const dim3 blocks((B * (1 << nbits) - 1) / threads + 1);
+    forward_face_index_map_cuda_kernel<float32, IS, RGB, A, D><<<blocks, threads>>>(faces, faces_inv, fim, wm, dm, finv, B, nf, near_, far_, nbits, lock);
+}
+template <int IS>
+int dispatch_flags(int flags, const float* faces, float* faces_inv, int32_t* fim, float* wm, float* dm, float* finv, int B, int nf,
+                   float near_, float far_, int nbits, int32_t* lock) {
+    switch (flags) {
+        case 0: launch_k7<IS, 0, 0, 0>(faces, faces_inv, fim, wm, dm, finv, B, nf, near_, far_, nbits, lock); break;
+        case 1: launch_k7<IS, 1, 0, 0>(faces, faces_inv, fim, wm, dm, finv, B, nf, near_, far_, nbits, lock); break;
+        case 2: launch_k7<IS, 0, 1, 0>(faces, faces_inv, fim, wm, dm, finv, B, nf, near_, far_, nbits, lock); break;
+        case 3: launch_k7<IS, 1, 1, 0>(faces, faces_inv, fim, wm, dm, finv, B, nf, near_, far_, nbits, lock); break;
+        case 4: launch_k7<IS, 0, 0, 1>(faces, faces_inv, fim, wm, dm, finv, B, nf, near_, far_, nbits, lock); break;
+        case 5: launch_k7<IS, 1, 0, 1>(faces, faces_inv, fim, wm, dm, finv, B, nf, near_, far_, nbits, lock); break;
+        case 6: launch_k7<IS, 0, 1, 1>(faces, faces_inv, fim, wm, dm, finv, B, nf, near_, far_, nbits, lock); break;
+        default: launch_k7<IS, 1, 1, 1>(faces, faces_inv, fim, wm, dm, finv, B, nf, near_, far_, nbits, lock); break;
+    }
+    return 0;
+}
+}  // namespace
+
+// face_inv_map_elems: number of floats in face_inv_map (B*is*is*9 when return_depth, else 1)
+extern "C" int ref_nmr_forward_face_index_map(const float* faces, float* faces_inv, int32_t* face_index_map, float* weight_map,
+                                              float* depth_map, float* face_inv_map, int32_t* lock, int B, int nf,
+                                              int image_size, float near_, float far_, int return_rgb, int return_alpha,
+                                              int return_depth, long face_inv_map_elems) {
+    const size_t npix = (size_t)B * image_size * image_size;
+    cudaMemset(face_index_map, 0xFF, npix * sizeof(int32_t));                      // thrust::fill(-1)
+    cudaMemset(weight_map, 0, npix * 3 * sizeof(float));
+    ref_fill_f32<<<(unsigned)((npix + 255) / 256), 256>>>(depth_map, npix, far_);    // thrust::fill(far)
+    cudaMemset(face_inv_map, 0, (size_t)face_inv_map_elems * sizeof(float));
+    cudaMemset(lock, 0, npix * sizeof(int32_t));
+    int nbits = 0;
+    while ((1 << nbits) < nf) nbits++;   // any n with 2^n >= num_faces maps threads to (batch, face) identically
+    const int flags = (return_rgb ? 1 : 0) | (return_alpha ? 2 : 0) | (return_depth ? 4 : 0);
+    switch (image_size) {
+        case 32: dispatch_flags<32>(flags, faces, faces_inv, face_index_map, weight_map, depth_map, face_inv_map, B, nf, near_, far_, nbits, lock); break;
+        case 48: dispatch_flags<48>(flags, faces, faces_inv, face_index_map, weight_map, depth_map, face_inv_map, B, nf, near_, far_, nbits, lock); break;
+        case 64: dispatch_flags<64>(flags, faces, faces_inv, face_index_map, weight_map, depth_map, face_inv_map, B, nf, near_, far_, nbits, lock); break;
+        case 256: dispatch_flags<256>(flags, faces, faces_inv, face_index_map, weight_map, depth_map, face_inv_map, B, nf, near_, far_, nbits, lock); break;
+        default: return -1;  // image size not instantiated
+    }
+    cudaError_t e = cudaDeviceSynchronize();
+    return (int)(e != cudaSuccess ? e : cudaGetLastError());
+}
+'''
+
+LAUNCH_NMR_K8 = r'''
+extern "C" int ref_nmr_forward_texture_sampling(const float* faces, const float* textures, const int32_t* face_index_map,
+                                                const float* weight_map, const float* depth_map, float* rgb_map,
+                                                int32_t* sampling_index_map, float* sampling_weight_map, int B, int nf,
+                                                int image_size, int texture_size, float eps) {
+    const size_t npix = (size_t)B * image_size * image_size;
+    cudaMemset(rgb_map, 0, npix * 3 * sizeof(float));
+    cudaMemset(sampling_index_map, 0, npix * 8 * sizeof(int32_t));
+    cudaMemset(sampling_weight_map, 0, npix * 8 * sizeof(float));
+    const int threads = 512;
+    const dim3 blocks((unsigned)((npix - 1) / threads + 1));
+    forward_texture_sampling_cuda_kernel<float32><<<blocks, threads>>>(faces, textures, face_index_map, weight_map, depth_map, rgb_map,
+                                                                       sampling_index_map, sampling_weight_map, (size_t)B, nf,
+                                                                       image_size, texture_size, eps);
+    cudaError_t e = cudaDeviceSynchronize();
+    return (int)(e != cudaSuccess ? e : cudaGetLastError());
+}
+'''
+
+LAUNCH_NMR_K9 = r'''
+extern "C" int ref_nmr_backward_pixel_map(const float* faces, int32_t* face_index_map, float* rgb_map, float* alpha_map,
+                                          float* grad_rgb_map, float* grad_alpha_map, float* grad_faces, int B, int nf,
+                                          int image_size, float eps, int return_rgb, int return_alpha) {
+    cudaMemset(grad_faces, 0, (size_t)B * nf * 9 * sizeof(float));
+    const int threads = 512;
+    const dim3 blocks(((size_t)B * nf - 1) / threads + 1);
+    backward_pixel_map_cuda_kernel<float32><<<blocks, threads>>>(faces, face_index_map, rgb_map, alpha_map, grad_rgb_map, grad_alpha_map,
+                                                                 grad_faces, (size_t)B, (size_t)nf, image_size, eps, return_rgb, return_alpha);
+    cudaError_t e = cudaDeviceSynchronize();
+    return (int)(e != cudaSuccess ? e : cudaGetLastError());
+}
+'''
+
+LAUNCH_NMR_K10 = r'''
+extern "C" int ref_nmr_backward_textures(const int32_t* face_index_map, float* sampling_weight_map, int32_t* sampling_index_map,
+                                         float* grad_rgb_map, float* grad_textures, int B, int nf, int image_size, int texture_size) {
+    cudaMemset(grad_textures, 0, (size_t)B * nf * texture_size * texture_size * texture_size * 3 * sizeof(float));
+    const int threads = 512;
+    const dim3 blocks(((size_t)B * image_size * image_size - 1) / threads + 1);
+    backward_textures_cuda_kernel<float32><<<blocks, threads>>>(face_index_map, sampling_weight_map, sampling_index_map, grad_rgb_map,
+                                                                grad_textures, (size_t)B, (size_t)nf, image_size, (size_t)texture_size);
+    cudaError_t e = cudaDeviceSynchronize();
+    return (int)(e != cudaSuccess ? e : cudaGetLastError());
+}
+'''
+
+LAUNCH_NMR_K11 = r'''
+extern "C" int ref_nmr_backward_depth_map(const float* faces, const float* depth_map, const int32_t* face_index_map,
+                                          const float* face_inv_map, const float* weight_map, float* grad_depth_map,
+                                          float* grad_faces, int B, int nf, int image_size) {
+    const int threads = 512;
+    const dim3 blocks(((size_t)B * image_size * image_size - 1) / threads + 1);
+    backward_depth_map_cuda_kernel<float32><<<blocks, threads>>>(faces, depth_map, face_index_map, face_inv_map, weight_map,
+                                                                 grad_depth_map, grad_faces, (size_t)B, (size_t)nf, image_size);
+    cudaError_t e = cudaDeviceSynchronize();
+    return (int)(e != cudaSuccess ? e : cudaGetLastError());
+}
+'''
+
+
 def generate():
     os.makedirs(OUT, exist_ok=True)
     base = os.path.join(REFERENCE, "jrender/renderer/dr/softras/cuda")
@@ -162,6 +283,17 @@ def generate():
     hdr = _capture(os.path.join(base, "soft_rasterize_coarse_to_fine.py"), "forward_soft_rasterize_coarse_to_fine", 6,
                    extra=[64, 1, 100, 1e-3, 1e-5, 2, 9.21, 1e-4, 1, 2, 0, 1, 64, 100])
     files.append(("ref_softras_c2f.cu", PREAMBLE + hdr + LAUNCH_C2F))
+    nmr = os.path.join(REFERENCE, "jrender/renderer/dr/n3mr/cuda/rasterize.py")
+    hdr = _capture(nmr, "forward_face_index_map", 6, extra=[64, 0.1, 100.0, 1, 1, 1])
+    files.append(("ref_nmr_k7.cu", PREAMBLE + hdr + LAUNCH_NMR_K7))
+    hdr = _capture(nmr, "forward_texture_sampling", 8, extra=[64, 1e-3])
+    files.append(("ref_nmr_k8.cu", PREAMBLE + hdr + LAUNCH_NMR_K8))
+    hdr = _capture(nmr, "backward_pixel_map", 7, extra=[64, 1e-3, 1, 1])
+    files.append(("ref_nmr_k9.cu", PREAMBLE + hdr + LAUNCH_NMR_K9))
+    hdr = _capture(nmr, "backward_textures", 5, extra=[100])
+    files.append(("ref_nmr_k10.cu", PREAMBLE + hdr + LAUNCH_NMR_K10))
+    hdr = _capture(nmr, "backward_depth_map", 7, extra=[64])
+    files.append(("ref_nmr_k11.cu", PREAMBLE + hdr + LAUNCH_NMR_K11))
     paths = []
     for name, text in files:
         p = os.path.join(OUT, name)

@@ -39,11 +39,91 @@ def fixtures():
     yield "sphere3280_default_64", fv3, tex3, dict(image_size=64)
 
 
+def _fill_back(fv, tex):
+    """N3mrRasterizer.render_rgb, rasterizer.py:83-88: reversed-winding copies appended, textures permuted."""
+    fv = np.concatenate([fv, fv[:, :, ::-1]], axis=1)
+    tex = np.concatenate([tex, tex.transpose(0, 1, 4, 3, 2, 5)], axis=1)
+    return np.ascontiguousarray(fv), np.ascontiguousarray(tex)
+
+
+def nmr_fixtures():
+    """(name, faces [B,nf,3,3], textures [B,nf,ts,ts,ts,3], kwargs of oracle.nmr.forward)"""
+    rng = np.random.default_rng(5)
+    fv, _ = wl.make_scene(280, batch=1)
+    tex = rng.random((1, fv.shape[1], 2, 2, 2, 3), dtype=np.float32)
+    f2, t2 = _fill_back(fv, tex)
+    yield "nmr_sphere280_fillback_ts2_64", f2, t2, dict(image_size=64, near=0.1, far=100.0, eps=1e-3, background_color=(0, 0, 0),
+                                                        return_rgb=True, return_alpha=True, return_depth=True)
+    # (texture_size 1 is left out on purpose: the reference's trilinear taps then leave the face's
+    # block and, for the last faces, the tensor -- undefined behaviour; see oracle/nmr_oracle.c K8)
+    tex1 = rng.random((1, fv.shape[1], 4, 4, 4, 3), dtype=np.float32)
+    yield "nmr_sphere280_ts4_bg_48", fv, tex1, dict(image_size=48, near=0.1, far=100.0, eps=1e-3, background_color=(0.2, 0.4, 0.6),
+                                                    return_rgb=True, return_alpha=True, return_depth=False)
+    fvr, _ = wl.random_triangles(2, 120, seed=11)
+    texr = rng.random((2, 120, 3, 3, 3, 3), dtype=np.float32)
+    yield "nmr_random120_ts3_nearfar_32", fvr, texr, dict(image_size=32, near=1.5, far=3.0, eps=1e-3, background_color=(1, 1, 1),
+                                                          return_rgb=True, return_alpha=False, return_depth=True)
+    fv3, _ = wl.make_scene(3280, batch=1)
+    tex3 = rng.random((1, fv3.shape[1], 2, 2, 2, 3), dtype=np.float32)
+    f3, t3 = _fill_back(fv3, tex3)
+    yield "nmr_sphere3280_alpha_64", f3, t3, dict(image_size=64, near=0.1, far=100.0, eps=1e-3, background_color=(0, 0, 0),
+                                                  return_rgb=False, return_alpha=True, return_depth=False)
+
+
+def nmr_main(out_dir, report):
+    import torch
+    from oracle import nmr as onmr
+    for name, faces, tex, kw in nmr_fixtures():
+        H = kw["image_size"]
+        B = faces.shape[0]
+        flags = (kw["return_rgb"], kw["return_alpha"], kw["return_depth"])
+        rng = np.random.default_rng(7)
+        grads = (rng.uniform(-1, 1, (B, H, H, 3)).astype(np.float32), rng.uniform(-1, 1, (B, H, H)).astype(np.float32),
+                 rng.uniform(-1, 1, (B, H, H)).astype(np.float32))
+        ref = ref_gpu.nmr_run(faces, tex, H, kw["near"], kw["far"], kw["eps"], kw["background_color"], flags, grads)
+        cpu = onmr.forward(faces, tex if flags[0] else None, **kw)
+        gf, gt = onmr.backward(faces, tex if flags[0] else None, cpu, H, kw["eps"], grads[0], grads[1], grads[2], *flags)
+        cpu["grad_faces"] = gf
+        if gt is not None:
+            cpu["grad_textures"] = gt
+        save = dict(faces=faces, textures=tex, grad_rgb_map=grads[0], grad_alpha_map=grads[1], grad_depth_map=grads[2],
+                    params=json.dumps(kw),
+                    provenance=json.dumps(dict(gpu=torch.cuda.get_device_name(0),
+                                               nvcc="12.9 -O3 -gencode arch=compute_100a,code=sm_100a (fmad default on)",
+                                               source="jrender/renderer/dr/n3mr/cuda/rasterize.py kernels via oracle/build_ref.py")))
+        for k, v in ref.items():
+            if k in ("alpha_map", "rgb_raw"):
+                continue  # alpha = (face_index_map >= 0); rgb_raw = rgb_map before the background mix
+            save[k] = v.astype(np.int16) if k == "face_index_map" and faces.shape[1] < 32767 else v
+        np.savez_compressed(os.path.join(out_dir, "ref_gpu_%s.npz" % name), **save)
+        r = dict(name=name, face_index_equal_frac=float((ref["face_index_map"] == cpu["face_index_map"]).mean()))
+        same = ref["face_index_map"] == cpu["face_index_map"]
+        for k in ("weight_map", "depth_map", "rgb_map", "sampling_index_map", "sampling_weight_map", "face_inv_map",
+                  "grad_faces", "grad_textures"):
+            if k not in ref or cpu.get(k) is None:
+                continue
+            a, b = ref[k].astype(np.float64), np.asarray(cpu[k]).astype(np.float64)
+            if a.shape[:3] == same.shape and k not in ("grad_faces", "grad_textures"):
+                m = np.broadcast_to(same.reshape(same.shape + (1,) * (a.ndim - 3)), a.shape)   # pixels where both picked the same face
+            else:
+                m = np.ones(a.shape, bool)
+            m = m & ~(np.isnan(a) | np.isnan(b))
+            d = np.abs(a - b)[m]
+            r[k] = dict(max_abs=float(d.max()) if d.size else 0.0, mean_abs=float(d.mean()) if d.size else 0.0,
+                        max_ref=float(np.abs(a[m]).max()) if d.size else 0.0)
+        report.append(r)
+        print(json.dumps(r), flush=True)
+
+
 def main():
     import torch
     out_dir = os.path.join("gpurun_out", "golden")
     os.makedirs(out_dir, exist_ok=True)
     report = []
+    if "--nmr-only" in sys.argv:
+        nmr_main(out_dir, report)
+        json.dump(report, open(os.path.join(out_dir, "report_nmr.json"), "w"), indent=1)
+        return
     for name, fv, tex, kw in fixtures():
         P = osr.Params(**kw)
         H = P["image_size"]
@@ -72,6 +152,7 @@ def main():
                         max_ref=float(np.abs(a[m]).max()) if d.size else 0.0, nan_ref=int(np.isnan(a).sum()), nan_cpu=int(np.isnan(b).sum()))
         report.append(r)
         print(json.dumps(r), flush=True)
+    nmr_main(out_dir, report)
     json.dump(report, open(os.path.join(out_dir, "report.json"), "w"), indent=1)
 
 

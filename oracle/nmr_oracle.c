@@ -144,7 +144,13 @@ void nmr_oracle_texture_sampling(const float *faces, const float *textures, cons
                 }
             }
             const int isc = tii[0] * ts * ts + tii[1] * ts + tii[2];
-            for (int k = 0; k < 3; k++) new_pixel[k] += w * texture[isc * 3 + k];
+            /* texture_size 1 (the Mesh default texture_res): ts - 1 - eps < 0, so the
+             * "+1" taps index past the face's own block -- the reference reads the next faces'
+             * texels (and, for the last faces, past the tensor: UB).  Restated as: taps inside the
+             * tensor are read as the reference reads them, taps past its end contribute 0. */
+            const size_t tap = ((size_t)bn * nf + face_index) * ts * ts * ts + (size_t)isc;
+            if (isc >= 0 && tap < (size_t)batch_size * nf * ts * ts * ts)
+                for (int k = 0; k < 3; k++) new_pixel[k] += w * texture[isc * 3 + k];
             sampling_index_map[i * 8 + pn] = isc;
             sampling_weight_map[i * 8 + pn] = w;
         }
@@ -298,6 +304,7 @@ void nmr_oracle_backward_textures(const int32_t *face_index_map, const float *sa
         for (int pn = 0; pn < 8; pn++) {
             const float w = sampling_weight_map[i * 8 + pn];
             const int isc = sampling_index_map[i * 8 + pn];
+            if (isc < 0 || base + (size_t)isc * 3 + 2 >= ntex) continue; /* tap past the tensor (ts == 1, see K8) */
             for (int k = 0; k < 3; k++) acc[base + (size_t)isc * 3 + k] += (double)(w * grad_rgb_map[i * 3 + k]);
         }
     }

@@ -21,7 +21,9 @@ import pytest
 from oracle import softras as osr
 from tests.conftest import ROOT
 
-FILES = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "ref_gpu_*.npz")))
+ALL = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "ref_gpu_*.npz")))
+FILES = [p for p in ALL if "ref_gpu_nmr_" not in p]        # SoftRas fixtures
+NMR_FILES = [p for p in ALL if "ref_gpu_nmr_" in p]        # NMR (dr_type='n3mr') fixtures
 
 
 def rel_l1(ref, got):
@@ -65,3 +67,43 @@ def test_oracle_matches_reference_kernels(path):
         assert rel_l1(ref_gt[:, :, 0], gt.sum(2)) <= 2e-3
     else:
         assert rel_l1(z["grad_textures"], gt) <= (5e-2 if subpixel else 2e-3)
+
+
+# --------------------------------------------------------------------------- NMR (dr_type='n3mr')
+# tests/golden/ref_gpu_nmr_*.npz: outputs of the reference's K7-K11 kernel strings
+# (jrender/renderer/dr/n3mr/cuda/rasterize.py) compiled by oracle/build_ref.py and run on a B200
+# through oracle/ref_gpu.nmr_run (host semantics of n3mr.py:29-123).  Measured differences
+# (gpurun_out/golden/report_nmr.json, FMA contraction in the reference build only): face_index_map
+# identical on every pixel of every fixture; weight / rgb / sampling weights <= 5e-5 (9e-4 on the
+# sub-pixel mesh), depth <= 3e-5, face_inv <= 9e-4 of values up to 146, grad_faces <= 2.6e-4 of max,
+# grad_textures <= 5e-5.  Thresholds are ~4x those.
+def test_nmr_golden_files_present():
+    assert len(NMR_FILES) >= 4
+    prov = json.loads(str(np.load(NMR_FILES[0])["provenance"]))
+    assert "B200" in prov["gpu"] and "n3mr/cuda/rasterize.py" in prov["source"]
+
+
+@pytest.mark.parametrize("path", NMR_FILES, ids=[os.path.basename(p)[12:-4] for p in NMR_FILES])
+def test_nmr_oracle_matches_reference_kernels(path):
+    from oracle import nmr as onmr
+    z = np.load(path)
+    kw = json.loads(str(z["params"]))
+    faces, tex = z["faces"], z["textures"]
+    flags = (kw["return_rgb"], kw["return_alpha"], kw["return_depth"])
+    H = kw["image_size"]
+    cpu = onmr.forward(faces, tex if flags[0] else None, **kw)
+    gf, gt = onmr.backward(faces, tex if flags[0] else None, cpu, H, kw["eps"], z["grad_rgb_map"], z["grad_alpha_map"],
+                           z["grad_depth_map"], *flags)
+    subpixel = "3280" in path
+    assert np.array_equal(z["face_index_map"].astype(np.int32), cpu["face_index_map"])     # every pixel, every fixture
+    assert np.abs(z["weight_map"] - cpu["weight_map"]).max() <= (4e-3 if subpixel else 2e-4)
+    assert np.abs(z["depth_map"] - cpu["depth_map"]).max() <= 1.2e-4
+    if flags[0]:
+        assert np.array_equal(z["sampling_index_map"], cpu["sampling_index_map"])
+        assert np.abs(z["sampling_weight_map"] - cpu["sampling_weight_map"]).max() <= 2e-4
+        assert np.abs(z["rgb_map"] - cpu["rgb_map"]).max() <= 1.2e-4
+        assert np.abs(z["grad_textures"] - gt).max() <= 2e-4 * max(1.0, float(np.abs(gt).max()))
+    if flags[2]:
+        ref_inv = z["face_inv_map"].reshape(cpu["face_inv_map"].shape)
+        assert np.abs(ref_inv - cpu["face_inv_map"]).max() <= 4e-5 * np.abs(cpu["face_inv_map"]).max()
+    assert np.abs(z["grad_faces"] - gf).max() <= 1e-3 * np.abs(gf).max()

@@ -57,6 +57,14 @@ def test_texture_size_1_and_odd_image(cuda_device):
     check(faces, tex, 75)
 
 
+def test_texture_size_1_last_faces_visible(cuda_device):
+    # texture_size 1 without fill_back: the "+1" trilinear taps of the LAST faces point past the
+    # texture tensor (reference UB); product and oracle both read them as 0 and drop their gradient
+    faces, tex = nmr_scene(280, batch=2, ts=1, fill_back=False)
+    ref, got = check(faces, tex, 48, bg=(0.1, 0.2, 0.3))
+    assert (ref["face_index_map"] >= 276).any()
+
+
 def test_overlapping_random_triangles_and_near_far(cuda_device):
     from jrender_b200 import workloads as wl
     fv, _ = wl.random_triangles(2, 200, seed=5, zmin=0.5, zmax=3.0)
