@@ -65,7 +65,7 @@ cudaError_t b200r_launch_backward(const SoftRasParams& P, const SoftRasWorkspace
         e = cudaMemsetAsync(grad_textures, 0, sizeof(float) * 3 * (size_t)P.T * nfaces, st);
         if (e != cudaSuccess) return e;
     }
-    B200R_DISPATCH_DIST_RGB((e = (D == 2 && R == 1 && !exact) ? launch_lane<D, R, (D != 2 || R != 1)>(P, W, textures, soft_colors, aggrs_info, ids, grad_soft_colors, grad_textures, st) : launch_lane<D, R, true>(P, W, textures, soft_colors, aggrs_info, ids, grad_soft_colors, grad_textures, st)))
+    B200R_DISPATCH_DIST_RGB((e = (D == 2 && !exact) ? launch_lane<D, R, (D != 2)>(P, W, textures, soft_colors, aggrs_info, ids, grad_soft_colors, grad_textures, st) : launch_lane<D, R, true>(P, W, textures, soft_colors, aggrs_info, ids, grad_soft_colors, grad_textures, st)))
     if (e != cudaSuccess) return e;
     {
         B200rProfScope prof(B200R_K_SOFTRAS_BWD_FINALIZE, st);

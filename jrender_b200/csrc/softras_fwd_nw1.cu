@@ -47,6 +47,6 @@ cudaError_t b200r_launch_forward_nw1(const SoftRasParams& P, const SoftRasWorksp
                                      float* aggrs_info, int32_t* ids, int variant, int persistent, int exact, cudaStream_t st) {
     cudaError_t e = cudaSuccess;
     (void)variant;  // only the per-lane-list variant is built for this layout
-    B200R_DISPATCH_DIST_RGB((e = (D == 2 && R == 1 && !exact) ? launch_v<D, R, 1, (D != 2 || R != 1)>(P, W, textures, soft_colors, aggrs_info, ids, persistent, st) : launch_v<D, R, 1, true>(P, W, textures, soft_colors, aggrs_info, ids, persistent, st)))
+    B200R_DISPATCH_DIST_RGB((e = (D == 2 && !exact) ? launch_v<D, R, 1, (D != 2)>(P, W, textures, soft_colors, aggrs_info, ids, persistent, st) : launch_v<D, R, 1, true>(P, W, textures, soft_colors, aggrs_info, ids, persistent, st)))
     return e;
 }

@@ -216,11 +216,16 @@ class SoftRasterizer(nn.Module):
 
     def forward(self, mesh, mode=None):
         image_size = self.image_size * (2 if self.anti_aliasing else 1)
+        # mode='silhouettes' returns images[:, 3] only (rasterizer.py:56-57).  Alpha and its gradient
+        # do not depend on the colour aggregation (with a zero colour gradient every colour term of
+        # the backward is exactly 0), so the kernels run with the colour path compiled out
+        # (B200R_RGB_NONE): same alpha, same gradients, no texture sampling / softmax.
+        aggr_func_rgb = 'none' if mode == 'silhouettes' else self.aggr_func_rgb
         images = soft_rasterize(mesh.face_vertices, mesh.face_textures, image_size,
                                 self.background_color, self.near, self.far,
                                 self.fill_back, self.eps,
                                 self.sigma_val, self.dist_func, self.dist_eps,
-                                self.gamma_val, self.aggr_func_rgb, self.aggr_func_alpha,
+                                self.gamma_val, aggr_func_rgb, self.aggr_func_alpha,
                                 self.texture_type, self.bin_size, self.max_elems_per_bin,
                                 self.max_faces_per_pixel_for_grad)
 

@@ -179,6 +179,36 @@ def test_public_module_api_and_antialiasing(cuda_device):
     assert np.abs(r(m, "silhouettes").cpu().numpy() - pooled[:, 3]).max() <= 2 * COLOR_ATOL
 
 
+@pytest.mark.parametrize("rgb", ["softmax", "hard"])
+def test_silhouette_mode_runs_without_the_colour_path(cuda_device, rgb):
+    """mode='silhouettes' compiles the colour aggregation out (B200R_RGB_NONE): alpha must be the same
+    bits as channel 3 of the full render and the vertex gradient the same as back-propagating through
+    the full render with a zero colour gradient (the oracle run in the reference's own mode)."""
+    import torch
+    from jrender_b200 import SoftRasterizer
+
+    class M:
+        pass
+    fv, tex = wl.make_scene(280, batch=2)
+    m = M()
+    m.face_vertices = torch.from_numpy(fv).cuda().requires_grad_(True)
+    m.face_textures = torch.from_numpy(tex).cuda()
+    r = SoftRasterizer(image_size=96, fill_back=True, aggr_func_rgb=rgb, sigma_val=1e-4)
+    sil = r(m, "silhouettes")
+    full_alpha, _ = r(m)
+    assert torch.equal(sil, full_alpha)
+    g = torch.from_numpy(np.random.default_rng(3).uniform(-1, 1, (2, 96, 96)).astype(np.float32)).cuda()
+    sil.backward(g)
+    P = osr.Params(image_size=96, aggr_func_rgb=rgb, sigma_val=1e-4)
+    ref = osr.forward(fv, tex, P)
+    g4 = np.zeros((2, 4, 96, 96), np.float32)
+    g4[:, 3] = g.cpu().numpy()
+    gf, _ = osr.backward(fv, tex, ref, g4, P)
+    assert np.array_equal(sil.detach().cpu().numpy(), ref["soft_colors"][:, 3]) or \
+        np.abs(sil.detach().cpu().numpy() - ref["soft_colors"][:, 3]).max() <= COLOR_ATOL
+    assert np.abs(m.face_vertices.grad.cpu().numpy() - gf).max() <= GRAD_RTOL * np.abs(gf).max()
+
+
 @pytest.mark.parametrize("nfaces,min_same,grad_l1", [(3280, 0.998, 0.05), (39200, 0.98, 0.15)])
 def test_against_reference_kernels_on_gpu(cuda_device, nfaces, min_same, grad_l1):
     """Product vs the reference's OWN kernels (oracle/_ref, compiled from /root/reference by
