@@ -62,7 +62,7 @@ def iou(a, b):
 
 
 def run(iters=200, image_size=64, batch_size=24, filename_input=None, camera_input=None, template_mesh=None,
-        output_dir=None, device="cuda", verbose=True):
+        output_dir=None, device="cuda", verbose=True, cuda_graph=False):
     dev = torch.device(device)
     if template_mesh:
         v, f = jr.load_obj(template_mesh)
@@ -87,23 +87,53 @@ def run(iters=200, image_size=64, batch_size=24, filename_input=None, camera_inp
         el = 30.0 * torch.sin(torch.arange(batch_size, device=dev, dtype=torch.float32))
         renderer.transform.set_eyes_from_angles(torch.full((batch_size,), 2.732 * 2, device=dev), el, az)
         target = synthetic_targets(renderer, f, batch_size, dev)
-    optimizer = torch.optim.Adam(model.parameters(), 0.01, betas=(0.5, 0.99))
+    optimizer = torch.optim.Adam(model.parameters(), 0.01, betas=(0.5, 0.99), capturable=cuda_graph)
     hist = []
-    torch.cuda.synchronize()
-    t0 = time.time()
-    for i in range(iters):
+
+    def iteration():
         mesh, laplacian_loss, flatten_loss = model(batch_size)
         images_pred = renderer.render_mesh(mesh, mode='silhouettes')
         loss = neg_iou_loss(images_pred, target) + 0.03 * laplacian_loss + 0.0003 * flatten_loss
         optimizer.zero_grad(set_to_none=True)
         loss.backward()
         optimizer.step()
+        return loss, images_pred
+
+    def log(i, loss, images_pred):
         if i % 20 == 0 or i == iters - 1:
             hist.append((i, float(loss.item()), iou(images_pred.detach(), target)))
             if verbose:
                 print("iter %4d  loss %.4f  IoU %.4f" % hist[-1], flush=True)
-    torch.cuda.synchronize()
-    dt = time.time() - t0
+
+    if cuda_graph:
+        # The whole iteration (model, transform, raster kernels through the C ABI, losses, autograd
+        # backward, Adam) is captured once and replayed: at 64^2 the loop is launch-bound, ~400 small
+        # kernels per iteration.  The library enqueues everything on the capturing stream and never
+        # synchronises, so it is capture-safe.  The warm-up iterations below are part of the fit.
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for i in range(3):
+                log(i, *iteration())
+        torch.cuda.current_stream(dev).wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        optimizer.zero_grad(set_to_none=True)
+        with torch.cuda.graph(graph):
+            static_loss, static_pred = iteration()
+        torch.cuda.synchronize()
+        t0 = time.time()
+        for i in range(4, iters):
+            graph.replay()
+            log(i, static_loss, static_pred)
+        torch.cuda.synchronize()
+        dt = (time.time() - t0) * iters / max(1, iters - 4)
+    else:
+        torch.cuda.synchronize()
+        t0 = time.time()
+        for i in range(iters):
+            log(i, *iteration())
+        torch.cuda.synchronize()
+        dt = time.time() - t0
     if output_dir:
         os.makedirs(output_dir, exist_ok=True)
         jr.save_obj(os.path.join(output_dir, 'plane.obj'), model(1)[0].vertices[0], model.faces[0])
@@ -119,6 +149,8 @@ if __name__ == '__main__':
     ap.add_argument('-b', '--batch-size', type=int, default=24)
     ap.add_argument('--iters', type=int, default=200)
     ap.add_argument('--image-size', type=int, default=64)
+    ap.add_argument('--cuda-graph', action='store_true', help='capture one iteration in a CUDA graph and replay it')
     a = ap.parse_args()
-    r = run(a.iters, a.image_size, a.batch_size, a.filename_input, a.camera_input, a.template_mesh, a.output_dir)
+    r = run(a.iters, a.image_size, a.batch_size, a.filename_input, a.camera_input, a.template_mesh, a.output_dir,
+            cuda_graph=a.cuda_graph)
     print("ms/iter %.2f  IoU %.4f -> %.4f" % (r["ms_per_iter"], r["first_iou"], r["final_iou"]))

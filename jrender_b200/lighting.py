@@ -12,10 +12,20 @@ from torch import nn
 import torch.nn.functional as F
 
 
+_CONST = {}
+
+
 def _t(x, like):
+    """Python constants (light colours / directions) live on the device once per (value, device):
+    building them per call is a pageable H2D copy, which stalls the stream and cannot be captured
+    in a CUDA graph."""
     if isinstance(x, torch.Tensor):
         return x.to(device=like.device, dtype=torch.float32)
-    return torch.tensor(x, dtype=torch.float32, device=like.device)
+    key = (repr(x), str(like.device))
+    t = _CONST.get(key)
+    if t is None:
+        t = _CONST[key] = torch.tensor(x, dtype=torch.float32, device=like.device)
+    return t
 
 
 def ambient_lighting(light, light_intensity=0.5, light_color=(1, 1, 1)):

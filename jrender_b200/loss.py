@@ -1,7 +1,7 @@
 """Mesh-fitting losses (host-side mirror in PyTorch of jrender/loss/*.py).
 
-neg_iou_loss  (iou_loss.py:1-5), LaplacianLoss (laplacian_loss.py:5-36, stored sparse here
-instead of the reference's dense nv x nv matrix -- same values), FlattenLoss
+neg_iou_loss  (iou_loss.py:1-5), LaplacianLoss (laplacian_loss.py:5-36, stored as a padded
+neighbour table instead of the reference's dense nv x nv matrix -- same values), FlattenLoss
 (flatten_loss.py:5-79, edge table built with a dictionary instead of the O(E*F) scan).
 """
 import numpy as np
@@ -27,17 +27,27 @@ class LaplacianLoss(nn.Module):
         e = np.concatenate([f[:, [0, 1]], f[:, [1, 0]], f[:, [1, 2]], f[:, [2, 1]], f[:, [2, 0]], f[:, [0, 2]]], 0)
         e = np.unique(e, axis=0)
         deg = np.bincount(e[:, 0], minlength=self.nv).astype(np.float32)
-        rows = np.concatenate([e[:, 0], np.arange(self.nv)])
-        cols = np.concatenate([e[:, 1], np.arange(self.nv)])
+        # Padded neighbour table instead of a sparse matrix: L x = diag * x + sum_k w[:, k] * x[nbr[:, k]].
+        # index_select forward / index_add backward are plain kernels (no thrust sort, no host
+        # synchronisation), so the loss can be captured in a CUDA graph; torch.sparse.mm cannot.
+        maxdeg = int(deg.max()) if e.size else 0
+        nbr = np.zeros((self.nv, max(maxdeg, 1)), np.int64)
+        w = np.zeros((self.nv, max(maxdeg, 1)), np.float32)
+        fill = np.zeros(self.nv, np.int64)
+        for a_, b_ in e:
+            nbr[a_, fill[a_]] = b_
+            w[a_, fill[a_]] = -1.0 / deg[a_]
+            fill[a_] += 1
         with np.errstate(divide='ignore', invalid='ignore'):
-            vals = np.concatenate([-1.0 / deg[e[:, 0]], deg / deg]).astype(np.float32)
-        lap = torch.sparse_coo_tensor(np.stack([rows, cols]), vals, (self.nv, self.nv)).coalesce()
-        self.register_buffer('laplacian', lap)
+            diag = (deg / deg).astype(np.float32)     # 1, or NaN for an isolated vertex like the dense 0/0
+        self.register_buffer('nbr', torch.from_numpy(nbr.reshape(-1)))
+        self.register_buffer('nbr_w', torch.from_numpy(w))
+        self.register_buffer('diag', torch.from_numpy(diag))
 
     def forward(self, x):
         batch_size = x.shape[0]
-        lap = self.laplacian.to(x.device)
-        y = torch.stack([torch.sparse.mm(lap, x[b]) for b in range(batch_size)], 0)
+        xn = torch.index_select(x, 1, self.nbr).view(batch_size, self.nv, -1, x.shape[2])
+        y = x * self.diag[None, :, None] + (xn * self.nbr_w[None, :, :, None]).sum(2)
         dims = tuple(range(y.dim())[1:])
         y = y.pow(2).sum(dims)
         if self.average:
@@ -67,10 +77,10 @@ class FlattenLoss(nn.Module):
 
     def forward(self, vertices, eps=1e-6):
         batch_size = vertices.shape[0]
-        v0s = vertices[:, self.v0s, :]
-        v1s = vertices[:, self.v1s, :]
-        v2s = vertices[:, self.v2s, :]
-        v3s = vertices[:, self.v3s, :]
+        v0s = torch.index_select(vertices, 1, self.v0s)   # backward = index_add (graph-capturable)
+        v1s = torch.index_select(vertices, 1, self.v1s)
+        v2s = torch.index_select(vertices, 1, self.v2s)
+        v3s = torch.index_select(vertices, 1, self.v3s)
 
         def half(b):
             a = v1s - v0s

@@ -19,7 +19,10 @@ def face_vertices(vertices, faces):
     bs, nv = vertices.shape[:2]
     faces = faces.long() + (torch.arange(bs, device=vertices.device) * nv)[:, None, None]
     vertices = vertices.reshape((bs * nv, vertices.shape[2]))
-    return vertices[faces]
+    # index_select: its backward is an index_add kernel (the scatter of grad_face_vertices to
+    # grad_vertices); `vertices[faces]` would back-propagate through a sort-based index_put that
+    # synchronises the host and cannot be captured in a CUDA graph
+    return torch.index_select(vertices, 0, faces.reshape(-1)).view(bs, faces.shape[1], 3, vertices.shape[1])
 
 
 class Mesh(object):
@@ -162,7 +165,7 @@ class Mesh(object):
         if self._vertex_normals_update:
             bs, nv = self.vertices.shape[:2]
             faces = (self.faces.long() + (torch.arange(bs, device=self.vertices.device) * nv)[:, None, None]).view(-1, 3)
-            vf = self.vertices.reshape((bs * nv, 3))[faces]
+            vf = torch.index_select(self.vertices.reshape((bs * nv, 3)), 0, faces.reshape(-1)).view(-1, 3, 3)
             normals = torch.zeros((bs * nv, 3), dtype=self.vertices.dtype, device=self.vertices.device)
             normals.index_add_(0, faces[:, 1], torch.cross(vf[:, 2] - vf[:, 1], vf[:, 0] - vf[:, 1], dim=1))
             normals.index_add_(0, faces[:, 2], torch.cross(vf[:, 0] - vf[:, 2], vf[:, 1] - vf[:, 2], dim=1))

@@ -11,13 +11,25 @@ from torch import nn
 import torch.nn.functional as F
 
 
+_CONST = {}
+
+
 def _t(x, like=None, dtype=torch.float32):
+    """Tensors pass through; Python / numpy constants (at, up, direction, a fixed eye) are placed on
+    the device once per (value, device) -- a per-call H2D copy would stall the stream and break CUDA
+    graph capture."""
     if isinstance(x, torch.Tensor):
         t = x.to(dtype)
-    else:
-        t = torch.tensor(np.asarray(x, dtype=np.float32), dtype=dtype)
-    if like is not None:
-        t = t.to(like.device)
+        return t.to(like.device) if like is not None else t
+    a = np.asarray(x, dtype=np.float32)
+    key = (a.tobytes(), a.shape, str(dtype), str(like.device) if like is not None else "cpu")
+    t = _CONST.get(key)
+    if t is None:
+        t = torch.tensor(a, dtype=dtype)
+        if like is not None:
+            t = t.to(like.device)
+        if len(_CONST) < 4096:
+            _CONST[key] = t
     return t
 
 
@@ -99,11 +111,18 @@ def look(vertices, eye, direction=[0, 1, 0], up=None, coordinate="right"):
     return torch.matmul(vertices, r.transpose(1, 2))
 
 
+_TAN_HALF_ANGLE = {}
+
+
 def perspective(vertices, angle=30.):
     """perspective.py:4-17."""
     if vertices.dim() != 3:
         raise ValueError('vertices Tensor should have 3 dimensions')
-    width = torch.tan(torch.tensor([angle / 180 * math.pi], dtype=torch.float32, device=vertices.device))[:, None]
+    key = (float(angle), str(vertices.device))
+    width = _TAN_HALF_ANGLE.get(key)   # device constant, built once: no per-call H2D copy (CUDA-graph safe)
+    if width is None:
+        width = _TAN_HALF_ANGLE[key] = torch.tan(
+            torch.tensor([angle / 180 * math.pi], dtype=torch.float32, device=vertices.device))[:, None]
     z = vertices[:, :, 2]
     x = vertices[:, :, 0] / z / width
     y = vertices[:, :, 1] / z / width

@@ -13,3 +13,49 @@ def test_demo2_deform_improves_iou(cuda_device):
     assert r["final_iou"] > r["first_iou"] + 0.15, r          # measured: 0.55 -> 0.78 after 80, 0.88 after 200 iterations
     losses = [h[1] for h in r["history"]]
     assert losses[-1] < 0.7 * losses[0], r
+
+
+def test_demo2_deform_under_cuda_graph(cuda_device):
+    """The whole iteration (host mirror, raster kernels through the C ABI, losses, autograd, Adam) is
+    captured once and replayed: the library must not synchronise, allocate or copy from pageable
+    host memory on the way, and the fit must follow the eager run."""
+    from examples.demo2_deform import run
+    eager = run(iters=100, image_size=64, batch_size=8, verbose=False)
+    graphed = run(iters=100, image_size=64, batch_size=8, verbose=False, cuda_graph=True)
+    assert graphed["final_iou"] > graphed["first_iou"] + 0.15, graphed
+    assert abs(graphed["final_iou"] - eager["final_iou"]) < 0.03, (eager, graphed)   # atomics order differs run to run
+
+
+def test_raster_op_replays_in_a_cuda_graph(cuda_device):
+    import numpy as np
+    import torch
+    from jrender_b200 import SoftRasterizeFunction, workloads as wl
+    fv_h, tex_h = wl.make_scene(3280, batch=2)
+    dev = torch.device("cuda:0")
+    fv = torch.from_numpy(fv_h).to(dev).requires_grad_(True)
+    tex = torch.from_numpy(tex_h).to(dev).requires_grad_(True)
+    g = torch.from_numpy(np.random.default_rng(0).uniform(-1, 1, (2, 4, 128, 128)).astype(np.float32)).to(dev)
+
+    def step():
+        fv.grad = None
+        tex.grad = None
+        img = SoftRasterizeFunction(image_size=128)(fv, tex)
+        img.backward(g)
+        return img, fv.grad, tex.grad
+    img0, gf0, gt0 = [t.clone() for t in step()]
+    side = torch.cuda.Stream(dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        step()
+    torch.cuda.current_stream(dev).wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    fv.grad = None
+    tex.grad = None
+    with torch.cuda.graph(graph):
+        img, gf, gt = step()
+    for _ in range(3):
+        graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(img, img0)
+    assert (gf - gf0).abs().max() <= 2e-5 * gf0.abs().max()
+    assert (gt - gt0).abs().max() <= 2e-5 * gt0.abs().max()
