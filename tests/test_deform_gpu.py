@@ -32,30 +32,32 @@ def test_raster_op_replays_in_a_cuda_graph(cuda_device):
     from jrender_b200 import SoftRasterizeFunction, workloads as wl
     fv_h, tex_h = wl.make_scene(3280, batch=2)
     dev = torch.device("cuda:0")
-    fv = torch.from_numpy(fv_h).to(dev).requires_grad_(True)
-    tex = torch.from_numpy(tex_h).to(dev).requires_grad_(True)
     g = torch.from_numpy(np.random.default_rng(0).uniform(-1, 1, (2, 4, 128, 128)).astype(np.float32)).to(dev)
 
-    def step():
+    def leaves():
+        return (torch.from_numpy(fv_h).to(dev).requires_grad_(True), torch.from_numpy(tex_h).to(dev).requires_grad_(True))
+
+    def step(fv, tex):
         fv.grad = None
         tex.grad = None
         img = SoftRasterizeFunction(image_size=128)(fv, tex)
         img.backward(g)
         return img, fv.grad, tex.grad
-    img0, gf0, gt0 = [t.clone() for t in step()]
+    img0, gf0, gt0 = [t.detach().clone() for t in step(*leaves())]     # eager reference on its own leaves
+    fv, tex = leaves()                                                  # fresh leaves: first used on the side stream
     side = torch.cuda.Stream(dev)
     side.wait_stream(torch.cuda.current_stream(dev))
     with torch.cuda.stream(side):
-        step()
+        step(fv, tex)
     torch.cuda.current_stream(dev).wait_stream(side)
     graph = torch.cuda.CUDAGraph()
     fv.grad = None
     tex.grad = None
     with torch.cuda.graph(graph):
-        img, gf, gt = step()
+        img, gf, gt = step(fv, tex)
     for _ in range(3):
         graph.replay()
     torch.cuda.synchronize()
-    assert torch.equal(img, img0)
+    assert torch.equal(img.detach(), img0)
     assert (gf - gf0).abs().max() <= 2e-5 * gf0.abs().max()
     assert (gt - gt0).abs().max() <= 2e-5 * gt0.abs().max()

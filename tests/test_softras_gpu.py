@@ -159,6 +159,33 @@ def test_full_size_properties_1024_39k(cuda_device):
     assert np.array_equal(got2["faces_id_buffer"], ids)
 
 
+@pytest.mark.parametrize("H,nfaces", [(2048, 3280), (4096, 280), (1000, 3280)])
+def test_large_and_odd_image_sizes(cuda_device, H, nfaces):
+    """Coarse bins grow to 128 / 256 px above 1024^2 (common.cuh b200r_geometry) and 4096 is the
+    maximum image size of the ABI; 1000 is not a multiple of the 8x4 / 16x16 tiles.  Forward against
+    the oracle on a strided row sample, backward through linearity."""
+    fv, tex = wl.make_scene(nfaces, batch=1)
+    P = osr.Params(image_size=H)
+    g = np.random.default_rng(4).uniform(-1, 1, (1, 4, H, H)).astype(np.float32)
+    got = run_cuda(fv, tex, P, grad=g, want_faces_info=False)
+    stride = H // 16
+    ref = osr.forward(fv, tex, P, row_stride=stride)
+    rows = np.arange(0, H, stride)
+    assert np.array_equal(got["faces_id_buffer"][:, :, rows], ref["faces_id_buffer"][:, :, rows])
+    assert np.abs(got["soft_colors"][:, :, rows] - ref["soft_colors"][:, :, rows]).max() <= COLOR_ATOL
+    assert (got["faces_id_buffer"][:, 0] >= 0).mean() > 0.1
+    got2 = run_cuda(fv, tex, P, grad=(0.5 * g).astype(np.float32), want_faces_info=False)
+    scale = np.abs(got["grad_faces"]).max()
+    assert scale > 0 and np.abs(got2["grad_faces"] - 0.5 * got["grad_faces"]).max() <= 4 * GRAD_RTOL * scale
+
+
+def test_image_size_above_abi_maximum_is_refused(cuda_device):
+    from jrender_b200._lib import B200RasterError
+    fv, tex = wl.make_scene(280, batch=1)
+    with pytest.raises(B200RasterError):
+        run_cuda(fv, tex, osr.Params(image_size=4104), want_faces_info=False)
+
+
 def test_public_module_api_and_antialiasing(cuda_device):
     """SoftRasterizer(mesh, mode): AA = render at 2x + 2x2 mean (rasterizer.py:45,54-55), mode slicing."""
     import torch
