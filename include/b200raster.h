@@ -134,6 +134,33 @@ B200R_API int b200r_nmr_backward(const float* faces, const int32_t* face_index_m
                                  int image_size, float eps, int return_rgb, int return_alpha,
                                  int return_depth, void* stream);
 
+/* ---- fused pre-raster geometry stage ------------------------------
+ * World-space vertices -> camera space -> projection -> per-face gather in ONE launch.  Replaces
+ * the tensor-op chain of jrender/renderer/transform/look_at.py:24-38 (or look.py:23-53),
+ * transform/perspective.py:11-16 / orthogonal.py:12-15 and structures/utils/faces_vertices.py:14-19,
+ * called from transform/transform.py:52-58 and structures/mesh.py (face_vertices property).
+ *   vertices       [vertices_batch, nv, 3]   world space; vertices_batch = B, or 1 = shared mesh
+ *   faces          [faces_batch, nf, 3] int32; faces_batch = B or 1; an index outside [0, nv) makes
+ *                  that corner NaN (the reference reads out of bounds)
+ *   eye            [eye_batch, 3] device; eye_batch = B or 1
+ *   face_vertices  [B, nf, 3, 3]   out: x, y projected (perspective: X/Z/width; orthogonal: X*scale), z = camera Z
+ *   at_or_direction, up: HOST float[3] (look_at: the `at` point; look: the viewing direction)
+ *   width_or_scale: tan(viewing_angle) (perspective.py:11-12) or viewing_scale (orthogonal)
+ * The backward overwrites grad_vertices [vertices_batch, nv, 3] with the sum over every (batch, face,
+ * corner) that references the vertex (float atomics).  No gradient for eye / at / up. */
+enum { B200R_CAM_LOOK_AT = 0, B200R_CAM_LOOK_RIGHT = 1, B200R_CAM_LOOK_LEFT = 2 };
+enum { B200R_PROJ_PERSPECTIVE = 0, B200R_PROJ_ORTHOGONAL = 1 };
+B200R_API int b200r_project_faces_forward(const float* vertices, const int32_t* faces, const float* eye,
+                                          float* face_vertices,
+                                          const float* at_or_direction, const float* up, float width_or_scale,
+                                          int camera_mode, int projection, int batch_size, int num_vertices,
+                                          int num_faces, int vertices_batch, int faces_batch, int eye_batch, void* stream);
+B200R_API int b200r_project_faces_backward(const float* vertices, const int32_t* faces, const float* eye,
+                                           const float* grad_face_vertices, float* grad_vertices,
+                                           const float* at_or_direction, const float* up, float width_or_scale,
+                                           int camera_mode, int projection, int batch_size, int num_vertices,
+                                           int num_faces, int vertices_batch, int faces_batch, int eye_batch, void* stream);
+
 /* Launch counter: number of kernels this library has launched in this process
  * (bench.py reports the delta over the timed region as "gpu_launches"). */
 B200R_API unsigned long long b200r_launch_count(void);
@@ -154,7 +181,8 @@ B200R_API int b200r_set_option(const char* name, int value);
  * dominant kernel; b200r_profile_read synchronises the outstanding events. */
 enum { B200R_K_FACE_SETUP = 0, B200R_K_COARSE_BIN = 1, B200R_K_SOFTRAS_FWD = 2, B200R_K_SOFTRAS_BWD = 3,
        B200R_K_TILE_ORDER = 4, B200R_K_NMR_SETUP = 5, B200R_K_NMR_FWD = 6, B200R_K_NMR_BWD_PIXEL = 7,
-       B200R_K_NMR_BWD_MAPS = 8, B200R_K_SOFTRAS_BWD_FINALIZE = 9, B200R_K_NMR_PACK = 10 };
+       B200R_K_NMR_BWD_MAPS = 8, B200R_K_SOFTRAS_BWD_FINALIZE = 9, B200R_K_NMR_PACK = 10,
+       B200R_K_PROJECT_FWD = 11, B200R_K_PROJECT_BWD = 12 };
 B200R_API void b200r_profile_enable(int on);
 B200R_API void b200r_profile_reset(void);
 B200R_API int b200r_profile_read(int kernel, double* total_ms, long long* launches);

@@ -12,5 +12,6 @@ from .transform import (Transform, LookAt, Look, Projection, look_at, look, pers
                         projection, get_points_from_angles)
 from .lighting import Lighting, AmbientLighting, DirectionalLighting  # noqa: F401
 from .renderer import Renderer  # noqa: F401
+from .preraster import project_faces  # noqa: F401
 from .loss import neg_iou_loss, LaplacianLoss, FlattenLoss  # noqa: F401
 from .io import load_obj, save_obj  # noqa: F401

@@ -59,6 +59,10 @@ def lib():
     L.b200r_nmr_backward.argtypes = [_P] * 15 + [C.c_size_t, _I, _I, _I, _I, _F, _I, _I, _I, _P]
     L.b200r_nmr_backward_scratch_bytes.restype = C.c_size_t
     L.b200r_nmr_backward_scratch_bytes.argtypes = [_I, _I]
+    L.b200r_project_faces_forward.restype = _I
+    L.b200r_project_faces_forward.argtypes = [_P, _P, _P, _P, _P, _P, _F] + [_I] * 8 + [_P]
+    L.b200r_project_faces_backward.restype = _I
+    L.b200r_project_faces_backward.argtypes = [_P, _P, _P, _P, _P, _P, _P, _F] + [_I] * 8 + [_P]
     L.b200r_set_option.restype = _I
     L.b200r_set_option.argtypes = [C.c_char_p, _I]
     _lib = L

@@ -35,6 +35,7 @@ class Mesh(object):
             faces = torch.from_numpy(faces).int()
         self._vertices = vertices
         self._faces = faces
+        self._projector = None
         if self._vertices.dim() == 2:
             self._vertices = self._vertices[None]
         if self._faces.dim() == 2:
@@ -124,10 +125,23 @@ class Mesh(object):
 
     @property
     def vertices(self):
+        if self._vertices is None and self._projector is not None:
+            self._vertices = self._projector.vertices()   # lazily, op by op (only if somebody asks)
         return self._vertices
+
+    def attach_projector(self, projector):
+        """Transform's fused path: `projector.face_vertices(faces)` yields the camera-space + projected
+        face_vertices in one launch from the world-space vertices (jrender_b200/preraster.py);
+        `projector.vertices()` is the op-by-op equivalent of `mesh.vertices = transform(mesh.vertices)`."""
+        self._projector = projector
+        self._vertices = None
+        self._face_vertices_update = True
+        self._surface_normals_update = True
+        self._vertex_normals_update = True
 
     @vertices.setter
     def vertices(self, vertices):
+        self._projector = None
         self._vertices = vertices
         self.num_vertices = self._vertices.shape[1]
         self._face_vertices_update = True
@@ -145,7 +159,10 @@ class Mesh(object):
     @property
     def face_vertices(self):
         if self._face_vertices_update:
-            self._face_vertices = face_vertices(self.vertices, self.faces)
+            if self._projector is not None:
+                self._face_vertices = self._projector.face_vertices(self.faces)
+            else:
+                self._face_vertices = face_vertices(self.vertices, self.faces)
             self._face_vertices_update = False
         return self._face_vertices
 
@@ -213,7 +230,8 @@ class Mesh(object):
         return cls(vertices, faces, textures, texture_res, texture_type, dr_type=dr_type, with_SSS=with_SSS)
 
     def to(self, device):
-        self._vertices = self._vertices.to(device)
+        self._vertices = self.vertices.to(device)
+        self._projector = None
         self._faces = self._faces.to(device)
         self._textures = self._textures.to(device)
         self.metallic_textures = self.metallic_textures.to(device)

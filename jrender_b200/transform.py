@@ -256,8 +256,42 @@ class Transform(nn.Module):
         self.coordinate = coordinate
 
     def forward(self, mesh):
-        mesh.vertices = self.transformer(mesh.vertices)
+        proj = self._fused_projector(mesh)
+        if proj is not None:
+            # One fused launch (csrc/preraster_api.cu) produces the rasterizer's face_vertices straight from
+            # the world-space vertices; `mesh.vertices` (camera space) stays available, evaluated lazily by
+            # the op-by-op mirror only if somebody reads it.
+            mesh.attach_projector(proj)
+        else:
+            mesh.vertices = self.transformer(mesh.vertices)
         return mesh
+
+    fused = True  # class-wide switch: False forces the op-by-op PyTorch mirror
+
+    def _fused_projector(self, mesh):
+        v = mesh.vertices
+        tr = self.transformer
+        if not (self.fused and self.camera_mode in ('look_at', 'look') and v.is_cuda and v.dtype == torch.float32):
+            return None
+        eye = tr._eye
+        if isinstance(eye, torch.Tensor) and eye.requires_grad:
+            return None   # camera optimisation: gradients w.r.t. the eye come from the op-by-op mirror
+        if not isinstance(eye, torch.Tensor) and isinstance(eye, (list, tuple)) and any(isinstance(c, torch.Tensor) for c in eye):
+            return None
+        from .preraster import project_faces
+        kw = dict(camera_mode=self.camera_mode, perspective=tr.perspective, viewing_angle=tr.viewing_angle,
+                  viewing_scale=tr.viewing_scale)
+        if self.camera_mode == 'look':
+            kw.update(direction=tr.camera_direction, up=tr.up, coordinate=tr.coordinate)
+        transformer = tr
+
+        class _Projector(object):
+            def face_vertices(self, faces):
+                return project_faces(v, faces, eye, **kw)
+
+            def vertices(self):
+                return transformer(v)
+        return _Projector()
 
     execute = forward
 

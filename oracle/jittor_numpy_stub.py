@@ -1,0 +1,110 @@
+"""A numpy-backed stand-in for the handful of `jittor` calls the reference's HOST-side transform
+code makes (TEST INFRASTRUCTURE -- never imported by the product).
+
+Jittor cannot be installed here (no network), but jrender/renderer/transform/{look_at,look,
+perspective,orthogonal}.py and jrender/structures/utils/faces_vertices.py are pure tensor algebra.
+Executing those files, where they lie under /root/reference, against this stub runs the REFERENCE'S
+OWN formulas (operand order, eps values, broadcasting) in float32 numpy, which pins
+oracle/preraster.py and the fused CUDA stage at the source level.  What it cannot pin is Jittor's
+internal reduction order inside matmul / norm (unspecified) -- hence float tolerances downstream.
+
+jt.normalize follows jittor.misc.normalize: `x / max(||x||_2, eps)` along `dim`.
+"""
+import sys
+import types
+
+import numpy as np
+
+
+class Var(np.ndarray):
+    """ndarray with the jittor.Var methods the reference transform code uses."""
+
+    def float32(self):
+        return np.asarray(self, dtype=np.float32).view(Var)
+
+    def unsqueeze(self, dim):
+        return np.expand_dims(np.asarray(self), dim).view(Var)
+
+    def broadcast(self, shape):
+        return np.broadcast_to(np.asarray(self), tuple(shape)).copy().view(Var)
+
+    def transpose(self, *axes):
+        if len(axes) == 1 and isinstance(axes[0], (tuple, list)):
+            axes = tuple(axes[0])
+        return np.transpose(np.asarray(self), axes).view(Var)
+
+    def reshape(self, *shape):
+        if len(shape) == 1 and isinstance(shape[0], (tuple, list)):
+            shape = tuple(shape[0])
+        return np.reshape(np.asarray(self), shape).view(Var)
+
+    @property
+    def shape(self):  # jittor shapes are lists (look_at.py:17: `[batch_size] + eye.shape`)
+        return list(np.asarray(self).shape)
+
+
+def _v(x):
+    return np.asarray(x).view(Var)
+
+
+def array(x, dtype=None):
+    a = np.asarray(x)
+    if dtype is not None:
+        a = a.astype(dtype)
+    elif a.dtype == np.float64:
+        a = a.astype(np.float32)   # jt.array of Python floats is float32
+    elif a.dtype == np.int64:
+        a = a.astype(np.int32)
+    return a.view(Var)
+
+
+def normalize(x, p=2, dim=1, eps=1e-12):
+    a = np.asarray(x, dtype=np.float32)
+    n = np.sqrt((a * a).sum(axis=dim, keepdims=True, dtype=np.float32)).astype(np.float32)
+    return (a / np.maximum(n, np.float32(eps))).astype(np.float32).view(Var)
+
+
+def cross(a, b, dim=-1):
+    return np.cross(np.asarray(a, np.float32), np.asarray(b, np.float32), axis=dim).astype(np.float32).view(Var)
+
+
+def matmul(a, b):
+    return np.matmul(np.asarray(a, np.float32), np.asarray(b, np.float32)).astype(np.float32).view(Var)
+
+
+def tan(a):
+    return np.tan(np.asarray(a, np.float32)).astype(np.float32).view(Var)
+
+
+def concat(xs, dim=0):
+    return np.concatenate([np.asarray(x) for x in xs], axis=dim).view(Var)
+
+
+def stack(xs, dim=0):
+    return np.stack([np.asarray(x) for x in xs], axis=dim).view(Var)
+
+
+def install():
+    """Put the stub into sys.modules as `jittor`; returns a function that restores the old state."""
+    jt = types.ModuleType("jittor")
+    jt.array, jt.normalize, jt.cross, jt.matmul, jt.tan, jt.stack = array, normalize, cross, matmul, tan, stack
+    jt.abs = lambda a: np.abs(np.asarray(a)).view(Var)
+    jt.sum = lambda a, dim=None: np.asarray(np.sum(np.asarray(a), axis=dim)).view(Var)
+    jt.contrib = types.SimpleNamespace(concat=concat)
+    jt.Var = Var
+    saved = sys.modules.get("jittor")
+    sys.modules["jittor"] = jt
+
+    def restore():
+        if saved is None:
+            sys.modules.pop("jittor", None)
+        else:
+            sys.modules["jittor"] = saved
+    return restore
+
+
+def load_reference_function(path, name):
+    """exec one reference .py (read in place, never copied) and return its function `name`."""
+    mod = types.ModuleType("ref_host_" + name)
+    exec(compile(open(path).read(), path, "exec"), mod.__dict__)
+    return getattr(mod, name)
