@@ -121,23 +121,30 @@ def run(iters=200, image_size=64, batch_size=24, filename_input=None, camera_inp
         with torch.cuda.graph(graph):
             static_loss, static_pred = iteration()
         torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.time()
+        e0.record()
         for i in range(4, iters):
             graph.replay()
             log(i, static_loss, static_pred)
+        e1.record()
         torch.cuda.synchronize()
-        dt = (time.time() - t0) * iters / max(1, iters - 4)
+        timed = max(1, iters - 4)
+        dt, dt_dev = (time.time() - t0) * iters / timed, e0.elapsed_time(e1) / 1000.0 * iters / timed
     else:
         torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.time()
+        e0.record()
         for i in range(iters):
             log(i, *iteration())
+        e1.record()
         torch.cuda.synchronize()
-        dt = time.time() - t0
+        dt, dt_dev = time.time() - t0, e0.elapsed_time(e1) / 1000.0
     if output_dir:
         os.makedirs(output_dir, exist_ok=True)
         jr.save_obj(os.path.join(output_dir, 'plane.obj'), model(1)[0].vertices[0], model.faces[0])
-    return dict(ms_per_iter=1000.0 * dt / iters, history=hist, final_iou=hist[-1][2], first_iou=hist[0][2])
+    return dict(ms_per_iter=1000.0 * dt / iters, device_ms_per_iter=1000.0 * dt_dev / iters, batch_size=batch_size, history=hist, final_iou=hist[-1][2], first_iou=hist[0][2])
 
 
 if __name__ == '__main__':

@@ -66,9 +66,15 @@ class Renderer(nn.Module):
         self.lighting.light_mode = mode
         self.rasterizer.texture_type = mode
 
+    # mode='silhouettes' returns alpha only, which no texture value can influence (the rasterizer runs
+    # with the colour path compiled out): the ~30 small lighting ops are skipped.
+    # Set to False to reproduce the reference's side effect of leaving lit textures on the mesh.
+    skip_unused_lighting = True
+
     def render_mesh(self, mesh, mode='rgb'):
         self.set_texture_mode(mesh.texture_type)
-        mesh = self.lighting(mesh, self.transform.eyes)
+        if not (self.skip_unused_lighting and mode == 'silhouettes'):
+            mesh = self.lighting(mesh, self.transform.eyes)
         mesh = self.transform(mesh)
         return self.rasterizer(mesh, mode)
 
