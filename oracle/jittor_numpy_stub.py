@@ -42,6 +42,40 @@ class Var(np.ndarray):
     def shape(self):  # jittor shapes are lists (look_at.py:17: `[batch_size] + eye.shape`)
         return list(np.asarray(self).shape)
 
+    # -- the few extra Var methods the loss / lighting sources use
+    def size(self, dim=None):
+        return list(np.asarray(self).shape) if dim is None else np.asarray(self).shape[dim]
+
+    def int(self):
+        return np.asarray(self).astype(np.int32).view(Var)
+
+    def numpy(self):
+        return np.asarray(self)
+
+    def stop_grad(self):
+        return self
+
+    def numel(self):
+        return int(np.asarray(self).size)
+
+    def pow(self, e):
+        return np.power(np.asarray(self), np.float32(e)).astype(np.asarray(self).dtype).view(Var)
+
+    def sqrt(self):
+        return np.sqrt(np.asarray(self)).view(Var)
+
+    def sum(self, dims=None, **kw):   # jittor: x.sum(dims) with a tuple of axes
+        if isinstance(dims, list):
+            dims = tuple(dims)
+        return np.asarray(np.asarray(self).sum(axis=dims, dtype=np.asarray(self).dtype)).view(Var)
+
+    def __getitem__(self, idx):
+        if isinstance(idx, tuple):
+            idx = tuple(np.asarray(i) if isinstance(i, Var) else i for i in idx)
+        elif isinstance(idx, Var):
+            idx = np.asarray(idx)
+        return np.asarray(np.asarray(self)[idx]).view(Var)
+
 
 def _v(x):
     return np.asarray(x).view(Var)
@@ -92,19 +126,34 @@ def install():
     jt.sum = lambda a, dim=None: np.asarray(np.sum(np.asarray(a), axis=dim)).view(Var)
     jt.contrib = types.SimpleNamespace(concat=concat)
     jt.Var = Var
-    saved = sys.modules.get("jittor")
+    jt.zeros = lambda shape, dtype="float32": np.zeros(tuple(shape), dtype).view(Var)
+    jt.ones = lambda shape, dtype="float32": np.ones(tuple(shape), dtype).view(Var)
+    jt.ones_like = lambda a: np.ones_like(np.asarray(a)).view(Var)
+    jt.clamp = lambda a, min_v=None, max_v=None: np.clip(np.asarray(a), min_v, max_v).view(Var)
+    jt.pow = lambda a, e: np.power(np.asarray(a), np.float32(e)).astype(np.asarray(a).dtype).view(Var)
+    nn = types.ModuleType("jittor.nn")
+
+    class Module(object):
+        def __call__(self, *a, **kw):
+            return self.execute(*a, **kw)
+    nn.Module = Module
+    nn.relu = lambda a: np.maximum(np.asarray(a), 0).view(Var)
+    jt.nn = nn
+    saved = {k: sys.modules.get(k) for k in ("jittor", "jittor.nn")}
     sys.modules["jittor"] = jt
+    sys.modules["jittor.nn"] = nn
 
     def restore():
-        if saved is None:
-            sys.modules.pop("jittor", None)
-        else:
-            sys.modules["jittor"] = saved
+        for k, m in saved.items():
+            if m is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = m
     return restore
 
 
 def load_reference_function(path, name):
-    """exec one reference .py (read in place, never copied) and return its function `name`."""
+    """exec one reference .py (read in place, never copied) and return its function / class `name`."""
     mod = types.ModuleType("ref_host_" + name)
     exec(compile(open(path).read(), path, "exec"), mod.__dict__)
     return getattr(mod, name)
