@@ -79,10 +79,15 @@ class _SoftRasterizeOp(torch.autograd.Function):
         fn.save_vars = (fv.detach(), tx.detach(), soft_colors.detach(), faces_info, aggrs_info.detach(),
                         faces_id_buffer.detach())
         ctx.mark_non_differentiable(aggrs_info, faces_id_buffer)
+        # Without this, autograd hands the backward zero-filled "gradients" for aggrs_info and for the
+        # int32 faces_id_buffer: a 268 MB (C3) / 2 GB (C5, 120 views) fill kernel per step for nothing.
+        ctx.set_materialize_grads(False)
         return soft_colors, aggrs_info, faces_id_buffer
 
     @staticmethod
     def backward(ctx, grad_soft_colors, _g1, _g2):
+        if grad_soft_colors is None:   # soft_colors did not take part in the loss
+            return None, None, None
         fv, tx, soft_colors, aggrs_info, faces_id_buffer, workspace = ctx.saved_tensors
         L = _lib.lib()
         dev = fv.device
