@@ -161,6 +161,20 @@ B200R_API int b200r_project_faces_backward(const float* vertices, const int32_t*
                                            int camera_mode, int projection, int batch_size, int num_vertices,
                                            int num_faces, int vertices_batch, int faces_batch, int eye_batch, void* stream);
 
+/* ---- fused mesh regularisers of the fitting loop ---------------------
+ * Each call writes loss [B] AND d(loss_b)/d(vertices) [B, nv, 3] (both overwritten) in one launch.
+ *   b200r_flatten_loss   <- jrender/loss/flatten_loss.py:38-79; v0s..v3s [E] int32 = the edge table the
+ *                           reference builds at :14-36 (edge v0-v1 shared by the faces with apexes v2, v3)
+ *   b200r_laplacian_loss <- jrender/loss/laplacian_loss.py:29-36 with the row-normalised Laplacian of :11-27
+ *                           stored as a padded neighbour table: (L x)_i = diag[i] x_i + sum_k w[i,k] x[nbr[i,k]],
+ *                           neighbours / neighbour_weights [nv, max_degree] (weight 0 = padding), diag [nv] */
+B200R_API int b200r_flatten_loss(const float* vertices, const int32_t* v0s, const int32_t* v1s, const int32_t* v2s,
+                                 const int32_t* v3s, float* loss, float* grad_vertices, int batch_size,
+                                 int num_vertices, int num_edges, float eps, void* stream);
+B200R_API int b200r_laplacian_loss(const float* vertices, const int32_t* neighbours, const float* neighbour_weights,
+                                   const float* diag, float* loss, float* grad_vertices, int batch_size,
+                                   int num_vertices, int max_degree, void* stream);
+
 /* Launch counter: number of kernels this library has launched in this process
  * (bench.py reports the delta over the timed region as "gpu_launches"). */
 B200R_API unsigned long long b200r_launch_count(void);
@@ -182,7 +196,7 @@ B200R_API int b200r_set_option(const char* name, int value);
 enum { B200R_K_FACE_SETUP = 0, B200R_K_COARSE_BIN = 1, B200R_K_SOFTRAS_FWD = 2, B200R_K_SOFTRAS_BWD = 3,
        B200R_K_TILE_ORDER = 4, B200R_K_NMR_SETUP = 5, B200R_K_NMR_FWD = 6, B200R_K_NMR_BWD_PIXEL = 7,
        B200R_K_NMR_BWD_MAPS = 8, B200R_K_SOFTRAS_BWD_FINALIZE = 9, B200R_K_NMR_PACK = 10,
-       B200R_K_PROJECT_FWD = 11, B200R_K_PROJECT_BWD = 12 };
+       B200R_K_PROJECT_FWD = 11, B200R_K_PROJECT_BWD = 12, B200R_K_FLATTEN_LOSS = 13, B200R_K_LAPLACIAN_LOSS = 14 };
 B200R_API void b200r_profile_enable(int on);
 B200R_API void b200r_profile_reset(void);
 B200R_API int b200r_profile_read(int kernel, double* total_ms, long long* launches);

@@ -63,6 +63,10 @@ def lib():
     L.b200r_project_faces_forward.argtypes = [_P, _P, _P, _P, _P, _P, _F] + [_I] * 8 + [_P]
     L.b200r_project_faces_backward.restype = _I
     L.b200r_project_faces_backward.argtypes = [_P, _P, _P, _P, _P, _P, _P, _F] + [_I] * 8 + [_P]
+    L.b200r_flatten_loss.restype = _I
+    L.b200r_flatten_loss.argtypes = [_P] * 7 + [_I, _I, _I, _F, _P]
+    L.b200r_laplacian_loss.restype = _I
+    L.b200r_laplacian_loss.argtypes = [_P] * 6 + [_I, _I, _I, _P]
     L.b200r_set_option.restype = _I
     L.b200r_set_option.argtypes = [C.c_char_p, _I]
     _lib = L

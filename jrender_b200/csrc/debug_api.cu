@@ -28,6 +28,17 @@ __global__ void k_debug_exact_math(const float* __restrict__ a, const float* __r
         const float q2 = __fdiv_rn(x, y);
         if (!same_f(q1, q2)) atomicAdd(&mismatch[0], 1);
         if (safe && midrange(x)) atomicAdd(&mismatch[6], 1);
+        // branch-free optimistic forms (DivGuard): whenever the guard stays up they must equal `/` too
+        DivGuard g;
+        g.ok = true;
+        const float q3 = optimistic_div_exact(x, y, r, safe, g);
+        if (g.ok && !same_f(q3, q2)) atomicAdd(&mismatch[0], 1);
+        g.ok = true;
+        const float q4 = optimistic_rcp(y, g);
+        if (g.ok && !same_f(q4, __fdiv_rn(1.f, y))) atomicAdd(&mismatch[0], 1);
+        g.ok = true;
+        const float q5 = optimistic_div(x, y, r, safe, g);   // relaxed range: exact whenever |x| >= 2^-60 as well
+        if (g.ok && midrange(x) && !same_f(q5, q2)) atomicAdd(&mismatch[0], 1);
     }
     if (midrange(x)) {
         if (!same_d(f2d_mid(x), (double)x)) atomicAdd(&mismatch[1], 1);

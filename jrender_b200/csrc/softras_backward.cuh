@@ -20,6 +20,10 @@
 #pragma once
 #include "softras_math.cuh"
 
+#ifndef B200R_BWD_OPTIMISTIC
+#define B200R_BWD_OPTIMISTIC 1   // 0: guarded (branching) divisions in the relaxed backward, for A/B builds
+#endif
+
 namespace b200r {
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -40,10 +44,20 @@ struct BwdPixel {
 // Gradient contribution of one (pixel, face) pair: gv[k*3+l] = d/d vertex k coord l; gt = texture
 // gradient (T == 1 surface: gt[0..2]; vertex: gt[j*3+k]).  For surface textures with T > 1 the hit
 // texel index is returned in texel_out and gt[0..2] holds its gradient.  (:1240-1358)
-template <int DIST, int RGB, bool EXACT>
+// OPT (only with !EXACT): every division is the branch-free optimistic flavour (exact_math.cuh, DivGuard) and
+// `guard.ok` says whether all of them were in range; the caller re-runs the pair with OPT = false otherwise.
+template <int DIST, int RGB, bool EXACT, bool OPT = false>
 __device__ __forceinline__ void pair_gradient(const FaceRec* rec, int fn, const BwdPixel& px, const SoftRasParams& P,
                                               const DivConst& dc, float nmf, float r_nmf, bool s_nmf,
-                                              const float* __restrict__ tex, float gv[9], float gt[9], int& texel_out) {
+                                              const float* __restrict__ tex, float gv[9], float gt[9], int& texel_out,
+                                              DivGuard& guard) {
+    static_assert(!(OPT && EXACT), "the optimistic divisions replace the relaxed ones only");
+    auto by_sigma = [&](float a) -> float { if constexpr (OPT) return dc.by_sigma_o(a, guard); else return dc.template by_sigma_t<EXACT>(a); };
+    auto by_gamma = [&](float a) -> float { if constexpr (OPT) return dc.by_gamma_o(a, guard); else return dc.template by_gamma_t<EXACT>(a); };
+    auto by_span = [&](float a) -> float { if constexpr (OPT) return dc.by_span_o(a, guard); else return dc.template by_span_t<EXACT>(a); };
+    auto dv = [&](float a, float b, float r, bool safe) -> float { if constexpr (OPT) return optimistic_div(a, b, r, safe, guard); else return div_t<EXACT>(a, b, r, safe); };
+    auto dvar = [&](float a, float b) -> float { if constexpr (OPT) return optimistic_div_var(a, b, guard); else return div_var_t<EXACT>(a, b); };
+    auto sigmoid = [&](float x) -> float { if constexpr (OPT) return sigmoid_from_negarg_opt(x, guard); else return sigmoid_from_negarg<EXACT>(x); };
     const float* f = rec->v;
     const float xp = px.xp, yp = px.yp;
     const int T = P.T;
@@ -56,11 +70,11 @@ __device__ __forceinline__ void pair_gradient(const FaceRec* rec, int fn, const 
     } else if (DIST == 1) {
         dis = barycentric_p2f_distance(w);
         t[0] = w[0]; t[1] = w[1]; t[2] = w[2];
-        soft_fragment = sigmoid_from_negarg<EXACT>(dc.template by_sigma_t<EXACT>(-dis));
+        soft_fragment = sigmoid(by_sigma(-dis));
     } else {
-        sign = euclidean_p2f_distance<EXACT>(dis_x, dis_y, t, w, rec, xp, yp);
+        sign = euclidean_p2f_distance<EXACT>(dis_x, dis_y, t, w, rec, xp, yp, OPT ? &guard : nullptr);
         dis = dis_x * dis_x + dis_y * dis_y;
-        soft_fragment = sigmoid_from_negarg<EXACT>(dc.template by_sigma_t<EXACT>(-sign * dis));
+        soft_fragment = sigmoid(by_sigma(-sign * dis));
     }
 
     float C_grad_xy = 0.f;
@@ -75,13 +89,15 @@ __device__ __forceinline__ void pair_gradient(const FaceRec* rec, int fn, const 
             const double prod = px.d_galpha * (px.d_one_minus_alpha / den);
             C_grad_xy_alpha = d_midrange(prod) ? d2f_mid(prod) : (float)prod;
         } else {
-            C_grad_xy_alpha = C_grad_xy_alpha * div_var_t<EXACT>(1.f - px.oc[3], fmaxf(omd, 1e-6f));
+            C_grad_xy_alpha = C_grad_xy_alpha * dvar(1.f - px.oc[3], fmaxf(omd, 1e-6f));
         }
     }
     C_grad_xy += C_grad_xy_alpha;
 
     const float w0[3] = {w[0], w[1], w[2]};
-    const float zp = clip_and_z<EXACT>(w, rec);
+    float zp;
+    if constexpr (OPT) zp = clip_and_z_opt(w, rec, guard);
+    else zp = clip_and_z<EXACT>(w, rec);
 
     if (RGB == 0) {
         if ((float)fn == px.softmax_max) {  // :1300 (int vs float compare, Q10)
@@ -97,9 +113,8 @@ __device__ __forceinline__ void pair_gradient(const FaceRec* rec, int fn, const 
         }
     } else if (RGB == 1) {
         float C_grad_xyz_rgb = 0.f;
-        const float zp_norm = dc.template by_span_t<EXACT>(P.far_ - zp);
-        const float zp_softmax = div_t<EXACT>(soft_fragment * expf(dc.template by_gamma_t<EXACT>(zp_norm - px.softmax_max)),
-                                              px.softmax_sum, px.r_ssum, px.s_ssum);
+        const float zp_norm = by_span(P.far_ - zp);
+        const float zp_softmax = dv(soft_fragment * expf(by_gamma(zp_norm - px.softmax_max)), px.softmax_sum, px.r_ssum, px.s_ssum);
         float col[3];
         if (P.tex_type == 0) {
             const int j = surface_texel(w, P.R);
@@ -123,19 +138,19 @@ __device__ __forceinline__ void pair_gradient(const FaceRec* rec, int fn, const 
 #pragma unroll
         for (int k = 0; k < 3; k++) C_grad_xyz_rgb += px.g[k] * (col[k] - px.oc[k]);
         C_grad_xyz_rgb *= zp_softmax;
-        C_grad_xy += div_var_t<EXACT>(C_grad_xyz_rgb, soft_fragment);
+        C_grad_xy += dvar(C_grad_xyz_rgb, soft_fragment);
 
-        const float C_grad_z_rgb = div_t<EXACT>(dc.template by_gamma_t<EXACT>(C_grad_xyz_rgb), nmf, r_nmf, s_nmf) * zp * zp;
+        const float C_grad_z_rgb = dv(by_gamma(C_grad_xyz_rgb), nmf, r_nmf, s_nmf) * zp * zp;
         const uint32_t fl = rec->flags;
 #pragma unroll
         for (int k = 0; k < 3; k++) {
             const bool sz = (fl & (16u << k)) != 0;
             const float z = f[3 * k + 2], rz = rec->rz[k];
-            gv[k * 3 + 2] = div_t<EXACT>(div_t<EXACT>(C_grad_z_rgb * w[k], z, rz, sz), z, rz, sz);
+            gv[k * 3 + 2] = dv(dv(C_grad_z_rgb * w[k], z, rz, sz), z, rz, sz);
         }
     }
 
-    C_grad_xy *= dc.template by_sigma_t<EXACT>(soft_fragment * (1.f - soft_fragment));  // :1336
+    C_grad_xy *= by_sigma(soft_fragment * (1.f - soft_fragment));  // :1336
     if (DIST == 1) {  // backward_barycentric_p2f_distance (:1118-1132), w := t (unclipped)
         const int pm = t[0] > t[1] ? (t[1] > t[2] ? 2 : 1) : (t[0] > t[2] ? 2 : 0);
         const float* inv = rec->inv;
@@ -233,7 +248,19 @@ k_softras_backward_lane(const SoftRasParams P, const FaceRec* __restrict__ recs,
         float gv[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         float gt[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         int texel;
-        pair_gradient<DIST, RGB, EXACT>(rec, fn, px, P, dc, nmf, r_nmf, s_nmf, btex + (size_t)fn * T * 3, gv, gt, texel);
+        DivGuard guard;
+        guard.ok = true;
+        if constexpr (!EXACT && B200R_BWD_OPTIMISTIC) {
+            // all divisions branch-free; one range flag for the whole pair, one (cold) re-run if it dropped
+            pair_gradient<DIST, RGB, false, true>(rec, fn, px, P, dc, nmf, r_nmf, s_nmf, btex + (size_t)fn * T * 3, gv, gt, texel, guard);
+            if (!guard.ok) {
+#pragma unroll
+                for (int c = 0; c < 9; c++) { gv[c] = 0.f; gt[c] = 0.f; }
+                pair_gradient<DIST, RGB, false, false>(rec, fn, px, P, dc, nmf, r_nmf, s_nmf, btex + (size_t)fn * T * 3, gv, gt, texel, guard);
+            }
+        } else {
+            pair_gradient<DIST, RGB, EXACT, false>(rec, fn, px, P, dc, nmf, r_nmf, s_nmf, btex + (size_t)fn * T * 3, gv, gt, texel, guard);
+        }
         float4* a = reinterpret_cast<float4*>(bacc + (size_t)fn * 12);
         atomicAdd(a + 0, make_float4(gv[0], gv[1], gv[2], gv[3]));
         atomicAdd(a + 1, make_float4(gv[4], gv[5], gv[6], gv[7]));
@@ -345,7 +372,9 @@ k_softras_backward(const SoftRasParams P, const FaceRec* __restrict__ recs, cons
         float gt[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // T==1: [k]; vertex: [j*3+k]
         if (mine) {
             int texel;
-            pair_gradient<DIST, RGB, true>(wrec, fn, px, P, dc, nmf, r_nmf, s_nmf, btex + (size_t)fn * T * 3, gv, gt, texel);
+            DivGuard guard;
+            guard.ok = true;
+            pair_gradient<DIST, RGB, true, false>(wrec, fn, px, P, dc, nmf, r_nmf, s_nmf, btex + (size_t)fn * T * 3, gv, gt, texel, guard);
             if (RGB != 2 && P.tex_type == 0 && T > 1) {  // per-lane texel: scalar atomics, not reduced
 #pragma unroll
                 for (int k = 0; k < 3; k++) atomicAdd(bgt + ((size_t)fn * T + texel) * 3 + k, gt[k]);

@@ -164,6 +164,115 @@ __device__ __forceinline__ void shade_face(const FaceRec* rec, PixState& st, con
     }
 }
 
+#ifndef B200R_FWD_OPTIMISTIC
+#define B200R_FWD_OPTIMISTIC 1   // 0: shade_face with guarded (branching) divisions only, for A/B builds
+#endif
+
+// shade_face with every division in its branch-free optimistic form (exact_math.cuh, DivGuard): the pair's
+// arithmetic up to the first state update runs without a single range branch, the range conditions are AND-ed
+// into one flag, and a pair whose flag dropped (practically never) is handed to shade_face above before anything
+// was committed.  With the flag up every intermediate equals shade_face<.., EXACT = false>'s bit for bit:
+// same Markstein sequences, and the two exp() of the online softmax collapse into one because
+// exp((max - z)/gamma) and exp((z - max)/gamma) are never both different from 1.
+template <int DIST, int RGB, int NT>
+__device__ __forceinline__ void shade_face_opt(const FaceRec* rec, PixState& st, const SoftRasParams& P, const DivConst& dc,
+                                               float xp, float yp, float threshold, float* s_qz, int* s_qid, int tid,
+                                               const float* __restrict__ btex) {
+    DivGuard g;
+    g.ok = true;
+    float w[3];
+    barycentric_coordinate(w, xp, yp, rec->inv);
+
+    float soft_fragment = 1.f;
+    if (DIST == 0) {
+        if (!check_pixel_inside(w)) return;  // :332-333
+    } else if (DIST == 1) {
+        const float dis = barycentric_p2f_distance(w);
+        if (-dis >= threshold) return;  // :337
+        soft_fragment = sigmoid_from_negarg_opt(dc.by_sigma_o(-dis, g), g);
+    } else {
+        float dis_x, dis_y, t[3];
+        const float sign = euclidean_p2f_distance<true>(dis_x, dis_y, t, w, rec, xp, yp, &g);
+        const float dis = dis_x * dis_x + dis_y * dis_y;
+        if (sign < 0.f && dis >= threshold && g.ok) return;  // :343 (an out-of-range pair falls through to the re-run)
+        soft_fragment = sigmoid_from_negarg_opt(dc.by_sigma_o(-sign * dis, g), g);
+    }
+
+    float wc[3] = {w[0], w[1], w[2]};
+    const float zp = clip_and_z_opt<true>(wc, rec, g);  // barycentric_clip :363 + zp :364
+    float zp_norm = 0.f, dz = 0.f, ex = 1.f;
+    if (RGB == 1) {
+        zp_norm = dc.by_span_o(P.far_ - zp, g);
+        dz = zp_norm - st.softmax_max;
+        ex = expf(dc.by_gamma_o(-fabsf(dz), g));   // = exp_delta_zp when dz > 0, exp_z otherwise (:402-407)
+    }
+    if (!g.ok) {  // cold: nothing has been committed yet
+        shade_face<DIST, RGB, NT, false>(rec, st, P, dc, xp, yp, threshold, s_qz, s_qid, tid, btex);
+        return;
+    }
+
+    // alpha aggregation, before any z test (:349-358, Q2)
+    if (P.alpha_func == 0) {
+        if (soft_fragment > 0.5f) st.alpha = 1.f;
+    } else if (P.alpha_func == 1) {
+        st.alpha += soft_fragment;
+    } else {
+        st.alpha = st.alpha * (1.f - soft_fragment);
+    }
+    if (zp < P.near_ || zp > P.far_) return;       // :365
+
+    const int fn = (int)rec->face_id;
+    const int K = P.K;
+    // top-K by z, "replace the current max" policy (:367-385)
+    if (st.q_size < K) {
+        s_qz[st.q_size * NT + tid] = zp;
+        s_qid[st.q_size * NT + tid] = fn;
+        if (zp > st.q_max_z) { st.q_max_z = zp; st.q_max_id = st.q_size; }
+        st.q_size++;
+    } else if (zp < st.q_max_z) {
+        s_qz[st.q_max_id * NT + tid] = zp;
+        s_qid[st.q_max_id * NT + tid] = fn;
+        st.q_max_z = -1.f;
+        for (int k = 0; k < st.q_size; k++) {
+            const float z = s_qz[k * NT + tid];
+            if (z > st.q_max_z) { st.q_max_z = z; st.q_max_id = k; }
+        }
+    }
+
+    const bool front = (rec->flags & 8u) != 0;
+    if (RGB == 0) {  // :390-397
+        if (zp < st.depth_min && check_pixel_inside(w) && (P.double_side || front)) {
+            st.depth_min = zp;
+            st.face_index_min = fn;
+            float col[3];
+            sample_texture_fwd(col, btex + (size_t)fn * P.T * 3, wc, P.R, P.tex_type, rec, zp);
+            st.sc0 = col[0]; st.sc1 = col[1]; st.sc2 = col[2];
+        }
+    } else if (RGB == 1) {  // :399-419
+        if (front || P.double_side) {
+            const bool up = dz > 0.f;            // zp_norm > softmax_max
+            const float exp_delta_zp = up ? ex : 1.f;
+            const float exp_z = up ? 1.f : ex;   // exp(0 / gamma) == 1 exactly
+            if (up) st.softmax_max = zp_norm;
+            st.softmax_sum = exp_delta_zp * st.softmax_sum + exp_z * soft_fragment;
+            float col[3];
+            sample_texture_fwd(col, btex + (size_t)fn * P.T * 3, wc, P.R, P.tex_type, rec, zp);
+            st.sc0 = exp_delta_zp * st.sc0 + exp_z * soft_fragment * col[0];
+            st.sc1 = exp_delta_zp * st.sc1 + exp_z * soft_fragment * col[1];
+            st.sc2 = exp_delta_zp * st.sc2 + exp_z * soft_fragment * col[2];
+        }
+    }
+}
+
+// EXACT (softras_exact_tail = 1) keeps the reference's double-precision tails and the strictly guarded divisions.
+template <int DIST, int RGB, int NT, bool EXACT>
+__device__ __forceinline__ void shade_pair(const FaceRec* rec, PixState& st, const SoftRasParams& P, const DivConst& dc,
+                                           float xp, float yp, float threshold, float* s_qz, int* s_qid, int tid,
+                                           const float* __restrict__ btex) {
+    if constexpr (!EXACT && B200R_FWD_OPTIMISTIC) shade_face_opt<DIST, RGB, NT>(rec, st, P, dc, xp, yp, threshold, s_qz, s_qid, tid, btex);
+    else shade_face<DIST, RGB, NT, EXACT>(rec, st, P, dc, xp, yp, threshold, s_qz, s_qid, tid, btex);
+}
+
 __device__ __forceinline__ bool pixel_in_rect(const FaceRec* rec, int px, int row) {
     const uint32_t rx = rec->rect_x, rr = rec->rect_r;
     const uint32_t x0 = rx & 0xffffu, r0 = rr & 0xffffu;
@@ -329,7 +438,7 @@ k_softras_forward(const SoftRasParams P, const FaceRec* __restrict__ recs, const
                     for (int it = 0; it < wcnt; it++) {
                         const FaceRec* rec = &S.rec[NW > 1 ? (int)S.wlist[warp][it] : it].r;
                         if (!pixel_in_rect(rec, px, row)) continue;
-                        shade_face<DIST, RGB, NT, EXACT>(rec, st, P, dc, xp, yp, threshold, s_qz, s_qid, tid, btex);
+                        shade_pair<DIST, RGB, NT, EXACT>(rec, st, P, dc, xp, yp, threshold, s_qz, s_qid, tid, btex);
                     }
                 } else {
                     // ---- each lane compacts its own list, then lanes walk private lists
@@ -345,7 +454,7 @@ k_softras_forward(const SoftRasParams P, const FaceRec* __restrict__ recs, const
                     for (int i = 0; i < maxcnt; i++) {
                         if (i < cnt) {
                             const FaceRec* rec = &S.rec[s_plist[i * NT + tid]].r;
-                            shade_face<DIST, RGB, NT, EXACT>(rec, st, P, dc, xp, yp, threshold, s_qz, s_qid, tid, btex);
+                            shade_pair<DIST, RGB, NT, EXACT>(rec, st, P, dc, xp, yp, threshold, s_qz, s_qid, tid, btex);
                         }
                     }
                 }

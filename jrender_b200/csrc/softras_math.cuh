@@ -31,6 +31,10 @@ struct DivConst {
     template <bool EXACT> __device__ __forceinline__ float by_sigma_t(float a) const { return div_t<EXACT>(a, sigma, r_sigma, s_sigma); }
     template <bool EXACT> __device__ __forceinline__ float by_gamma_t(float a) const { return div_t<EXACT>(a, gamma, r_gamma, s_gamma); }
     template <bool EXACT> __device__ __forceinline__ float by_span_t(float a) const { return div_t<EXACT>(a, span, r_span, s_span); }
+    // optimistic (branch-free) flavours, see DivGuard in exact_math.cuh
+    __device__ __forceinline__ float by_sigma_o(float a, DivGuard& g) const { return optimistic_div(a, sigma, r_sigma, s_sigma, g); }
+    __device__ __forceinline__ float by_gamma_o(float a, DivGuard& g) const { return optimistic_div(a, gamma, r_gamma, s_gamma, g); }
+    __device__ __forceinline__ float by_span_o(float a, DivGuard& g) const { return optimistic_div(a, span, r_span, s_span, g); }
 };
 
 // :20-25
@@ -93,6 +97,30 @@ __device__ __forceinline__ float clip_and_z(float w[3], const FaceRec* rec) {
     return 1.f / (a + b + c);
 }
 
+// Optimistic flavour of clip_and_z: always the unchecked sequence; the per-face flag test, (STRICT: the forward,
+// where zp orders the top-K list) the "weights are 0 or >= 2^-58" condition and the final reciprocal's range go
+// into the guard.  With the guard up the result equals clip_and_z<STRICT>'s bit for bit.
+template <bool STRICT = false>
+__device__ __forceinline__ float clip_and_z_opt(float w[3], const FaceRec* rec, DivGuard& g) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) w[k] = fmaxf(fminf(w[k], 1.f), 0.f);
+    const float w_sum = fmaxf(w[0] + w[1] + w[2], 1e-5f);
+    g.ok = g.ok && ((rec->flags & 0x70u) == 0x70u);
+    if (STRICT) {
+        const float tiny = 3.4694469519536142e-18f;  // 2^-58
+        g.ok = g.ok && (w[0] == 0.f || w[0] >= tiny) && (w[1] == 0.f || w[1] >= tiny) && (w[2] == 0.f || w[2] >= tiny);
+    }
+    if (w_sum != 1.f) {  // x / 1 == x exactly
+        const float r = rcp_refined(w_sum);
+#pragma unroll
+        for (int k = 0; k < 3; k++) w[k] = div_nocheck(w[k], w_sum, r);
+    }
+    const float a = div_nocheck(w[0], rec->v[2], rec->rz[0]);
+    const float b = div_nocheck(w[1], rec->v[5], rec->rz[1]);
+    const float c = div_nocheck(w[2], rec->v[8], rec->rz[2]);
+    return optimistic_rcp(a + b + c, g);
+}
+
 __device__ __forceinline__ float sel3(int i, float a, float b, float c) { return i == 0 ? a : (i == 1 ? b : c); }
 
 // :57-147.  rec->a0 holds the pre-subtracted Gram-matrix rows.  Returns sign; writes
@@ -100,9 +128,14 @@ __device__ __forceinline__ float sel3(int i, float a, float b, float c) { return
 template <bool STRICT = true>
 __device__ __forceinline__ float euclidean_p2f_distance(float& dis_x, float& dis_y, float t[3],
                                                         const float w[3], const FaceRec* rec,
-                                                        float xp, float yp) {
+                                                        float xp, float yp, DivGuard* guard = nullptr) {
     const float* f = rec->v;
     const uint32_t fl = rec->flags;
+    // guard != nullptr (a compile-time fact after inlining): branch-free division, range folded into the guard
+    auto edge_div = [&](float a, float b, float r, bool safe) -> float {
+        if (guard != nullptr) return STRICT ? optimistic_div_exact(a, b, r, safe, *guard) : optimistic_div(a, b, r, safe, *guard);
+        return div_t<STRICT>(a, b, r, safe);
+    };
     if (w[0] > 0.f && w[1] > 0.f && w[2] > 0.f && w[0] < 1.f && w[1] < 1.f && w[2] < 1.f) {
         float dis_min = 100000000.f;
         float dis_x_min = 0.f, dis_y_min = 0.f;
@@ -112,8 +145,8 @@ __device__ __forceinline__ float euclidean_p2f_distance(float& dis_x, float& dis
             const int v0 = k, v1 = (k + 1) % 3, v2 = (k + 2) % 3;
             const float* a = rec->a0 + 3 * k;
             float t0[3];
-            t0[v0] = div_t<STRICT>(w[0] * a[0] + w[1] * a[1] + w[2] * a[2] - a[v1], a[v0] - a[v1], rec->rden[k],
-                                   (fl & (128u << k)) != 0);
+            t0[v0] = edge_div(w[0] * a[0] + w[1] * a[1] + w[2] * a[2] - a[v1], a[v0] - a[v1], rec->rden[k],
+                              (fl & (128u << k)) != 0);
             t0[v1] = 1.f - t0[v0];
             t0[v2] = 0.f;
             t0[0] -= w[0];
@@ -154,8 +187,8 @@ __device__ __forceinline__ float euclidean_p2f_distance(float& dis_x, float& dis
         const float a_0 = a[0], a_1 = a[1], a_2 = a[2];
         const float a_v0 = sel3(v0, a_0, a_1, a_2);
         const float a_v1 = sel3(v1, a_0, a_1, a_2);
-        const float tv0 = div_t<STRICT>(w[0] * a_0 + w[1] * a_1 + w[2] * a_2 - a_v1, a_v0 - a_v1, rec->rden[v0],
-                                        (fl & (128u << v0)) != 0);
+        const float tv0 = edge_div(w[0] * a_0 + w[1] * a_1 + w[2] * a_2 - a_v1, a_v0 - a_v1, rec->rden[v0],
+                                   (fl & (128u << v0)) != 0);
         const float tv1 = 1.f - tv0;
         const float c0 = fminf(fmaxf(tv0, 0.f), 1.f);
         const float c1 = fminf(fmaxf(tv1, 0.f), 1.f);
@@ -186,6 +219,11 @@ template <bool EXACT>
 __device__ __forceinline__ float sigmoid_from_negarg(float x) {
     if (EXACT) return sigmoid_tail(expf(x));
     return 1.f / (1.f + expf(x));
+}
+
+// optimistic flavour of sigmoid_from_negarg<false>: same two roundings, reciprocal without the IEEE slow path
+__device__ __forceinline__ float sigmoid_from_negarg_opt(float x, DivGuard& g) {
+    return optimistic_rcp(1.f + expf(x), g);
 }
 
 // alpha "prod" aggregation  alpha *= 1. - D  (:357); see sigmoid_from_negarg for EXACT.

@@ -4,9 +4,41 @@ neg_iou_loss  (iou_loss.py:1-5), LaplacianLoss (laplacian_loss.py:5-36, stored a
 neighbour table instead of the reference's dense nv x nv matrix -- same values), FlattenLoss
 (flatten_loss.py:5-79, edge table built with a dictionary instead of the O(E*F) scan).
 """
+import ctypes as C
+
 import numpy as np
 import torch
 from torch import nn
+
+from . import _lib
+
+
+class _FusedMeshLoss(torch.autograd.Function):
+    """loss [B] and d loss / d vertices from ONE launch of csrc/mesh_loss_api.cu; the backward is a scale."""
+
+    @staticmethod
+    def forward(ctx, vertices, launch):
+        v = vertices.contiguous()
+        dev = v.device
+        with torch.cuda.device(dev):
+            loss = torch.empty((v.shape[0],), dtype=torch.float32, device=dev)
+            grad = torch.empty_like(v)
+            launch(v, loss, grad, C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+        ctx.save_for_backward(grad)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        (grad,) = ctx.saved_tensors
+        return grad * grad_loss[:, None, None], None
+
+
+def _fusable(x):
+    return x.is_cuda and x.dtype == torch.float32 and x.dim() == 3 and x.shape[2] == 3 and 0 < x.shape[0] <= 65535
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr())
 
 
 def neg_iou_loss(predict, target):
@@ -41,11 +73,23 @@ class LaplacianLoss(nn.Module):
         with np.errstate(divide='ignore', invalid='ignore'):
             diag = (deg / deg).astype(np.float32)     # 1, or NaN for an isolated vertex like the dense 0/0
         self.register_buffer('nbr', torch.from_numpy(nbr.reshape(-1)))
+        self.register_buffer('nbr32', torch.from_numpy(nbr.astype(np.int32)))
         self.register_buffer('nbr_w', torch.from_numpy(w))
         self.register_buffer('diag', torch.from_numpy(diag))
 
+    fused = True   # CUDA float32 [B, nv, 3] inputs take the one-launch kernel (b200r_laplacian_loss)
+
     def forward(self, x):
         batch_size = x.shape[0]
+        if self.fused and _fusable(x) and x.shape[1] == self.nv:
+            L = _lib.lib()
+            maxdeg = self.nbr_w.shape[1]
+
+            def launch(v, loss, grad, stream):
+                _lib.check(L.b200r_laplacian_loss(_p(v), _p(self.nbr32), _p(self.nbr_w), _p(self.diag), _p(loss), _p(grad),
+                                                  v.shape[0], self.nv, maxdeg, stream), "b200r_laplacian_loss")
+            y = _FusedMeshLoss.apply(x, launch)
+            return y.sum() / batch_size if self.average else y
         xn = torch.index_select(x, 1, self.nbr).view(batch_size, self.nv, -1, x.shape[2])
         y = x * self.diag[None, :, None] + (xn * self.nbr_w[None, :, :, None]).sum(2)
         dims = tuple(range(y.dim())[1:])
@@ -74,9 +118,22 @@ class FlattenLoss(nn.Module):
         v3s = np.array([opp[e][1] for e in edges], np.int64)
         for name, v in (('v0s', v0s), ('v1s', v1s), ('v2s', v2s), ('v3s', v3s)):
             self.register_buffer(name, torch.from_numpy(v))
+        self.register_buffer('e32', torch.from_numpy(np.stack([v0s, v1s, v2s, v3s]).astype(np.int32)))
+
+    fused = True   # CUDA float32 [B, nv, 3] inputs take the one-launch kernel (b200r_flatten_loss)
 
     def forward(self, vertices, eps=1e-6):
         batch_size = vertices.shape[0]
+        if self.fused and _fusable(vertices):
+            L = _lib.lib()
+            E = int(self.v0s.shape[0])
+
+            def launch(v, loss, grad, stream):
+                _lib.check(L.b200r_flatten_loss(_p(v), _p(self.e32[0]), _p(self.e32[1]), _p(self.e32[2]), _p(self.e32[3]),
+                                                _p(loss), _p(grad), v.shape[0], v.shape[1], E, float(eps), stream),
+                           "b200r_flatten_loss")
+            loss = _FusedMeshLoss.apply(vertices, launch)
+            return loss.sum() / batch_size if self.average else loss
         v0s = torch.index_select(vertices, 1, self.v0s)   # backward = index_add (graph-capturable)
         v1s = torch.index_select(vertices, 1, self.v1s)
         v2s = torch.index_select(vertices, 1, self.v2s)
