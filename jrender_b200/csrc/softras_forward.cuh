@@ -67,10 +67,15 @@ __device__ __forceinline__ void cta_sync() {
     else __syncthreads();
 }
 
-// dynamic shared memory: FwdSmem<NW> | qz [K][NT] f32 | qid [K][NT] i32 | plist [CHUNK][NT] u8 (VARIANT 1)
+// Per-pixel depth list stride in floats: K rounded up to a multiple of 4, plus 4.  Pixel-major so that the
+// "find the new maximum" rescan reads a lane's K depths with K/4 LDS.128; stride/4 is odd for K = 8, 16, 32, 64,
+// which makes those 16-byte accesses bank-conflict free across the 8 lanes of a quarter warp.
+__host__ __device__ static inline int fwd_qz_stride(int K) { return ((K + 3) / 4) * 4 + 4; }
+
+// dynamic shared memory: FwdSmem<NW> | qz [NT][stride] f32 | qid [K][NT] i32 | plist [CHUNK][NT] u8 (VARIANT 1)
 template <int NW>
 static inline size_t fwd_smem_bytes(int K, int variant) {
-    size_t b = sizeof(FwdSmem<NW>) + (size_t)K * FwdCfg<NW>::NT * 8;
+    size_t b = sizeof(FwdSmem<NW>) + (size_t)FwdCfg<NW>::NT * (fwd_qz_stride(K) + K) * 4;
     if (variant == 1) b += (size_t)FwdCfg<NW>::CHUNK * FwdCfg<NW>::NT;
     return (b + 15) & ~(size_t)15;
 }
@@ -79,6 +84,38 @@ struct PixState {
     float sc0, sc1, sc2, alpha, softmax_sum, softmax_max, depth_min, q_max_z;
     int face_index_min, q_size, q_max_id;
 };
+
+// top-K by z with the reference's "replace the current max" policy (:367-385).  my_qz = this pixel's K depths
+// (16-byte aligned, slot order), s_qid = ids [K][NT].  The rescan after a replacement is the reference's loop
+// (first strictly greater depth wins, so ties keep the lowest slot) reading four slots per LDS.128.
+template <int NT>
+__device__ __forceinline__ void topk_insert(PixState& st, float zp, int fn, int K, float* my_qz, int* s_qid, int tid) {
+    if (st.q_size < K) {
+        my_qz[st.q_size] = zp;
+        s_qid[st.q_size * NT + tid] = fn;
+        if (zp > st.q_max_z) { st.q_max_z = zp; st.q_max_id = st.q_size; }
+        st.q_size++;
+    } else if (zp < st.q_max_z) {
+        my_qz[st.q_max_id] = zp;
+        s_qid[st.q_max_id * NT + tid] = fn;
+        float m = -1.f;
+        int id = st.q_max_id;
+        int k = 0;
+        for (; k + 4 <= st.q_size; k += 4) {
+            const float4 v = *reinterpret_cast<const float4*>(my_qz + k);
+            if (v.x > m) { m = v.x; id = k; }
+            if (v.y > m) { m = v.y; id = k + 1; }
+            if (v.z > m) { m = v.z; id = k + 2; }
+            if (v.w > m) { m = v.w; id = k + 3; }
+        }
+        for (; k < st.q_size; k++) {
+            const float z = my_qz[k];
+            if (z > m) { m = z; id = k; }
+        }
+        st.q_max_z = m;
+        st.q_max_id = id;
+    }
+}
 
 // The reference's per-face loop body (:318-420) for one (pixel, face) pair whose pixel is
 // inside the face's check_border rectangle.
@@ -119,22 +156,7 @@ __device__ __forceinline__ void shade_face(const FaceRec* rec, PixState& st, con
     if (zp < P.near_ || zp > P.far_) return;       // :365
 
     const int fn = (int)rec->face_id;
-    const int K = P.K;
-    // top-K by z, "replace the current max" policy (:367-385)
-    if (st.q_size < K) {
-        s_qz[st.q_size * NT + tid] = zp;
-        s_qid[st.q_size * NT + tid] = fn;
-        if (zp > st.q_max_z) { st.q_max_z = zp; st.q_max_id = st.q_size; }
-        st.q_size++;
-    } else if (zp < st.q_max_z) {
-        s_qz[st.q_max_id * NT + tid] = zp;
-        s_qid[st.q_max_id * NT + tid] = fn;
-        st.q_max_z = -1.f;
-        for (int k = 0; k < st.q_size; k++) {
-            const float z = s_qz[k * NT + tid];
-            if (z > st.q_max_z) { st.q_max_z = z; st.q_max_id = k; }
-        }
-    }
+    topk_insert<NT>(st, zp, fn, P.K, s_qz, s_qid, tid);   // s_qz = this pixel's depth list
 
     const bool front = (rec->flags & 8u) != 0;
     if (RGB == 0) {  // :390-397
@@ -222,22 +244,7 @@ __device__ __forceinline__ void shade_face_opt(const FaceRec* rec, PixState& st,
     if (zp < P.near_ || zp > P.far_) return;       // :365
 
     const int fn = (int)rec->face_id;
-    const int K = P.K;
-    // top-K by z, "replace the current max" policy (:367-385)
-    if (st.q_size < K) {
-        s_qz[st.q_size * NT + tid] = zp;
-        s_qid[st.q_size * NT + tid] = fn;
-        if (zp > st.q_max_z) { st.q_max_z = zp; st.q_max_id = st.q_size; }
-        st.q_size++;
-    } else if (zp < st.q_max_z) {
-        s_qz[st.q_max_id * NT + tid] = zp;
-        s_qid[st.q_max_id * NT + tid] = fn;
-        st.q_max_z = -1.f;
-        for (int k = 0; k < st.q_size; k++) {
-            const float z = s_qz[k * NT + tid];
-            if (z > st.q_max_z) { st.q_max_z = z; st.q_max_id = k; }
-        }
-    }
+    topk_insert<NT>(st, zp, fn, P.K, s_qz, s_qid, tid);   // s_qz = this pixel's depth list
 
     const bool front = (rec->flags & 8u) != 0;
     if (RGB == 0) {  // :390-397
@@ -290,14 +297,17 @@ k_softras_forward(const SoftRasParams P, const FaceRec* __restrict__ recs, const
     constexpr int TW = 8 * WX, TH = 4 * WY;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FwdSmem<NW>& S = *reinterpret_cast<FwdSmem<NW>*>(smem_raw);
-    float* s_qz = reinterpret_cast<float*>(smem_raw + sizeof(FwdSmem<NW>));  // [K][NT]
-    int* s_qid = reinterpret_cast<int*>(s_qz + (size_t)P.K * NT);
+    const int qzs = fwd_qz_stride(P.K);
+    float* s_qz_all = reinterpret_cast<float*>(smem_raw + sizeof(FwdSmem<NW>));  // [NT][qzs]
+    int* s_qid = reinterpret_cast<int*>(s_qz_all + (size_t)NT * qzs);             // [K][NT]
     unsigned char* s_plist = reinterpret_cast<unsigned char*>(s_qid + (size_t)P.K * NT);  // VARIANT 1: [CHUNK][NT]
+    float* s_qz = s_qz_all + (size_t)threadIdx.x * qzs;                           // this pixel's K depths, slot order
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int is = P.is, nf = P.nf, K = P.K;
     const int tiles_per_image = P.fntx * P.fnty;
     const int lx = (warp % WX) * 8 + (lane & 7), ly = (warp / WX) * 4 + (lane >> 3);
+    const int tpix = ly * (8 * WX) + lx;  // pixel index inside the tile, row-major: the index of the [K][TH][TW] id planes
     const float threshold = P.dist_eps * P.sigma;  // :289
     const size_t npix = (size_t)is * is;
     DivConst dc;
@@ -351,6 +361,13 @@ k_softras_forward(const SoftRasParams P, const FaceRec* __restrict__ recs, const
         st.q_size = 0;
         st.q_max_z = -1.f;
         st.q_max_id = -1;
+        // id slots start as -1 (the reference memsets the whole buffer, :470): the tile's ids are then written
+        // out plane by plane as 16-byte row segments straight from shared memory.  The previous tile's stores
+        // finished reading s_qid at the cta_sync at the top of this iteration.
+        const bool vec_ids = ((is & 3) == 0) && ((K & 3) == 0);
+        if (vec_ids) {
+            for (int j = tid; j < K * NT / 4; j += NT) reinterpret_cast<int4*>(s_qid)[j] = make_int4(-1, -1, -1, -1);
+        }
 
         const int cbin = (tr0 / P.coarse_px) * P.ncs + (tx0 / P.coarse_px);
         const int n_coarse = coarse_cnt[b * P.ncs * P.ncs + cbin];
@@ -438,7 +455,7 @@ k_softras_forward(const SoftRasParams P, const FaceRec* __restrict__ recs, const
                     for (int it = 0; it < wcnt; it++) {
                         const FaceRec* rec = &S.rec[NW > 1 ? (int)S.wlist[warp][it] : it].r;
                         if (!pixel_in_rect(rec, px, row)) continue;
-                        shade_pair<DIST, RGB, NT, EXACT>(rec, st, P, dc, xp, yp, threshold, s_qz, s_qid, tid, btex);
+                        shade_pair<DIST, RGB, NT, EXACT>(rec, st, P, dc, xp, yp, threshold, s_qz, s_qid, tpix, btex);
                     }
                 } else {
                     // ---- each lane compacts its own list, then lanes walk private lists
@@ -454,7 +471,7 @@ k_softras_forward(const SoftRasParams P, const FaceRec* __restrict__ recs, const
                     for (int i = 0; i < maxcnt; i++) {
                         if (i < cnt) {
                             const FaceRec* rec = &S.rec[s_plist[i * NT + tid]].r;
-                            shade_pair<DIST, RGB, NT, EXACT>(rec, st, P, dc, xp, yp, threshold, s_qz, s_qid, tid, btex);
+                            shade_pair<DIST, RGB, NT, EXACT>(rec, st, P, dc, xp, yp, threshold, s_qz, s_qid, tpix, btex);
                         }
                     }
                 }
@@ -483,7 +500,6 @@ k_softras_forward(const SoftRasParams P, const FaceRec* __restrict__ recs, const
         // 16-byte stores (TW*4 contiguous bytes per tile row).
         cta_sync<NW>();
         float* s_out = reinterpret_cast<float*>(S.rec);  // 6 * NT floats
-        const int tpix = ly * TW + lx;
         s_out[0 * NT + tpix] = o0;
         s_out[1 * NT + tpix] = o1;
         s_out[2 * NT + tpix] = o2;
@@ -515,10 +531,21 @@ k_softras_forward(const SoftRasParams P, const FaceRec* __restrict__ recs, const
             }
         }
         // top-K ids, slot order, -1 padded (replaces cudaMemsetAsync(out3_p, -1, ...) :470 + :453-455)
-        if (px < is && row < is) {
+        if (vec_ids) {
+            // s_qid is [K][TH][TW]: int4 number u covers plane u / (NT/4), tile row (u % (NT/4)) / (TW/4)
+            // (every lane's own id writes were ordered before these cross-lane reads by the cta_sync above)
+            constexpr int QPR = TW / 4, QPP = NT / 4;
+            int* bids = ids_out + (size_t)b * K * npix;
+            for (int u = tid; u < K * QPP; u += NT) {
+                const int k = u / QPP, pq = u - k * QPP;
+                const int orow = tr0 + pq / QPR, ocol = tx0 + (pq % QPR) * 4;
+                if (orow < is && ocol < is)
+                    *reinterpret_cast<int4*>(bids + (size_t)k * npix + (size_t)orow * is + ocol) = reinterpret_cast<const int4*>(s_qid)[u];
+            }
+        } else if (px < is && row < is) {
             int* dst = ids_out + (size_t)b * K * npix + (size_t)row * is + px;
             for (int k = 0; k < K; k++)
-                dst[(size_t)k * npix] = (k < st.q_size) ? s_qid[k * NT + tid] : -1;
+                dst[(size_t)k * npix] = (k < st.q_size) ? s_qid[k * NT + tpix] : -1;
         }
     }
 }
