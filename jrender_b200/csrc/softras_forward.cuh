@@ -38,6 +38,9 @@ struct __align__(16) FaceRecS {
     uint4 pad;
 };
 
+#ifndef B200R_FWD_MASKLIST
+#define B200R_FWD_MASKLIST 1   // 1-warp CTAs: a lane's private face list is a bit mask in a register, not bytes in shared memory
+#endif
 #ifndef B200R_FWD_CHUNK1
 #define B200R_FWD_CHUNK1 16   // records staged per round by a 1-warp CTA
 #endif
@@ -76,7 +79,7 @@ __host__ __device__ static inline int fwd_qz_stride(int K) { return ((K + 3) / 4
 template <int NW>
 static inline size_t fwd_smem_bytes(int K, int variant) {
     size_t b = sizeof(FwdSmem<NW>) + (size_t)FwdCfg<NW>::NT * (fwd_qz_stride(K) + K) * 4;
-    if (variant == 1) b += (size_t)FwdCfg<NW>::CHUNK * FwdCfg<NW>::NT;
+    if (variant == 1 && !(B200R_FWD_MASKLIST && FwdCfg<NW>::CHUNK <= 32)) b += (size_t)FwdCfg<NW>::CHUNK * FwdCfg<NW>::NT;
     return (b + 15) & ~(size_t)15;
 }
 
@@ -459,6 +462,22 @@ k_softras_forward(const SoftRasParams P, const FaceRec* __restrict__ recs, const
                     }
                 } else {
                     // ---- each lane compacts its own list, then lanes walk private lists
+                    if constexpr (B200R_FWD_MASKLIST && CHUNK <= 32) {
+                        // the list is a bit mask over the staged records (ascending record = ascending face id)
+                        unsigned mask = 0u;
+                        for (int it = 0; it < wcnt; it++) {
+                            const int j = NW > 1 ? (int)S.wlist[warp][it] : it;
+                            if (pixel_in_rect(&S.rec[j].r, px, row)) mask |= 1u << j;
+                        }
+                        const int maxcnt = __reduce_max_sync(0xffffffffu, __popc(mask));
+                        for (int i = 0; i < maxcnt; i++) {
+                            if (mask != 0u) {
+                                const FaceRec* rec = &S.rec[__ffs(mask) - 1].r;
+                                mask &= mask - 1u;
+                                shade_pair<DIST, RGB, NT, EXACT>(rec, st, P, dc, xp, yp, threshold, s_qz, s_qid, tpix, btex);
+                            }
+                        }
+                    } else {
                     int cnt = 0;
                     for (int it = 0; it < wcnt; it++) {
                         const int j = NW > 1 ? (int)S.wlist[warp][it] : it;
@@ -473,6 +492,7 @@ k_softras_forward(const SoftRasParams P, const FaceRec* __restrict__ recs, const
                             const FaceRec* rec = &S.rec[s_plist[i * NT + tid]].r;
                             shade_pair<DIST, RGB, NT, EXACT>(rec, st, P, dc, xp, yp, threshold, s_qz, s_qid, tpix, btex);
                         }
+                    }
                     }
                 }
                 head += m;
