@@ -47,6 +47,12 @@ struct __align__(16) FaceRecS {
 #ifndef B200R_FWD_MINB1
 #define B200R_FWD_MINB1 24    // resident 1-warp CTAs per SM the register allocation must allow
 #endif
+#ifndef B200R_FWD_MINB1_SIL
+// Silhouette instantiations (RGB none): at the 80-register cap of 24 CTAs/SM ptxas spills inside the pair loop;
+// 20 CTAs/SM (96 registers) measured 18 % faster on the C5 forward (2.57 -> 2.09 ms, 60 views), while the colour
+// instantiations are faster at 24 (C3: 0.975 vs 1.041 ms).
+#define B200R_FWD_MINB1_SIL 20
+#endif
 
 template <int NW>
 struct FwdCfg {
@@ -290,7 +296,7 @@ __device__ __forceinline__ bool pixel_in_rect(const FaceRec* rec, int px, int ro
 }
 
 template <int DIST, int RGB, int VARIANT, int WX, int WY, bool EXACT>
-__global__ void __launch_bounds__(32 * WX * WY, (WX * WY >= 8) ? 2 : ((WX * WY >= 2) ? 8 : B200R_FWD_MINB1))
+__global__ void __launch_bounds__(32 * WX * WY, (WX * WY >= 8) ? 2 : ((WX * WY >= 2) ? 8 : (RGB == 2 ? B200R_FWD_MINB1_SIL : B200R_FWD_MINB1)))
 k_softras_forward(const SoftRasParams P, const FaceRec* __restrict__ recs, const uint2* __restrict__ rects,
                   const int* __restrict__ coarse_cnt, const int* __restrict__ coarse_ids,
                   const float* __restrict__ textures, float* __restrict__ soft_colors,

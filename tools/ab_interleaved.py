@@ -93,7 +93,7 @@ def main():
                 ms, cnt = C.c_double(0), C.c_longlong(0)
                 L.b200r_profile_read(kid, C.byref(ms), C.byref(cnt))
                 res[n_][key].append(ms.value / max(1, cnt.value))
-    print(json.dumps({"workload": name, **{n_: {k: round(float(np.median(v)), 4) for k, v in d.items()} for n_, d in res.items()}}))
+    print(json.dumps({"workload": name, **{n_: {k: [round(float(np.min(v)), 4), round(float(np.median(v)), 4), round(float(np.max(v)), 4)] for k, v in d.items()} for n_, d in res.items()}}))
 
 
 if __name__ == "__main__":
