@@ -224,6 +224,7 @@ k_softras_backward_lane(const SoftRasParams P, const FaceRec* __restrict__ recs,
 
     DivConst dc;
     dc.init(P);
+    const bool consts_ok = dc.consts_ok();
     BwdPixel px;
     px.xp = b200r_pix_coord(pxi, is);
     px.yp = b200r_pix_coord(is - 1 - row, is);
@@ -253,7 +254,7 @@ k_softras_backward_lane(const SoftRasParams P, const FaceRec* __restrict__ recs,
         float gt[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         int texel;
         DivGuard guard;
-        guard.ok = true;
+        guard.ok = consts_ok;   // launch-constant denominators (sigma, gamma, far - near) validated once per thread
         if constexpr (!EXACT && B200R_BWD_OPTIMISTIC) {
             // all divisions branch-free; one range flag for the whole pair, one (cold) re-run if it dropped
             pair_gradient<DIST, RGB, false, true>(rec, fn, px, P, dc, nmf, r_nmf, s_nmf, btex + (size_t)fn * T * 3, gv, gt, texel, guard);

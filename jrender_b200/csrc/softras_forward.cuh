@@ -173,7 +173,7 @@ __device__ __forceinline__ void shade_face(const FaceRec* rec, PixState& st, con
             st.depth_min = zp;
             st.face_index_min = fn;
             float col[3];
-            sample_texture_fwd(col, btex + (size_t)fn * P.T * 3, wc, P.R, P.tex_type, rec, zp);
+            sample_texture_fwd(col, btex, fn, P.T, wc, P.R, P.tex_type, rec, zp);
             st.sc0 = col[0]; st.sc1 = col[1]; st.sc2 = col[2];
         }
     } else if (RGB == 1) {  // :399-419
@@ -187,7 +187,7 @@ __device__ __forceinline__ void shade_face(const FaceRec* rec, PixState& st, con
             const float exp_z = expf(dc.template by_gamma_t<EXACT>(zp_norm - st.softmax_max));
             st.softmax_sum = exp_delta_zp * st.softmax_sum + exp_z * soft_fragment;
             float col[3];
-            sample_texture_fwd(col, btex + (size_t)fn * P.T * 3, wc, P.R, P.tex_type, rec, zp);
+            sample_texture_fwd(col, btex, fn, P.T, wc, P.R, P.tex_type, rec, zp);
             st.sc0 = exp_delta_zp * st.sc0 + exp_z * soft_fragment * col[0];
             st.sc1 = exp_delta_zp * st.sc1 + exp_z * soft_fragment * col[1];
             st.sc2 = exp_delta_zp * st.sc2 + exp_z * soft_fragment * col[2];
@@ -208,9 +208,9 @@ __device__ __forceinline__ void shade_face(const FaceRec* rec, PixState& st, con
 template <int DIST, int RGB, int NT>
 __device__ __forceinline__ void shade_face_opt(const FaceRec* rec, PixState& st, const SoftRasParams& P, const DivConst& dc,
                                                float xp, float yp, float threshold, float* s_qz, int* s_qid, int tid,
-                                               const float* __restrict__ btex) {
+                                               const float* __restrict__ btex, bool consts_ok) {
     DivGuard g;
-    g.ok = true;
+    g.ok = consts_ok;   // dc.consts_ok(), evaluated once per thread by the kernel
     float w[3];
     barycentric_coordinate(w, xp, yp, rec->inv);
 
@@ -261,7 +261,7 @@ __device__ __forceinline__ void shade_face_opt(const FaceRec* rec, PixState& st,
             st.depth_min = zp;
             st.face_index_min = fn;
             float col[3];
-            sample_texture_fwd(col, btex + (size_t)fn * P.T * 3, wc, P.R, P.tex_type, rec, zp);
+            sample_texture_fwd(col, btex, fn, P.T, wc, P.R, P.tex_type, rec, zp);
             st.sc0 = col[0]; st.sc1 = col[1]; st.sc2 = col[2];
         }
     } else if (RGB == 1) {  // :399-419
@@ -272,7 +272,7 @@ __device__ __forceinline__ void shade_face_opt(const FaceRec* rec, PixState& st,
             if (up) st.softmax_max = zp_norm;
             st.softmax_sum = exp_delta_zp * st.softmax_sum + exp_z * soft_fragment;
             float col[3];
-            sample_texture_fwd(col, btex + (size_t)fn * P.T * 3, wc, P.R, P.tex_type, rec, zp);
+            sample_texture_fwd(col, btex, fn, P.T, wc, P.R, P.tex_type, rec, zp);
             st.sc0 = exp_delta_zp * st.sc0 + exp_z * soft_fragment * col[0];
             st.sc1 = exp_delta_zp * st.sc1 + exp_z * soft_fragment * col[1];
             st.sc2 = exp_delta_zp * st.sc2 + exp_z * soft_fragment * col[2];
@@ -284,8 +284,8 @@ __device__ __forceinline__ void shade_face_opt(const FaceRec* rec, PixState& st,
 template <int DIST, int RGB, int NT, bool EXACT>
 __device__ __forceinline__ void shade_pair(const FaceRec* rec, PixState& st, const SoftRasParams& P, const DivConst& dc,
                                            float xp, float yp, float threshold, float* s_qz, int* s_qid, int tid,
-                                           const float* __restrict__ btex) {
-    if constexpr (!EXACT && B200R_FWD_OPTIMISTIC) shade_face_opt<DIST, RGB, NT>(rec, st, P, dc, xp, yp, threshold, s_qz, s_qid, tid, btex);
+                                           const float* __restrict__ btex, bool consts_ok) {
+    if constexpr (!EXACT && B200R_FWD_OPTIMISTIC) shade_face_opt<DIST, RGB, NT>(rec, st, P, dc, xp, yp, threshold, s_qz, s_qid, tid, btex, consts_ok);
     else shade_face<DIST, RGB, NT, EXACT>(rec, st, P, dc, xp, yp, threshold, s_qz, s_qid, tid, btex);
 }
 
@@ -321,6 +321,7 @@ k_softras_forward(const SoftRasParams P, const FaceRec* __restrict__ recs, const
     const size_t npix = (size_t)is * is;
     DivConst dc;
     dc.init(P);
+    const bool consts_ok = dc.consts_ok();
     const float softmax_sum0 = expf(P.eps / P.gamma);
 
     for (int titer = 0;; titer++) {
@@ -464,7 +465,7 @@ k_softras_forward(const SoftRasParams P, const FaceRec* __restrict__ recs, const
                     for (int it = 0; it < wcnt; it++) {
                         const FaceRec* rec = &S.rec[NW > 1 ? (int)S.wlist[warp][it] : it].r;
                         if (!pixel_in_rect(rec, px, row)) continue;
-                        shade_pair<DIST, RGB, NT, EXACT>(rec, st, P, dc, xp, yp, threshold, s_qz, s_qid, tpix, btex);
+                        shade_pair<DIST, RGB, NT, EXACT>(rec, st, P, dc, xp, yp, threshold, s_qz, s_qid, tpix, btex, consts_ok);
                     }
                 } else {
                     // ---- each lane compacts its own list, then lanes walk private lists
@@ -480,7 +481,7 @@ k_softras_forward(const SoftRasParams P, const FaceRec* __restrict__ recs, const
                             if (mask != 0u) {
                                 const FaceRec* rec = &S.rec[__ffs(mask) - 1].r;
                                 mask &= mask - 1u;
-                                shade_pair<DIST, RGB, NT, EXACT>(rec, st, P, dc, xp, yp, threshold, s_qz, s_qid, tpix, btex);
+                                shade_pair<DIST, RGB, NT, EXACT>(rec, st, P, dc, xp, yp, threshold, s_qz, s_qid, tpix, btex, consts_ok);
                             }
                         }
                     } else {
@@ -496,7 +497,7 @@ k_softras_forward(const SoftRasParams P, const FaceRec* __restrict__ recs, const
                     for (int i = 0; i < maxcnt; i++) {
                         if (i < cnt) {
                             const FaceRec* rec = &S.rec[s_plist[i * NT + tid]].r;
-                            shade_pair<DIST, RGB, NT, EXACT>(rec, st, P, dc, xp, yp, threshold, s_qz, s_qid, tpix, btex);
+                            shade_pair<DIST, RGB, NT, EXACT>(rec, st, P, dc, xp, yp, threshold, s_qz, s_qid, tpix, btex, consts_ok);
                         }
                     }
                     }

@@ -31,10 +31,13 @@ struct DivConst {
     template <bool EXACT> __device__ __forceinline__ float by_sigma_t(float a) const { return div_t<EXACT>(a, sigma, r_sigma, s_sigma); }
     template <bool EXACT> __device__ __forceinline__ float by_gamma_t(float a) const { return div_t<EXACT>(a, gamma, r_gamma, s_gamma); }
     template <bool EXACT> __device__ __forceinline__ float by_span_t(float a) const { return div_t<EXACT>(a, span, r_span, s_span); }
-    // optimistic (branch-free) flavours, see DivGuard in exact_math.cuh
-    __device__ __forceinline__ float by_sigma_o(float a, DivGuard& g) const { return optimistic_div(a, sigma, r_sigma, s_sigma, g); }
-    __device__ __forceinline__ float by_gamma_o(float a, DivGuard& g) const { return optimistic_div(a, gamma, r_gamma, s_gamma, g); }
-    __device__ __forceinline__ float by_span_o(float a, DivGuard& g) const { return optimistic_div(a, span, r_span, s_span, g); }
+    // optimistic (branch-free) flavours, see DivGuard in exact_math.cuh.  The three denominators are launch constants:
+    // a pair's guard STARTS as consts_ok() (so a launch with an out-of-range sigma / gamma / far - near simply runs
+    // every pair through the guarded functions) and the per-division test covers the numerator only.
+    __device__ __forceinline__ bool consts_ok() const { return s_sigma && s_gamma && s_span; }
+    __device__ __forceinline__ float by_sigma_o(float a, DivGuard& g) const { return optimistic_div_okden(a, sigma, r_sigma, g); }
+    __device__ __forceinline__ float by_gamma_o(float a, DivGuard& g) const { return optimistic_div_okden(a, gamma, r_gamma, g); }
+    __device__ __forceinline__ float by_span_o(float a, DivGuard& g) const { return optimistic_div_okden(a, span, r_span, g); }
 };
 
 // :20-25
@@ -107,8 +110,11 @@ __device__ __forceinline__ float clip_and_z_opt(float w[3], const FaceRec* rec, 
     const float w_sum = fmaxf(w[0] + w[1] + w[2], 1e-5f);
     g.ok = g.ok && ((rec->flags & 0x70u) == 0x70u);
     if (STRICT) {
-        const float tiny = 3.4694469519536142e-18f;  // 2^-58
-        g.ok = g.ok && (w[0] == 0.f || w[0] >= tiny) && (w[1] == 0.f || w[1] >= tiny) && (w[2] == 0.f || w[2] >= tiny);
+        // each clamped weight (in [+0, 1]) must be 0 or >= 2^-58: on the bit patterns, (bits - 1) >= (bits(2^-58) - 1)
+        // unsigned (0 wraps to 0xffffffff) -- one add + one compare-and-AND per weight
+        const uint32_t lim = 0x22800000u - 1u;  // bits(2^-58) - 1
+#pragma unroll
+        for (int k = 0; k < 3; k++) g.ok = g.ok && (__float_as_uint(w[k]) - 1u) >= lim;
     }
     if (w_sum != 1.f) {  // x / 1 == x exactly
         const float r = rcp_refined(w_sum);
@@ -185,8 +191,8 @@ __device__ __forceinline__ float euclidean_p2f_distance(float& dis_x, float& dis
         const int v1 = v0 == 2 ? 0 : v0 + 1;
         const float* a = rec->a0 + 3 * v0;
         const float a_0 = a[0], a_1 = a[1], a_2 = a[2];
-        const float a_v0 = sel3(v0, a_0, a_1, a_2);
-        const float a_v1 = sel3(v1, a_0, a_1, a_2);
+        const float a_v0 = a[v0];   // the record lives in shared memory (forward) / L1 (backward): two indexed loads
+        const float a_v1 = a[v1];   // are cheaper than two compare-select chains
         const float tv0 = edge_div(w[0] * a_0 + w[1] * a_1 + w[2] * a_2 - a_v1, a_v0 - a_v1, rec->rden[v0],
                                    (fl & (128u << v0)) != 0);
         const float tv1 = 1.f - tv0;
@@ -244,13 +250,18 @@ __device__ __forceinline__ int surface_texel(const float w[3], int R) {
 }
 
 // :156-173 forward flavour (vertex mode perspective-correct); tex points at this face's texels
-__device__ __forceinline__ void sample_texture_fwd(float col[3], const float* __restrict__ tex,
+__device__ __forceinline__ void sample_texture_fwd(float col[3], const float* __restrict__ btex, int fn, int T,
                                                    const float w[3], int R, int tex_type,
                                                    const FaceRec* rec, float z) {
     if (tex_type == 0) {
-        if (R == 1) {
+        if (R == 1) {   // the face colour travels in the record: no texture address arithmetic at all
             col[0] = rec->col[0]; col[1] = rec->col[1]; col[2] = rec->col[2];
-        } else {
+            return;
+        }
+    }
+    const float* __restrict__ tex = btex + (size_t)fn * T * 3;   // this face's texels
+    if (tex_type == 0) {
+        {
             const int j = surface_texel(w, R);
 #pragma unroll
             for (int k = 0; k < 3; k++) col[k] = __ldg(tex + j * 3 + k);
