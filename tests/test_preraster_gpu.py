@@ -138,3 +138,25 @@ def test_project_faces_cuda_graph_replay(cuda_device):
     ref = opr.project_faces(v[None], f[None], np.float32([[1.0, 0.5, -2.5]]))
     assert np.abs(out.detach().cpu().numpy() - ref).max() <= FWD_TOL * np.abs(ref).max()
     assert not torch.equal(vt.grad, eager)
+
+
+def test_silhouette_render_skips_lighting_without_changing_alpha(cuda_device):
+    """Renderer.skip_unused_lighting: mode='silhouettes' never reads a texture value, so leaving the lighting ops
+    out must give the same alpha bits and the same vertex gradient as the reference's always-light order."""
+    v, f = wl.sphere_by_faces(280)
+    res = {}
+    for skip in (True, False):
+        jr.Renderer.skip_unused_lighting = skip
+        try:
+            vt = torch.from_numpy(v)[None].to(cuda_device).requires_grad_(True)
+            mesh = jr.Mesh(vt, torch.from_numpy(f)[None].to(cuda_device))
+            r = jr.Renderer(image_size=64, camera_mode='look_at', sigma_val=1e-4, aggr_func_rgb='hard')
+            r.transform.set_eyes_from_angles(2.732, 20.0, 75.0)
+            a = r.render_mesh(mesh, mode='silhouettes')
+            a.sum().backward()
+            res[skip] = (a.detach().cpu().numpy(), vt.grad.cpu().numpy(), mesh.textures.detach().cpu().numpy())
+        finally:
+            jr.Renderer.skip_unused_lighting = True
+    assert np.array_equal(res[True][0], res[False][0])
+    assert np.abs(res[True][1] - res[False][1]).max() <= BWD_TOL * np.abs(res[False][1]).max()
+    assert np.all(res[True][2] == 1.0) and not np.all(res[False][2] == 1.0)   # the documented side-effect difference
