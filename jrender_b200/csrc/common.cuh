@@ -106,7 +106,13 @@ static inline SoftRasWorkspace b200r_carve(void* base, int B, int nf, int image_
 #ifdef __CUDACC__
 // NDC coordinate of pixel index i (x: column; y: is-1-row), evaluated in double and
 // rounded to float exactly like `(2. * xi + 1. - is) / is` (cuda/soft_rasterize.py:282-283).
+//
+// Evaluated as ONE fp32 division of the exact integers 2i + 1 - is and is: both are exactly representable, so the
+// IEEE quotient is the correctly rounded value of the rational -- and so is the reference's double quotient rounded to
+// float (a double rounding could only differ if the 53-bit quotient fell on a 24-bit rounding midpoint, which a ratio
+// of integers below 2^14 cannot approach closer than 2^-38 relative).  Checked exhaustively for every image size up to
+// the API limit of 4096 and every pixel index (tests/test_oracle_cpu.py).  The double division cost ~2 % of the forward.
 __device__ __forceinline__ float b200r_pix_coord(int i, int is) {
-    return (float)((2.0 * (double)i + 1.0 - (double)is) / (double)is);
+    return __fdiv_rn((float)(2 * i + 1 - is), (float)is);
 }
 #endif

@@ -41,6 +41,9 @@ struct __align__(16) FaceRecS {
 #ifndef B200R_FWD_MASKLIST
 #define B200R_FWD_MASKLIST 1   // 1-warp CTAs: a lane's private face list is a bit mask in a register, not bytes in shared memory
 #endif
+#ifndef B200R_FWD_LANEMASK
+#define B200R_FWD_LANEMASK 1   // 1-warp CTAs: build the per-lane face masks by transposing per-record lane masks
+#endif
 #ifndef B200R_FWD_CHUNK1
 #define B200R_FWD_CHUNK1 16   // records staged per round by a 1-warp CTA
 #endif
@@ -66,6 +69,7 @@ struct FwdSmem {
     FaceRecS rec[FwdCfg<NW>::CHUNK];                     // reused as the output staging area
     int ids[FwdCfg<NW>::CHUNK + FwdCfg<NW>::UNR * FwdCfg<NW>::NT];  // pending tile-face ids, ascending
     unsigned char wlist[NW][FwdCfg<NW>::CHUNK];          // per-warp sub-list (indices into rec[])
+    uint32_t lmask[16];                                  // 1-warp CTAs: per staged record, the lanes whose pixel it covers
     int s_warp[NW];
     int s_tile;
 };
@@ -242,13 +246,13 @@ __device__ __forceinline__ void shade_face_opt(const FaceRec* rec, PixState& st,
         return;
     }
 
-    // alpha aggregation, before any z test (:349-358, Q2)
-    if (P.alpha_func == 0) {
-        if (soft_fragment > 0.5f) st.alpha = 1.f;
+    // alpha aggregation, before any z test (:349-358, Q2); the default ('prod') is tested first
+    if (P.alpha_func == 2) {
+        st.alpha = st.alpha * (1.f - soft_fragment);
     } else if (P.alpha_func == 1) {
         st.alpha += soft_fragment;
     } else {
-        st.alpha = st.alpha * (1.f - soft_fragment);
+        if (soft_fragment > 0.5f) st.alpha = 1.f;
     }
     if (zp < P.near_ || zp > P.far_) return;       // :365
 
@@ -472,9 +476,37 @@ k_softras_forward(const SoftRasParams P, const FaceRec* __restrict__ recs, const
                     if constexpr (B200R_FWD_MASKLIST && CHUNK <= 32) {
                         // the list is a bit mask over the staged records (ascending record = ascending face id)
                         unsigned mask = 0u;
-                        for (int it = 0; it < wcnt; it++) {
-                            const int j = NW > 1 ? (int)S.wlist[warp][it] : it;
-                            if (pixel_in_rect(&S.rec[j].r, px, row)) mask |= 1u << j;
+                        if constexpr (B200R_FWD_LANEMASK && NW == 1 && CHUNK == 16) {
+                            // Transposed build: lane j turns record j's rectangle, clipped to the 8x4 block, into the
+                            // 32-bit set of covered lanes (a column mask replicated over the covered rows); every lane
+                            // then picks its own bit out of the 16 words (4 broadcast LDS.128).  ~40 instructions per
+                            // round instead of 16 x (rectangle load + two range tests).
+                            uint32_t lm = 0u;
+                            if (lane < wcnt) {
+                                const uint32_t rx = S.rec[lane].r.rect_x, rr = S.rec[lane].r.rect_r;
+                                const int cx0 = max((int)(rx & 0xffffu) - tx0, 0), cx1 = min((int)(rx >> 16) - tx0, 7);
+                                const int ry0 = max((int)(rr & 0xffffu) - tr0, 0), ry1 = min((int)(rr >> 16) - tr0, 3);
+                                if (cx0 <= cx1 && ry0 <= ry1) {
+                                    const uint32_t cols = (2u << cx1) - (1u << cx0);
+                                    const uint32_t rows = (0xffffffffu >> (24 - 8 * ry1)) & (0xffffffffu << (8 * ry0));
+                                    lm = (cols * 0x01010101u) & rows;
+                                }
+                            }
+                            if (lane < 16) S.lmask[lane] = lm;
+                            __syncwarp();
+#pragma unroll
+                            for (int q = 0; q < 4; q++) {
+                                const uint4 m4 = reinterpret_cast<const uint4*>(S.lmask)[q];
+                                mask |= ((m4.x >> lane) & 1u) << (4 * q + 0);
+                                mask |= ((m4.y >> lane) & 1u) << (4 * q + 1);
+                                mask |= ((m4.z >> lane) & 1u) << (4 * q + 2);
+                                mask |= ((m4.w >> lane) & 1u) << (4 * q + 3);
+                            }
+                        } else {
+                            for (int it = 0; it < wcnt; it++) {
+                                const int j = NW > 1 ? (int)S.wlist[warp][it] : it;
+                                if (pixel_in_rect(&S.rec[j].r, px, row)) mask |= 1u << j;
+                            }
                         }
                         const int maxcnt = __reduce_max_sync(0xffffffffu, __popc(mask));
                         for (int i = 0; i < maxcnt; i++) {

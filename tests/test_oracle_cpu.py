@@ -117,3 +117,13 @@ def test_texture_gradient_is_the_softmax_weight_for_T1(scene):
     _, gt = osr.backward(fv, tex, out, g, P)
     tot = gt[..., 0].sum()
     assert 0.0 < tot <= 2 * 32 * 32 * (1 + 1e-4)
+
+
+def test_pixel_coordinate_fp32_division_equals_reference_double_formula():
+    """csrc/common.cuh b200r_pix_coord: float(2i+1-is) / float(is) in fp32 must equal the reference's
+    (float)((2.*i + 1. - is) / is) (cuda/soft_rasterize.py:282-283) for every image size the ABI accepts."""
+    for isz in range(1, 4097):
+        i = np.arange(isz, dtype=np.float64)
+        ref = ((2.0 * i + 1.0 - isz) / isz).astype(np.float32)
+        got = (2 * np.arange(isz) + 1 - isz).astype(np.float32) / np.float32(isz)
+        assert np.array_equal(ref.view(np.uint32), got.view(np.uint32)), isz
