@@ -23,6 +23,13 @@
 #pragma once
 #include "softras_math.cuh"
 
+#ifndef B200R_BWD_MINB
+// resident 256-thread CTAs per SM the backward's register allocation must allow.  Measured at C3: 2 (107 registers)
+// 0.571 ms, 3 (80) 0.481 ms, 4 (64, 16 B spilled) 0.483 ms -- past 24 warps/SM the kernel is bound by the divergent
+// 160-byte record gathers (L1 throughput 66 %), not by latency; at C5 (3 280 large faces, 60 views) all three give
+// 0.77 ms: there the float atomics on a few thousand hot accumulator rows are the limit.
+#define B200R_BWD_MINB 3
+#endif
 #ifndef B200R_BWD_OPTIMISTIC
 #define B200R_BWD_OPTIMISTIC 1   // 0: guarded (branching) divisions in the relaxed backward, for A/B builds
 #endif
@@ -204,7 +211,7 @@ __device__ __forceinline__ void load_pixel(BwdPixel& px, const float* __restrict
 
 // ---------------------------------------------------------------- VARIANT 1: per-lane walk + vector atomics
 template <int DIST, int RGB, bool EXACT>
-__global__ void __launch_bounds__(B200R_TILE_THREADS, 3)
+__global__ void __launch_bounds__(B200R_TILE_THREADS, B200R_BWD_MINB)
 k_softras_backward_lane(const SoftRasParams P, const FaceRec* __restrict__ recs, const float* __restrict__ textures,
                         const float* __restrict__ soft_colors, const float* __restrict__ aggrs_info,
                         const int* __restrict__ ids_in, const float* __restrict__ grad_soft_colors,
