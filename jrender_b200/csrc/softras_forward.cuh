@@ -51,10 +51,11 @@ struct __align__(16) FaceRecS {
 #define B200R_FWD_MINB1 24    // resident 1-warp CTAs per SM the register allocation must allow
 #endif
 #ifndef B200R_FWD_MINB1_SIL
-// Silhouette instantiations (RGB none): at the 80-register cap of 24 CTAs/SM ptxas spills inside the pair loop;
-// 20 CTAs/SM (96 registers) measured 18 % faster on the C5 forward (2.57 -> 2.09 ms, 60 views), while the colour
-// instantiations are faster at 24 (C3: 0.975 vs 1.041 ms).
-#define B200R_FWD_MINB1_SIL 20
+// Silhouette instantiations (RGB none) have their own occupancy target because ptxas' register allocation differs:
+// while the pair loop still spilled at the 80-register cap, 20 CTAs/SM (96 registers) was 18 % faster on the C5
+// forward; after the register-pressure work (guards seeded with consts_ok, mask lists) 24 wins again
+// (1.83 vs 2.22 ms, 60 views), as it always did for the colour instantiations (C3: 0.873 vs 0.910 ms).
+#define B200R_FWD_MINB1_SIL 24
 #endif
 
 template <int NW>

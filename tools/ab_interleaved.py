@@ -20,8 +20,14 @@ _F, _I, _P = C.c_float, C.c_int, C.c_void_p
 SCAL = [_I, _I, _I, _I, _I, _F, _F, _F, _F, _F, _F, _I, _I, _I, _I, _I, _P]
 
 
-def load(path):
+def load(spec):
+    """spec = path[#option=value[,option=value...]]: options are applied to this library instance."""
+    path, _, opts = spec.partition("#")
     L = C.CDLL(path)
+    L.b200r_set_option.argtypes = [C.c_char_p, _I]
+    for kv in filter(None, opts.split(",")):
+        k, v = kv.split("=")
+        assert L.b200r_set_option(k.encode(), int(v)) == 0, kv
     L.b200r_softras_workspace_bytes.restype = C.c_size_t
     L.b200r_softras_workspace_bytes.argtypes = [_I, _I, _I]
     L.b200r_softras_forward.restype = _I
@@ -37,6 +43,9 @@ def scene(name):
     if name == "c3":
         fv, tex = wl.make_scene(39200, batch=4)
         return fv, tex, 1024, 1e-5, 1   # rgb softmax
+    if name == "c2":
+        fv, tex = wl.make_scene(3280, batch=8)
+        return fv, tex, 1024, 1e-5, 1
     views = 60
     v, f = wl.sphere_by_faces(3280, radius=1.0)
     v = v * 0.5
@@ -64,6 +73,15 @@ def main():
     scal = (B, nf, 1, H, K, 1.0, 100.0, 1e-3, float(np.float32(sigma)), float(np.float32(1e-4)),
             float(np.float32(math.log(1.0 / 1e-4 - 1.0))), 2, rgb, 2, 0, 1)
     Ls = [(os.path.basename(l), load(l)) for l in libs]
+    if len(set(l.partition('#')[0] for l in libs)) != len(libs):   # the same file loaded twice would share one handle (and its options)
+        import shutil, tempfile
+        tmp = tempfile.mkdtemp()
+        Ls = []
+        for i, l in enumerate(libs):
+            path, _, opts = l.partition("#")
+            cp = os.path.join(tmp, "%d_%s" % (i, os.path.basename(path)))
+            shutil.copy(path, cp)
+            Ls.append((os.path.basename(l), load(cp + ("#" + opts if opts else ""))))
     ws = {}
     for n_, L in Ls:
         nb = L.b200r_softras_workspace_bytes(B, nf, H)
