@@ -23,6 +23,9 @@
 #pragma once
 #include "softras_math.cuh"
 
+#ifndef B200R_BWD_MERGE
+#define B200R_BWD_MERGE 1        // warp-side aggregation levels before the atomics: 0 off, 1 = lanes ^1 and ^8, 2 = also ^2 and ^16
+#endif
 #ifndef B200R_BWD_MINB
 // resident 256-thread CTAs per SM the backward's register allocation must allow.  Measured at C3: 2 (107 registers)
 // 0.571 ms, 3 (80) 0.481 ms, 4 (64, 16 B spilled) 0.483 ms -- past 24 warps/SM the kernel is bound by the divergent
@@ -209,6 +212,29 @@ __device__ __forceinline__ void load_pixel(BwdPixel& px, const float* __restrict
     px.d_one_minus_alpha = (double)(1.f - px.oc[3]);
 }
 
+// One butterfly level of warp-side aggregation: lanes L and L ^ D that hold the SAME face add their 12 (silhouette: 6)
+// gradient values into the lower lane; the upper lane drops out (key = -1).  Keys differ -> nothing happens.
+template <int D, int RGB>
+__device__ __forceinline__ void merge_same_face(int& key, float gv[9], float gt[9], int lane) {
+    const int pkey = __shfl_xor_sync(0xffffffffu, key, D);
+    const bool same = (pkey == key) && (key >= 0);
+    const bool lower = (lane & D) == 0;
+#pragma unroll
+    for (int c = 0; c < 9; c++) {
+        if (RGB == 2 && (c % 3) == 2) continue;   // silhouettes: the z gradients are identically 0
+        const float o = __shfl_xor_sync(0xffffffffu, gv[c], D);
+        if (same && lower) gv[c] += o;
+    }
+    if (RGB != 2) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const float o = __shfl_xor_sync(0xffffffffu, gt[c], D);
+            if (same && lower) gt[c] += o;
+        }
+    }
+    if (same && !lower) key = -1;
+}
+
 // ---------------------------------------------------------------- VARIANT 1: per-lane walk + vector atomics
 template <int DIST, int RGB, bool EXACT>
 __global__ void __launch_bounds__(B200R_TILE_THREADS, B200R_BWD_MINB)
@@ -227,7 +253,15 @@ k_softras_backward_lane(const SoftRasParams P, const FaceRec* __restrict__ recs,
     const size_t pn = (size_t)row * is + pxi;
     const int* src = ids_in + (size_t)b * K * npix + pn;
     int fn = valid ? __ldg(src) : -1;
-    if (fn < 0) return;  // list ends at the first -1 (:1236)
+    // MERGE: the warp stays convergent (lanes whose list is empty or exhausted idle with key -1) so that lanes holding
+    // the same face can combine their contributions by shuffle before the atomics
+    constexpr bool MERGE = B200R_BWD_MERGE != 0;
+    if (MERGE) {
+        if (__all_sync(0xffffffffu, fn < 0)) return;
+    } else {
+        if (fn < 0) return;  // list ends at the first -1 (:1236)
+    }
+    const bool has_list = fn >= 0;
 
     DivConst dc;
     dc.init(P);
@@ -235,7 +269,7 @@ k_softras_backward_lane(const SoftRasParams P, const FaceRec* __restrict__ recs,
     BwdPixel px;
     px.xp = b200r_pix_coord(pxi, is);
     px.yp = b200r_pix_coord(is - 1 - row, is);
-    load_pixel(px, soft_colors, aggrs_info, grad_soft_colors, b, pn, npix, true);
+    load_pixel(px, soft_colors, aggrs_info, grad_soft_colors, b, pn, npix, has_list);
     const float nmf = P.near_ - P.far_;
     const float r_nmf = rcp_refined(nmf);
     const bool s_nmf = midrange(nmf);
@@ -248,9 +282,15 @@ k_softras_backward_lane(const SoftRasParams P, const FaceRec* __restrict__ recs,
     // ids are fetched two slots ahead, so the id of the NEXT face is already in a register when
     // its record is prefetched (waiting for a just-issued id load here stalled every iteration).
     // Prefetching two pairs ahead (ids three ahead) was measured too: no gain (0.487 vs 0.480 ms at C3).
-    int fn_next = (1 < K) ? __ldg(src + npix) : -1;
-    for (int m = 0; m < K && fn >= 0; m++) {
-        const int fn_next2 = (m + 2 < K) ? __ldg(src + (size_t)(m + 2) * npix) : -1;
+    const bool merge_ok = MERGE && (tex_in_acc || RGB == 2);   // texel-indexed texture gradients are not merged
+    int fn_next = (1 < K && has_list) ? __ldg(src + npix) : -1;
+    for (int m = 0; m < K; m++) {
+        if (MERGE) {
+            if (__all_sync(0xffffffffu, fn < 0)) break;
+        } else if (fn < 0) {
+            break;
+        }
+        const int fn_next2 = (m + 2 < K && has_list) ? __ldg(src + (size_t)(m + 2) * npix) : -1;
         if (fn_next >= 0) {  // pull the next face's record (two 128-byte lines) towards L1 behind this pair's math
             const char* nr = reinterpret_cast<const char*>(brecs + fn_next);
             asm volatile("prefetch.global.L1 [%0];" ::"l"(nr));
@@ -262,6 +302,9 @@ k_softras_backward_lane(const SoftRasParams P, const FaceRec* __restrict__ recs,
         int texel;
         DivGuard guard;
         guard.ok = consts_ok;   // launch-constant denominators (sigma, gamma, far - near) validated once per thread
+        if (MERGE && fn < 0) {
+            texel = 0;   // idle lane: contributes nothing, only takes part in the shuffles below
+        } else
         if constexpr (!EXACT && B200R_BWD_OPTIMISTIC) {
             // all divisions branch-free; one range flag for the whole pair, one (cold) re-run if it dropped
             pair_gradient<DIST, RGB, false, true>(rec, fn, px, P, dc, nmf, r_nmf, s_nmf, btex + (size_t)fn * T * 3, gv, gt, texel, guard);
@@ -273,11 +316,26 @@ k_softras_backward_lane(const SoftRasParams P, const FaceRec* __restrict__ recs,
         } else {
             pair_gradient<DIST, RGB, EXACT, false>(rec, fn, px, P, dc, nmf, r_nmf, s_nmf, btex + (size_t)fn * T * 3, gv, gt, texel, guard);
         }
-        float4* a = reinterpret_cast<float4*>(bacc + (size_t)fn * 12);
-        atomicAdd(a + 0, make_float4(gv[0], gv[1], gv[2], gv[3]));
-        atomicAdd(a + 1, make_float4(gv[4], gv[5], gv[6], gv[7]));
-        atomicAdd(a + 2, make_float4(gv[8], tex_in_acc ? gt[0] : 0.f, tex_in_acc ? gt[1] : 0.f, tex_in_acc ? gt[2] : 0.f));
-        if (RGB != 2 && !tex_in_acc) {
+        int key = fn;
+        if (merge_ok) {
+            // neighbouring pixels mostly hold the same face in the same slot (52 % of horizontal neighbours at C3, 79 %
+            // at C2; ~4 / ~9 lanes per distinct face per step): the backward is bound by the L2's fp32 atomic rate
+            // (~250 G adds/s measured at C2, C3 and C5 alike), so every merged pair of lanes is time saved
+            merge_same_face<1, RGB>(key, gv, gt, lane);   // horizontal neighbour
+            merge_same_face<8, RGB>(key, gv, gt, lane);   // vertical neighbour
+#if B200R_BWD_MERGE >= 2
+            merge_same_face<2, RGB>(key, gv, gt, lane);
+            merge_same_face<16, RGB>(key, gv, gt, lane);
+#endif
+        }
+        if (key >= 0) {
+            float4* a = reinterpret_cast<float4*>(bacc + (size_t)key * 12);
+            atomicAdd(a + 0, make_float4(gv[0], gv[1], gv[2], gv[3]));
+            atomicAdd(a + 1, make_float4(gv[4], gv[5], gv[6], gv[7]));
+            if (RGB != 2)   // silhouettes: gv[8] (a z gradient) and the colour gradients are identically 0
+                atomicAdd(a + 2, make_float4(gv[8], tex_in_acc ? gt[0] : 0.f, tex_in_acc ? gt[1] : 0.f, tex_in_acc ? gt[2] : 0.f));
+        }
+        if (RGB != 2 && !tex_in_acc && fn >= 0) {
             if (P.tex_type == 0) {
 #pragma unroll
                 for (int k = 0; k < 3; k++) atomicAdd(bgt + ((size_t)fn * T + texel) * 3 + k, gt[k]);
