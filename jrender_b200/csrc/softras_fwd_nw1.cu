@@ -19,6 +19,11 @@ cudaError_t launch_v(const SoftRasParams& P, const SoftRasWorkspace& W, const fl
     if (cfg_smem.load() != smem) {
         cudaError_t e = cudaFuncSetAttribute(k_softras_forward<DIST, RGB, VARIANT, WX, WY, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
+        // The persistent grid is sized for the occupancy the FULL shared-memory carve-out allows.  Left to the driver's
+        // per-function heuristic the carve-out sometimes came out smaller: the same kernel then ran with fewer resident
+        // CTAs than the grid assumed and was 25-35 % slower for the lifetime of the process (seen on C2 / C5).
+        e = cudaFuncSetAttribute(k_softras_forward<DIST, RGB, VARIANT, WX, WY, EXACT>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
         int occ = 1;
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_softras_forward<DIST, RGB, VARIANT, WX, WY, EXACT>, NT, smem);
         if (e != cudaSuccess) return e;
