@@ -17,6 +17,7 @@ SURVEY.md F1) on this box's host cores on a bounded sample.
 """
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -141,10 +142,8 @@ def time_oracle(workload, target_s, nthreads=0, want_steps=1):
     # every core this process may run on; torchrun exports OMP_NUM_THREADS=1, which must not shrink the CPU baseline
     cores = nthreads if nthreads > 0 else len(os.sched_getaffinity(0))
     nthreads = cores
-    # Cost model t(n) = a + b*n for n sampled rows: a = per-image work that does not depend on the rows (face setup over all
-    # faces, output buffers, thread start-up, the backward's per-thread accumulators and their reduction), b = per-row work.
-    # Each step times n and 2n evenly spaced rows and reports a + b*H -- multiplying one sample by H/n would charge `a`
-    # H/n times, which on a 128-core box is most of the sample.
+    # One whole image is always timed first.  If that fits the per-step budget every step times a whole image; otherwise the
+    # steps time a row sample scaled by a factor calibrated against that whole image (see below).
     def run(stride):
         t0 = time.perf_counter()
         out = osr.forward(fv, tex, P, row_stride=stride, nthreads=nthreads)
@@ -153,23 +152,33 @@ def time_oracle(workload, target_s, nthreads=0, want_steps=1):
         return t1 - t0, time.perf_counter() - t1
 
     run(max(1, H // 4))                       # warm-up: page faults, OpenMP thread pool
-    f0, b0 = run(max(1, H // 8))
-    per_row = (f0 + b0) / max(1, len(range(0, H, max(1, H // 8))))   # upper bound (includes a)
-    rows = int(min(H // 2, max(4, target_s / 3.0 / max(per_row, 1e-9))))
-    s2 = max(1, H // (2 * rows))              # 2n rows
-    s1 = 2 * s2                               # n rows (a subset pattern of the same spacing family)
-    n1, n2 = len(range(0, H, s1)), len(range(0, H, s2))
+    f0, b0 = run(1)                           # one WHOLE image: the honest number, and the best size estimate
     times = []
+    if f0 + b0 <= target_s:                   # affordable per step: time whole images, no extrapolation at all
+        for _ in range(want_steps):
+            times.append(run(1))
+        return (H, H), H, cores, times
+    # Too slow to repeat per step: every step times a bounded sample of evenly spaced rows and is scaled by the factor
+    # calibrated ONCE against the whole image just measured (whole / sample), so the per-image fixed costs (face setup,
+    # buffers, the backward's per-thread accumulators) are counted once, as in a real frame, not H/n times.
+    stride = int(min(H // 8, max(2, math.ceil((f0 + b0) / max(target_s, 1e-3)))))
+    n1 = len(range(0, H, stride))
+    fs, bs = run(stride)
+    kf, kb = f0 / max(fs, 1e-9), b0 / max(bs, 1e-9)
     for _ in range(want_steps):
-        fa, ba = run(s1)
-        fb, bb = run(s2)
-        full = []
-        for ta, tb in ((fa, fb), (ba, bb)):
-            slope = max(0.0, (tb - ta) / max(1, n2 - n1))
-            icpt = max(0.0, tb - slope * n2)
-            full.append(icpt + slope * H)
-        times.append(tuple(full))
+        fa, ba = run(stride)
+        times.append((fa * kf, ba * kb))
+    n2 = H
     return (n1, n2), H, cores, times
+
+
+def cpu_sample_text(n_rows, H, nf, cores):
+    if n_rows[0] >= H:
+        what = "every step timed the WHOLE %dx%d image (%d faces), no extrapolation" % (H, H, nf)
+    else:
+        what = ("every step timed %d evenly spaced rows of one %dx%d image (%d faces), scaled by the whole-image / sample "
+                "ratio calibrated once on a whole image" % (n_rows[0], H, H, nf))
+    return "oracle fwd+bwd: %s; fwd and bwd OpenMP %d threads" % (what, cores)
 
 
 def cpu_frames_per_s(n_rows, H, times):
@@ -190,8 +199,7 @@ def run_reference(args, rank, world):
     timed = times[args.warmup:] if len(times) > args.warmup else times
     v = cpu_frames_per_s(n_rows, H, timed)
     nf, _, bpg, desc = WORKLOADS[args.workload]
-    sample = "fwd+bwd of %d and %d evenly spaced rows of one %dx%d image (%d faces), two-point fit a + b*rows evaluated at %d rows; fwd and bwd OpenMP %d threads" % (
-        n_rows[0], n_rows[1], H, H, nf, H, cores)
+    sample = cpu_sample_text(n_rows, H, nf, cores)
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup,
@@ -415,8 +423,7 @@ def run_ours(args, rank, world, local_rank):
         v = cpu_frames_per_s(n_rows, HH, times)
         line["cpu_baseline"] = {
             "value": v, "unit": "frames/s", "cores": cores, "kind": "port",
-            "sample": "oracle fwd+bwd on %d and %d evenly spaced rows of one %dx%d image (%d faces), two-point fit a + b*rows evaluated at %d rows; fwd and bwd OpenMP %d threads"
-                      % (n_rows[0], n_rows[1], HH, HH, nf, HH, cores)}
+            "sample": cpu_sample_text(n_rows, HH, nf, cores)}
     print(json.dumps(line), flush=True)
 
 
