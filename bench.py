@@ -391,6 +391,22 @@ def run_ours(args, rank, world, local_rank):
             traffic = json.load(f).get(args.workload, {}).get(dom)
     except OSError:
         pass
+    # Secondary, more telling figure for this SIMT-bound path: warp instructions per launch (from the committed ncu
+    # capture) over the measured kernel time, against the SM's issue ceiling (SMs x 4 schedulers x SM clock).
+    issue = None
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_traffic.json")) as f:
+            ninst = json.load(f).get(args.workload + "_warp_instructions", {}).get(dom)
+        if ninst and clocks and clocks.get("sm_mhz"):
+            import torch as _t
+            sms = _t.cuda.get_device_properties(dev).multi_processor_count
+            peak_i = sms * 4 * clocks["sm_mhz"] * 1e6
+            ach_i = ninst / (kern[dom]["avg_ms"] / 1000.0)
+            issue = {"kernel": dom, "warp_instructions_per_launch": int(ninst), "achieved_ginst_s": ach_i / 1e9,
+                     "peak_ginst_s": peak_i / 1e9, "frac": ach_i / peak_i,
+                     "note": "instruction count from the committed ncu capture (profiles/), time measured live"}
+    except Exception:
+        issue = None
     step_alg = bpg * (48 * P + 3 * (36 + 12 * T) * nf)
     line = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
@@ -416,6 +432,8 @@ def run_ours(args, rank, world, local_rank):
                           "achieved_gbs": step_alg / (total_ms / args.steps / 1000.0) / 1e9,
                           "frac": step_alg / (total_ms / args.steps / 1000.0) / 1e9 / peak},
     }
+    if issue is not None:
+        line["roofline_issue"] = issue
     if gather_ms is not None:
         line["allgather_images_ms"] = gather_ms
     if world == 1 and not args.no_cpu_baseline:
