@@ -69,6 +69,26 @@ class Var(np.ndarray):
             dims = tuple(dims)
         return np.asarray(np.asarray(self).sum(axis=dims, dtype=np.asarray(self).dtype)).view(Var)
 
+    def float64(self):
+        return np.asarray(self, dtype=np.float64).view(Var)
+
+    def long(self):
+        return np.asarray(self).astype(np.int64).view(Var)
+
+    def view(self, *shape):   # jittor's Var.view == reshape (shadows ndarray.view on purpose: reference code only)
+        if len(shape) == 1 and isinstance(shape[0], (tuple, list)):
+            shape = tuple(shape[0])
+        if len(shape) == 1 and isinstance(shape[0], type):   # ndarray.view(Var) used inside this stub
+            return np.ndarray.view(self, shape[0])
+        return np.reshape(np.asarray(self), shape).view(Var)
+
+    def reindex_reduce(self, op, shape, indexes, extras):
+        """Only the scatter-add pattern structures/mesh.py:241-244 uses: out[e0[i0], i1] += x[i0, i1]."""
+        assert op == "sum" and list(indexes) == ["@e0(i0)", "i1"] and len(extras) == 1
+        out = np.zeros(tuple(shape), np.asarray(self).dtype)
+        np.add.at(out, np.asarray(extras[0]).astype(np.int64), np.asarray(self))
+        return out.view(Var)
+
     def __getitem__(self, idx):
         if isinstance(idx, tuple):
             idx = tuple(np.asarray(i) if isinstance(i, Var) else i for i in idx)
@@ -93,13 +113,17 @@ def array(x, dtype=None):
 
 
 def normalize(x, p=2, dim=1, eps=1e-12):
-    a = np.asarray(x, dtype=np.float32)
-    n = np.sqrt((a * a).sum(axis=dim, keepdims=True, dtype=np.float32)).astype(np.float32)
-    return (a / np.maximum(n, np.float32(eps))).astype(np.float32).view(Var)
+    a = np.asarray(x)
+    dt = a.dtype if a.dtype == np.float64 else np.float32   # structures/mesh.py:219-221 normalises in float64
+    a = a.astype(dt)
+    n = np.sqrt((a * a).sum(axis=dim, keepdims=True, dtype=dt)).astype(dt)
+    return (a / np.maximum(n, dt.type(eps) if hasattr(dt, "type") else dt(eps))).astype(dt).view(Var)
 
 
 def cross(a, b, dim=-1):
-    return np.cross(np.asarray(a, np.float32), np.asarray(b, np.float32), axis=dim).astype(np.float32).view(Var)
+    a, b = np.asarray(a), np.asarray(b)
+    dt = np.float64 if a.dtype == np.float64 or b.dtype == np.float64 else np.float32
+    return np.cross(a.astype(dt), b.astype(dt), axis=dim).astype(dt).view(Var)
 
 
 def matmul(a, b):
@@ -126,6 +150,7 @@ def install():
     jt.sum = lambda a, dim=None: np.asarray(np.sum(np.asarray(a), axis=dim)).view(Var)
     jt.contrib = types.SimpleNamespace(concat=concat)
     jt.Var = Var
+    jt.arange = lambda n: np.arange(int(n), dtype=np.int32).view(Var)
     jt.zeros = lambda shape, dtype="float32": np.zeros(tuple(shape), dtype).view(Var)
     jt.ones = lambda shape, dtype="float32": np.ones(tuple(shape), dtype).view(Var)
     jt.ones_like = lambda a: np.ones_like(np.asarray(a)).view(Var)

@@ -41,3 +41,12 @@ def test_lighting_kernels_match_reference_python():
                                        torch.from_numpy(g["roughness"]))
         assert _close(d.numpy(), g["diffuse_" + tag], 5e-6), tag
         assert _close(s.numpy(), g["specular_" + tag], 5e-5), tag   # GGX ratio: (1 - cos)^5 and a2/denom^2 amplify ulps
+
+
+def test_mesh_normals_match_reference_python():
+    """Mesh.surface_normals (float64 cross, normalised, back to float32) and Mesh.vertex_normals (face normals
+    scatter-added to the vertices) against structures/mesh.py:213-248 executed through the stub."""
+    g = np.load(os.path.join(G, "ref_host_mesh_normals.npz"))
+    mesh = jr.Mesh(torch.from_numpy(g["vertices"]), torch.from_numpy(g["faces"]))
+    assert _close(mesh.surface_normals.numpy(), g["surface_normals"], 2e-6)
+    assert _close(mesh.vertex_normals.numpy(), g["vertex_normals"], 2e-6)
