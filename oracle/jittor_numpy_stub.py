@@ -72,6 +72,15 @@ class Var(np.ndarray):
     def float64(self):
         return np.asarray(self, dtype=np.float64).view(Var)
 
+    def float(self):
+        return self.float32()
+
+    def min(self, dim=None, **kw):   # jittor: x.min(0) reduces that axis
+        return np.asarray(np.asarray(self).min(axis=dim)).view(Var)
+
+    def max(self, dim=None, **kw):
+        return np.asarray(np.asarray(self).max(axis=dim)).view(Var)
+
     def long(self):
         return np.asarray(self).astype(np.int64).view(Var)
 
