@@ -75,6 +75,10 @@ class Var(np.ndarray):
     def float(self):
         return self.float32()
 
+    def sqr(self):
+        a = np.asarray(self)
+        return (a * a).view(Var)
+
     def min(self, dim=None, **kw):   # jittor: x.min(0) reduces that axis
         return np.asarray(np.asarray(self).min(axis=dim)).view(Var)
 
@@ -159,6 +163,9 @@ def install():
     jt.sum = lambda a, dim=None: np.asarray(np.sum(np.asarray(a), axis=dim)).view(Var)
     jt.contrib = types.SimpleNamespace(concat=concat)
     jt.Var = Var
+    jt.sqrt = lambda a: np.sqrt(np.asarray(a)).view(Var)
+    jt.cos = lambda a: np.cos(np.asarray(a)).astype(np.asarray(a).dtype).view(Var)
+    jt.sin = lambda a: np.sin(np.asarray(a)).astype(np.asarray(a).dtype).view(Var)
     jt.arange = lambda n: np.arange(int(n), dtype=np.int32).view(Var)
     jt.zeros = lambda shape, dtype="float32": np.zeros(tuple(shape), dtype).view(Var)
     jt.ones = lambda shape, dtype="float32": np.ones(tuple(shape), dtype).view(Var)

@@ -65,3 +65,14 @@ def test_obj_loader_matches_reference_python():
     assert np.array_equal(f1.numpy().astype(np.float32), g["faces_normalized_call"])
     v2, f2, t2 = jr.load_obj(fn, normalization=True, load_texture=True, texture_type='vertex')
     assert np.array_equal(t2.numpy(), g["vertex_textures"]) and _close(v2.numpy(), g["vertices_normalized"], 1e-6)
+
+
+def test_projection_camera_and_angle_points_match_reference_python():
+    """jr.projection (camera_mode='projection': R/t, radial + tangential distortion, K, pixel -> NDC) and the tensor
+    branch of jr.get_points_from_angles against transform/projection.py and utils/get_points_from_angles.py."""
+    g = np.load(os.path.join(G, "ref_host_camera_extras.npz"))
+    t = lambda k: torch.from_numpy(g[k])
+    out = jr.projection(t("vertices"), t("K"), t("R"), t("t"), t("dist_coeffs"), int(g["orig_size"]))
+    assert _close(out.numpy(), g["projected"], 5e-6)
+    pts = jr.get_points_from_angles(t("distance"), t("elevation"), t("azimuth"))
+    assert _close(pts.numpy(), g["points"], 2e-6)
