@@ -76,3 +76,14 @@ def test_projection_camera_and_angle_points_match_reference_python():
     assert _close(out.numpy(), g["projected"], 5e-6)
     pts = jr.get_points_from_angles(t("distance"), t("elevation"), t("azimuth"))
     assert _close(pts.numpy(), g["points"], 2e-6)
+
+
+def test_lighting_stage_matches_reference_python():
+    """jr.Lighting (surface mode: ambient + directional, Cook-Torrance branch and diffuse-only) applied to a jr.Mesh
+    against the reference's Lighting.execute (lighting/lighting.py:159-223) run through the stub on the same mesh."""
+    g = np.load(os.path.join(G, "ref_host_lighting_stage.npz"))
+    for tag, spec in (("specular", True), ("diffuse", False)):
+        mesh = jr.Mesh(torch.from_numpy(g["vertices"]), torch.from_numpy(g["faces"]), textures=torch.from_numpy(g["textures"].copy()))
+        mesh.with_specular = spec
+        out = jr.Lighting()(mesh, torch.from_numpy(g["eyes"]))
+        assert _close(out.textures.numpy(), g["lit_" + tag], 2e-5), tag
