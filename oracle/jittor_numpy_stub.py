@@ -75,6 +75,9 @@ class Var(np.ndarray):
     def float(self):
         return self.float32()
 
+    def clone(self):
+        return np.array(np.asarray(self), copy=True).view(Var)
+
     def sqr(self):
         a = np.asarray(self)
         return (a * a).view(Var)
@@ -169,6 +172,7 @@ def install():
     jt.arange = lambda n: np.arange(int(n), dtype=np.int32).view(Var)
     jt.zeros = lambda shape, dtype="float32": np.zeros(tuple(shape), dtype).view(Var)
     jt.ones = lambda shape, dtype="float32": np.ones(tuple(shape), dtype).view(Var)
+    jt.transpose = lambda a, axes: np.transpose(np.asarray(a), axes).view(Var)
     jt.ones_like = lambda a: np.ones_like(np.asarray(a)).view(Var)
     jt.clamp = lambda a, min_v=None, max_v=None: np.clip(np.asarray(a), min_v, max_v).view(Var)
     jt.pow = lambda a, e: np.power(np.asarray(a), np.float32(e)).astype(np.asarray(a).dtype).view(Var)
@@ -178,6 +182,18 @@ def install():
         def __call__(self, *a, **kw):
             return self.execute(*a, **kw)
     nn.Module = Module
+
+    def pool(x, kernel_size, op, stride=None):   # nn.pool(images, 2, "mean", stride=2) of dr/softras/rasterizer.py:55
+        assert op == "mean" and kernel_size == 2 and stride in (2, None)
+        a = np.asarray(x)
+        b_, c_, h_, w_ = a.shape
+        return a.reshape(b_, c_, h_ // 2, 2, w_ // 2, 2).mean(axis=(3, 5), dtype=a.dtype).view(Var)
+    nn.pool = pool
+
+    class Function(object):   # jittor.Function: calling the object runs execute()
+        def __call__(self, *a, **kw):
+            return self.execute(*a, **kw)
+    jt.Function = Function
     nn.relu = lambda a: np.maximum(np.asarray(a), 0).view(Var)
     jt.nn = nn
     saved = {k: sys.modules.get(k) for k in ("jittor", "jittor.nn")}

@@ -87,3 +87,57 @@ def test_lighting_stage_matches_reference_python():
         mesh.with_specular = spec
         out = jr.Lighting()(mesh, torch.from_numpy(g["eyes"]))
         assert _close(out.textures.numpy(), g["lit_" + tag], 2e-5), tag
+
+
+def test_softras_host_logic_matches_reference_python(monkeypatch):
+    """Rows a1 / a2 of the scope table on CPU: the scalar arguments SoftRasterizeFunction hands to the kernel (enum maps,
+    dist_eps logit, K, fill_back) and SoftRasterizer's anti-aliasing pool + mode slicing, against the reference's
+    dr/softras/{soft_rasterize,rasterizer}.py executed through the stub with the CPU oracle standing in for the CUDA op
+    (the same substitution is made here for jrender_b200's op, which has no CPU path)."""
+    import json
+    import types
+    from jrender_b200 import softras as jsr
+    from oracle import softras as osr
+    g = np.load(os.path.join(G, "ref_host_softras_logic.npz"))
+    meta = json.loads(bytes(g["meta_json"]).decode())
+    fv, tex = g["face_vertices"], g["textures"]
+
+    def oracle_soft_rasterize(face_vertices, textures, image_size, background_color, near, far, fill_back, eps, sigma_val,
+                              dist_func, dist_eps, gamma_val, aggr_func_rgb, aggr_func_alpha, texture_type, bin_size,
+                              max_elems_per_bin, max_faces_per_pixel_for_grad):
+        P = osr.Params(image_size=image_size, near=near, far=far, fill_back=fill_back, eps=eps, sigma_val=sigma_val,
+                       dist_func=dist_func, dist_eps=dist_eps, gamma_val=gamma_val, aggr_func_rgb=aggr_func_rgb,
+                       aggr_func_alpha=aggr_func_alpha, texture_type=texture_type,
+                       max_faces_per_pixel_for_grad=max_faces_per_pixel_for_grad)
+        return torch.from_numpy(osr.forward(face_vertices.numpy(), textures.numpy(), P)["soft_colors"])
+    seen = []
+    real_fn = jsr.SoftRasterizeFunction
+
+    def recording_soft_rasterize(face_vertices, textures, image_size, background_color, near, far, fill_back, eps, sigma_val,
+                                 dist_func, dist_eps, gamma_val, aggr_func_rgb, aggr_func_alpha, texture_type, bin_size,
+                                 max_elems_per_bin, max_faces_per_pixel_for_grad):
+        # what jrender_b200.softras.soft_rasterize does (softras.py), minus the CUDA call: build the Function, pack scalars
+        fn = real_fn(image_size, background_color, near, far, fill_back, eps, sigma_val, dist_func, dist_eps, gamma_val,
+                     aggr_func_rgb, aggr_func_alpha, texture_type, bin_size, max_elems_per_bin, max_faces_per_pixel_for_grad)
+        seen.append(fn._scalars(face_vertices.shape[0], face_vertices.shape[1], textures.shape[2]))
+        return oracle_soft_rasterize(face_vertices, textures, image_size, background_color, near, far, fill_back, eps,
+                                     sigma_val, dist_func, dist_eps, gamma_val, aggr_func_rgb, aggr_func_alpha, texture_type,
+                                     bin_size, max_elems_per_bin, max_faces_per_pixel_for_grad)
+    monkeypatch.setattr(jsr, "soft_rasterize", recording_soft_rasterize)
+    for name, m in meta.items():
+        kw, ks = m["kwargs"], m["kernel_scalars"]
+        r = jsr.SoftRasterizer(**kw)
+        mesh = types.SimpleNamespace(face_vertices=torch.from_numpy(fv), face_textures=torch.from_numpy(tex))
+        seen.clear()
+        alpha, rgb = r(mesh, None)
+        sc = seen[0]
+        got = dict(image_size=sc[3], K=sc[4], near=sc[5], far=sc[6], eps=sc[7], sigma_val=sc[8], gamma_val=sc[9], dist_eps=sc[10],
+                   func_dist_type=sc[11], func_rgb_type=sc[12], func_alpha_type=sc[13], texture_type=sc[14], fill_back=sc[15])
+        for k, v in got.items():
+            ref = ks[k]
+            if isinstance(v, float):
+                assert np.float32(v) == np.float32(ref), (name, k, v, ref)   # the kernel takes these as float
+            else:
+                assert v == ref, (name, k, v, ref)
+        assert _close(alpha.numpy(), g[name + "_alpha"], 1e-6) and _close(rgb.numpy(), g[name + "_rgb"], 1e-6), name
+        assert torch.equal(r(mesh, "rgb"), rgb)
