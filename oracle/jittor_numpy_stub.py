@@ -75,6 +75,12 @@ class Var(np.ndarray):
     def float(self):
         return self.float32()
 
+    def permute(self, *axes):
+        return self.transpose(*axes)
+
+    def sync(self):
+        return self
+
     def clone(self):
         return np.array(np.asarray(self), copy=True).view(Var)
 
@@ -170,8 +176,10 @@ def install():
     jt.cos = lambda a: np.cos(np.asarray(a)).astype(np.asarray(a).dtype).view(Var)
     jt.sin = lambda a: np.sin(np.asarray(a)).astype(np.asarray(a).dtype).view(Var)
     jt.arange = lambda n: np.arange(int(n), dtype=np.int32).view(Var)
-    jt.zeros = lambda shape, dtype="float32": np.zeros(tuple(shape), dtype).view(Var)
-    jt.ones = lambda shape, dtype="float32": np.ones(tuple(shape), dtype).view(Var)
+    _shape = lambda sh: (sh,) if isinstance(sh, int) else tuple(sh)
+    jt.zeros = lambda shape, dtype="float32": np.zeros(_shape(shape), dtype).view(Var)
+    jt.ones = lambda shape, dtype="float32": np.ones(_shape(shape), dtype).view(Var)
+    jt.empty = lambda shape, dtype="float32": np.zeros(_shape(shape), dtype).view(Var)
     jt.transpose = lambda a, axes: np.transpose(np.asarray(a), axes).view(Var)
     jt.ones_like = lambda a: np.ones_like(np.asarray(a)).view(Var)
     jt.clamp = lambda a, min_v=None, max_v=None: np.clip(np.asarray(a), min_v, max_v).view(Var)

@@ -141,3 +141,49 @@ def test_softras_host_logic_matches_reference_python(monkeypatch):
                 assert v == ref, (name, k, v, ref)
         assert _close(alpha.numpy(), g[name + "_alpha"], 1e-6) and _close(rgb.numpy(), g[name + "_rgb"], 1e-6), name
         assert torch.equal(r(mesh, "rgb"), rgb)
+
+
+def test_nmr_host_logic_matches_reference_python(monkeypatch):
+    """Rows a8 / a9 on CPU: N3mrRasterizer (fill_back concat + texture permutation + gather) and rasterize_rgbad (background
+    mix, alpha, NHWC -> NCHW, vertical flip, 2x2 mean pool, the alpha/depth channel dim the reference keeps under AA)
+    against dr/n3mr/{n3mr,rasterizer}.py executed through the stub with the CPU oracle's kernels standing in for the two
+    forward CUDA ops (the same substitution is made here for jrender_b200's op)."""
+    import json
+    import types
+    from jrender_b200 import n3mr as jn
+    from oracle import nmr as onmr
+    g = np.load(os.path.join(G, "ref_host_nmr_logic.npz"))
+    meta = json.loads(bytes(g["meta_json"]).decode())
+    seen = []
+
+    class OracleOp(object):
+        @staticmethod
+        def apply(faces, textures, fn):
+            seen.append(dict(image_size=int(fn.image_size), near=float(fn.near), far=float(fn.far), eps=float(fn.eps),
+                             flags=[int(bool(fn.return_rgb)), int(bool(fn.return_alpha)), int(bool(fn.return_depth))],
+                             nf=int(faces.shape[1])))
+            out = onmr.forward(faces.numpy(), textures.numpy() if fn.return_rgb else None, fn.image_size, fn.near, fn.far, fn.eps,
+                               fn.background_color if fn.background_color is not None else (0, 0, 0), fn.return_rgb,
+                               fn.return_alpha, fn.return_depth)
+            e = torch.empty(0)
+            return (torch.from_numpy(out["rgb_map"]) if fn.return_rgb else e,
+                    torch.from_numpy(out["alpha_map"]) if fn.return_alpha else e,
+                    torch.from_numpy(out["depth_map"]) if fn.return_depth else e)
+    monkeypatch.setattr(jn, "_RasterizeOp", OracleOp)
+    for name, m in meta.items():
+        kw, kc = m["kwargs"], m["kernel_call"]
+        r = jn.N3mrRasterizer(**kw)
+        mesh = types.SimpleNamespace(vertices=torch.from_numpy(g["vertices"]), faces=torch.from_numpy(g["faces"]),
+                                     textures=torch.from_numpy(g["textures"]))
+        seen.clear()
+        rgb, depth, alpha = r(mesh, None)
+        for k in ("image_size", "nf", "flags"):
+            assert seen[0][k] == kc[k], (name, k, seen[0][k], kc[k])
+        for k in ("near", "far", "eps"):
+            assert np.float32(seen[0][k]) == np.float32(kc[k]), (name, k)
+        for got, key in ((rgb, "_rgb"), (depth, "_depth"), (alpha, "_alpha")):
+            ref = g[name + key]
+            assert tuple(got.shape) == ref.shape, (name, key, tuple(got.shape), ref.shape)
+            assert _close(got.numpy(), ref, 1e-6), (name, key)
+        sil = r(mesh, "silhouettes")
+        assert tuple(sil.shape) == g[name + "_silhouettes"].shape and _close(sil.numpy(), g[name + "_silhouettes"], 1e-6), name
