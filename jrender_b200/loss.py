@@ -81,7 +81,7 @@ class LaplacianLoss(nn.Module):
 
     def forward(self, x):
         batch_size = x.shape[0]
-        if self.fused and _fusable(x) and x.shape[1] == self.nv:
+        if self.fused and _fusable(x) and x.shape[1] == self.nv and self.nbr32.device == x.device:
             L = _lib.lib()
             maxdeg = self.nbr_w.shape[1]
 
@@ -107,11 +107,16 @@ class FlattenLoss(nn.Module):
         self.nf = faces.shape[0]
         self.average = average
         f = faces.detach().cpu().numpy().astype(np.int64)
+        self.nv_min = int(f.max()) + 1 if f.size else 0   # smallest vertex count the edge table is valid for
         opp = {}
         for tri in f:
             for a, b_, c in ((tri[0], tri[1], tri[2]), (tri[1], tri[2], tri[0]), (tri[2], tri[0], tri[1])):
                 opp.setdefault((min(a, b_), max(a, b_)), []).append(c)
-        edges = sorted(k for k, v in opp.items() if len(v) >= 2)   # the reference assumes a closed manifold
+        # flatten_loss.py:13 takes the edge set from columns (0,1) and (1,2) of every face ONLY: an edge that is the
+        # (v2, v0) edge of both of its faces carries no dihedral term in the reference, so it carries none here.
+        # v2 / v3 = third vertex of the first / second face (in face order) containing the edge (:19-30).
+        listed = set((min(a, b_), max(a, b_)) for a, b_ in np.concatenate((f[:, 0:2], f[:, 1:3]), axis=0))
+        edges = sorted(k for k in listed if len(opp[k]) >= 2)      # the reference assumes a closed manifold
         v0s = np.array([e[0] for e in edges], np.int64)
         v1s = np.array([e[1] for e in edges], np.int64)
         v2s = np.array([opp[e][0] for e in edges], np.int64)
@@ -124,7 +129,10 @@ class FlattenLoss(nn.Module):
 
     def forward(self, vertices, eps=1e-6):
         batch_size = vertices.shape[0]
-        if self.fused and _fusable(vertices):
+        # the kernel dereferences the module's index buffers and indexes vertices with them: they must live on the
+        # input's device and the mesh must have every vertex the table names; anything else takes the index_select
+        # path below, which raises torch's own device-mismatch / index-out-of-range errors
+        if self.fused and _fusable(vertices) and self.e32.device == vertices.device and vertices.shape[1] >= self.nv_min:
             L = _lib.lib()
             E = int(self.v0s.shape[0])
 

@@ -205,6 +205,8 @@ extern "C" int ref_nmr_forward_face_index_map(const float* faces, float* faces_i
         case 48: dispatch_flags<48>(flags, faces, faces_inv, face_index_map, weight_map, depth_map, face_inv_map, B, nf, near_, far_, nbits, lock); break;
         case 64: dispatch_flags<64>(flags, faces, faces_inv, face_index_map, weight_map, depth_map, face_inv_map, B, nf, near_, far_, nbits, lock); break;
         case 256: dispatch_flags<256>(flags, faces, faces_inv, face_index_map, weight_map, depth_map, face_inv_map, B, nf, near_, far_, nbits, lock); break;
+        case 512: dispatch_flags<512>(flags, faces, faces_inv, face_index_map, weight_map, depth_map, face_inv_map, B, nf, near_, far_, nbits, lock); break;
+        case 1024: dispatch_flags<1024>(flags, faces, faces_inv, face_index_map, weight_map, depth_map, face_inv_map, B, nf, near_, far_, nbits, lock); break;
         default: return -1;  // image size not instantiated
     }
     cudaError_t e = cudaDeviceSynchronize();

@@ -145,7 +145,7 @@ def nmr_run(faces, textures, image_size, near=0.1, far=100.0, eps=1e-4, backgrou
     rc = L.ref_nmr_forward_face_index_map(p(fc), p(faces_inv), p(fim), p(wm), p(dm), p(finv), p(lock), B, nf, H,
                                           float(near), float(far), int(rrgb), int(ralpha), int(rdepth), finv.numel())
     if rc != 0:
-        raise RuntimeError("reference forward_face_index_map failed: %d (image sizes instantiated: 32, 48, 64, 256)" % rc)
+        raise RuntimeError("reference forward_face_index_map failed: %d (image sizes instantiated: 32, 48, 64, 256, 512, 1024)" % rc)
     out = dict(face_index_map=fim, weight_map=wm, depth_map=dm)
     if rdepth:
         out["face_inv_map"] = finv

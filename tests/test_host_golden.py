@@ -26,8 +26,26 @@ def test_losses_match_reference_python():
     assert lap.shape == g["laplacian"].shape and _close(lap, g["laplacian"], 2e-5)   # (L x)^2 summed over 142 x 3 terms
     flat = jr.FlattenLoss(f)(v).numpy()
     assert flat.shape == g["flatten"].shape and _close(flat, g["flatten"], 2e-5)
+    # rotated per-face index order: the reference lists only the (v0,v1) and (v1,v2) edges of each face, so some
+    # edges of this mesh carry no dihedral term (flatten_loss.py:13); the mirror must drop exactly the same ones
+    fr = torch.from_numpy(g["faces_rot"])
+    lr = jr.FlattenLoss(fr)
+    assert int(lr.v0s.shape[0]) < int(jr.FlattenLoss(f).v0s.shape[0])
+    assert _close(lr(v).numpy(), g["flatten_rot"], 2e-5)
     iou = float(jr.neg_iou_loss(torch.from_numpy(g["iou_predict"]), torch.from_numpy(g["iou_target"])))
     assert abs(iou - float(g["neg_iou"])) <= 1e-6
+
+
+def test_mesh_loss_oracle_matches_reference_python():
+    """oracle/mesh_loss.py (float64 restatement + numeric gradients, the independent checker of the fused loss
+    kernels' gradients) is pinned to the reference's own Python values, rotated-face-order fixture included."""
+    from oracle import mesh_loss as oml
+    g = np.load(os.path.join(G, "ref_host_loss_sphere280.npz"))
+    v = g["vertices"]
+    assert _close(oml.laplacian(v, oml.laplacian_matrix(v.shape[1], g["faces"])), g["laplacian"], 2e-5)
+    assert _close(oml.flatten(v, oml.flatten_edges(g["faces"])), g["flatten"], 2e-5)
+    e = oml.flatten_edges(g["faces_rot"])
+    assert len(e[0]) == len(e[3]) and _close(oml.flatten(v, e), g["flatten_rot"], 2e-5)
 
 
 def test_lighting_kernels_match_reference_python():

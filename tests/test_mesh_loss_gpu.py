@@ -43,6 +43,48 @@ def test_fused_losses_match_mirror_and_golden(which, cuda_device):
     assert np.abs(out[True][1] - out[False][1]).max() <= GRAD_TOL * np.abs(out[False][1]).max()
 
 
+@pytest.mark.parametrize("which", ["laplacian", "flatten", "flatten_rot"])
+def test_fused_loss_gradients_against_numeric_oracle(which, cuda_device):
+    """Gradients of the fused kernels against oracle/mesh_loss.py: float64 restatement of the reference's expressions,
+    differentiated by central differences (independent of the PyTorch mirror and of any autograd)."""
+    from oracle import mesh_loss as oml
+    g = np.load(os.path.join(G, "ref_host_loss_sphere280.npz"))
+    vb = g["vertices"]
+    faces = g["faces_rot"] if which == "flatten_rot" else g["faces"]
+    f = torch.from_numpy(faces)
+    if which == "laplacian":
+        mod = jr.LaplacianLoss(torch.from_numpy(vb[0]), f)
+        lap = oml.laplacian_matrix(vb.shape[1], faces)
+        fn = lambda x: oml.laplacian(x, lap)                      # noqa: E731
+    else:
+        mod = jr.FlattenLoss(f)
+        edges = oml.flatten_edges(faces)
+        fn = lambda x: oml.flatten(x, edges)                      # noqa: E731
+    mod = mod.to(cuda_device)
+    v = torch.from_numpy(vb).to(cuda_device).requires_grad_(True)
+    val = mod(v)
+    w = np.linspace(0.5, 1.5, val.numel())
+    (val * torch.from_numpy(w.astype(np.float32)).to(cuda_device)).sum().backward()
+    ref_val = fn(vb)
+    ref_grad = oml.numeric_grad(fn, vb, w)
+    assert np.abs(val.detach().cpu().numpy() - ref_val).max() <= VAL_TOL * np.abs(ref_val).max()
+    assert np.abs(v.grad.cpu().numpy() - ref_grad).max() <= GRAD_TOL * np.abs(ref_grad).max()
+
+
+def test_fused_loss_buffers_on_another_device_do_not_reach_the_kernel(cuda_device):
+    """A loss module left on the CPU with CUDA vertices must raise torch's device error, never hand host pointers to
+    the kernel; a mesh smaller than the edge table must raise an index error, never read out of bounds."""
+    g = np.load(os.path.join(G, "ref_host_loss_sphere280.npz"))
+    f = torch.from_numpy(g["faces"])
+    v = torch.from_numpy(g["vertices"]).to(cuda_device)
+    for mod in (jr.LaplacianLoss(torch.from_numpy(g["vertices"][0]), f), jr.FlattenLoss(f)):   # buffers stay on the CPU
+        with pytest.raises(RuntimeError):
+            mod(v)
+    with pytest.raises((RuntimeError, IndexError)):
+        jr.FlattenLoss(f).to(cuda_device)(v[:, :100].contiguous())
+    torch.cuda.synchronize()
+
+
 def test_fused_losses_large_mesh_average_and_graph(cuda_device):
     v, f = wl.sphere_by_faces(3280)
     rng = np.random.default_rng(9)
