@@ -52,6 +52,7 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-reference-gpu", action="store_true", help="skip the reference-CUDA-kernels-on-this-GPU leg")
     ap.add_argument("--option", action="append", default=[], metavar="NAME=VALUE",
                     help="b200r_set_option() knob for A/B runs, e.g. --option nmr_bwd_unroll=2")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU-baseline sample time")
@@ -129,85 +130,80 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-# --------------------------------------------------------------------------- CPU oracle timing
-def time_oracle(workload, target_s, nthreads=0, want_steps=1):
-    """Times the CPU oracle (oracle/softras_oracle.c) on evenly spaced rows of ONE image of the
-    workload and extrapolates to frames/s.  Returns (frames_per_s, info dict, per-step times)."""
-    from oracle import softras as osr
-    from jrender_b200 import workloads as wl
+# --------------------------------------------------------------------------- baselines (subprocesses)
+def workload_config(workload, world):
+    """The `config` object, identical in both arms (the driver compares them key by key)."""
+    nf, H, bpg, desc = WORKLOADS[workload]
+    return {"workload": desc, "images_per_gpu": bpg, "global_batch": bpg * world, "faces": nf, "image_size": H,
+            "params": "T=1 sigma=1e-5 gamma=1e-4 euclidean/softmax/prod K=16 near=1 far=100 fill_back",
+            "parallelism": "batch-sharded dp%d, no data-path collective" % world,
+            "l2": "256 MiB buffer written between timed steps (outside the event pairs)",
+            "baseline_note": "vs_baseline = value / (1000/35.5 ms): README.md:69, GPU and batch unstated"}
+
+
+def _run_json(cmd, timeout):
+    """Runs a baseline helper under oracle/ as a subprocess and parses the JSON object it prints."""
+    env = dict(os.environ)
+    for k in ("OMP_NUM_THREADS", "OMP_PROC_BIND", "OMP_PLACES"):   # torchrun exports OMP_NUM_THREADS=1
+        env.pop(k, None)
+    try:
+        r = subprocess.run([sys.executable] + cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=timeout)
+        for line in reversed(r.stdout.strip().splitlines()):
+            if line.startswith("{"):
+                return json.loads(line)
+        return {"unavailable": "no JSON from %s (rc %d): %s" % (cmd[0], r.returncode, r.stderr.strip()[-300:])}
+    except Exception as e:
+        return {"unavailable": "%s: %s" % (type(e).__name__, e)}
+
+
+def cpu_oracle(workload, step_seconds, steps=1, warmup=0, one_thread_seconds=4.0):
+    """CPU oracle fwd+bwd on this box's host cores, pinned one thread per physical core (oracle/cpu_bench.py)."""
     nf, H, _, _ = WORKLOADS[workload]
-    fv, tex = wl.make_scene(nf, batch=1)
-    P = osr.Params(image_size=H)
-    g = np.random.default_rng(2).uniform(-1.0, 1.0, (1, 4, H, H)).astype(np.float32)
-    # every core this process may run on; torchrun exports OMP_NUM_THREADS=1, which must not shrink the CPU baseline
-    cores = nthreads if nthreads > 0 else len(os.sched_getaffinity(0))
-    nthreads = cores
-    # One whole image is always timed first.  If that fits the per-step budget every step times a whole image; otherwise the
-    # steps time a row sample scaled by a factor calibrated against that whole image (see below).
-    def run(stride):
-        t0 = time.perf_counter()
-        out = osr.forward(fv, tex, P, row_stride=stride, nthreads=nthreads)
-        t1 = time.perf_counter()
-        osr.backward(fv, tex, out, g, P, row_stride=stride, nthreads=cores)
-        return t1 - t0, time.perf_counter() - t1
-
-    run(max(1, H // 4))                       # warm-up: page faults, OpenMP thread pool
-    f0, b0 = run(1)                           # one WHOLE image: the honest number, and the best size estimate
-    times = []
-    if f0 + b0 <= target_s:                   # affordable per step: time whole images, no extrapolation at all
-        for _ in range(want_steps):
-            times.append(run(1))
-        return (H, H), H, cores, times
-    # Too slow to repeat per step: every step times a bounded sample of evenly spaced rows and is scaled by the factor
-    # calibrated ONCE against the whole image just measured (whole / sample), so the per-image fixed costs (face setup,
-    # buffers, the backward's per-thread accumulators) are counted once, as in a real frame, not H/n times.
-    stride = int(min(H // 8, max(2, math.ceil((f0 + b0) / max(target_s, 1e-3)))))
-    n1 = len(range(0, H, stride))
-    fs, bs = run(stride)
-    kf, kb = f0 / max(fs, 1e-9), b0 / max(bs, 1e-9)
-    for _ in range(want_steps):
-        fa, ba = run(stride)
-        times.append((fa * kf, ba * kb))
-    n2 = H
-    return (n1, n2), H, cores, times
+    budget = 120 + (steps + warmup + 3) * max(step_seconds, 40.0)
+    return _run_json([os.path.join("oracle", "cpu_bench.py"), "--faces", str(nf), "--image-size", str(H), "--steps", str(steps),
+                      "--warmup", str(warmup), "--step-seconds", str(step_seconds), "--one-thread-seconds", str(one_thread_seconds)],
+                     timeout=budget)
 
 
-def cpu_sample_text(n_rows, H, nf, cores):
-    if n_rows[0] >= H:
-        what = "every step timed the WHOLE %dx%d image (%d faces), no extrapolation" % (H, H, nf)
-    else:
-        what = ("every step timed %d evenly spaced rows of one %dx%d image (%d faces), scaled by the whole-image / sample "
-                "ratio calibrated once on a whole image" % (n_rows[0], H, H, nf))
-    return "oracle fwd+bwd: %s; fwd and bwd OpenMP %d threads" % (what, cores)
-
-
-def cpu_frames_per_s(n_rows, H, times):
-    """times = per-step (forward, backward) seconds already extrapolated to a full image by time_oracle."""
-    return 1.0 / float(np.mean([a + b for a, b in times]))
+def cpu_baseline_object(r):
+    if "unavailable" in r:
+        return {"value": None, "unit": "frames/s", "cores": 0, "kind": "port", "sample": r["unavailable"]}
+    o = {"value": r["frames_per_s"], "unit": "frames/s", "cores": r["threads"], "kind": "port",
+         "sample": "oracle fwd+bwd: %s; %d OpenMP threads (%s)" % (r["sample"], r["threads"], r["binding"]),
+         "cpu_model": r["cpu_model"], "logical_cpus": r["logical_cpus_in_mask"], "fwd_s_per_image": r["fwd_s"], "bwd_s_per_image": r["bwd_s"]}
+    if "one_thread" in r:
+        o["one_thread_value"] = r["one_thread"]["frames_per_s"]
+        o["one_thread_note"] = r["one_thread"]["note"]
+    return o
 
 
 # --------------------------------------------------------------------------- reference arm
 def run_reference(args, rank, world):
     """The reference has no CPU implementation (every op is CUDA-only) and Jittor is
     not installable here, so this arm times the CPU restatement of the reference kernels
-    (oracle/, kind "port") with all host threads on rank 0."""
+    (oracle/, kind "port") on rank 0, one OpenMP thread per physical core.  One STEP = forward + backward of ONE
+    image of the workload (a bounded sample when a whole image does not fit the per-step budget); `value` is
+    images/s, `ms_per_step` the wall time each step actually took."""
     if rank != 0:
         return
     total_steps = args.steps + args.warmup
     target = max(0.5, min(15.0, 150.0 / max(1, total_steps)))
-    n_rows, H, cores, times = time_oracle(args.workload, target, want_steps=total_steps)
-    timed = times[args.warmup:] if len(times) > args.warmup else times
-    v = cpu_frames_per_s(n_rows, H, timed)
-    nf, _, bpg, desc = WORKLOADS[args.workload]
-    sample = cpu_sample_text(n_rows, H, nf, cores)
+    r = cpu_oracle(args.workload, target, steps=args.steps, warmup=args.warmup, one_thread_seconds=0.0)
+    if "unavailable" in r:
+        print(json.dumps({"impl": "reference", "unavailable": r["unavailable"]}), flush=True)
+        return
+    v = r["frames_per_s"]
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1000.0 * bpg * args.gpus / v, "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": 1000.0 * float(np.mean(r["step_wall_s"])), "frames_per_step": 1,
+        "higher_is_better": True, "scaling": "weak",
         "vs_baseline": v / (1000.0 / README_39K_MS) if args.workload == "c3" else None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": desc, "note": "CPU restatement of the reference CUDA kernels; the reference ships no CPU path"},
-        "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": workload_config(args.workload, args.gpus),
+        "note": "CPU restatement of the reference CUDA kernels (the reference ships no CPU path); one step = one image "
+                "(or a bounded row sample of it); value = 1 / extrapolated seconds per whole image",
+        "cpu_baseline": cpu_baseline_object(r),
         "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -356,6 +352,42 @@ def run_ours(args, rank, world, local_rank):
     h2d = fv_h.nbytes + tex_h.nbytes
     d2h = fv_h.nbytes + tex_h.nbytes + 4
 
+    # ---- render workload end to end (demo1-style: the caller wants the IMAGES): pinned host inputs -> H2D -> forward
+    # only (no autograd graph) -> D2H of soft_colors [bpg,4,H,H] into pinned memory, every step, same stream pipeline
+    img_p = [torch.empty((bpg, 4, H, H), dtype=torch.float32).pin_memory() for _ in range(2)]
+
+    def render_run(n):
+        for i in range(n):
+            k = i & 1
+            with torch.cuda.stream(s_in):
+                if i >= 2:
+                    s_in.wait_event(ev_free[k])
+                d_fv[k].copy_(fv_p, non_blocking=True)
+                d_tex[k].copy_(tex_p, non_blocking=True)
+                ev_in[k].record(s_in)
+            s_main.wait_event(ev_in[k])
+            with torch.no_grad():
+                img = SoftRasterizeFunction(image_size=H)(d_fv[k], d_tex[k])
+            ev_free[k].record(s_main)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_free[k])
+                img.record_stream(s_out)
+                img_p[k].copy_(img, non_blocking=True)
+        s_out.synchronize()
+        s_main.synchronize()
+
+    render_run(3)
+    barrier()
+    t0 = time.perf_counter()
+    render_run(e2e_steps)
+    t_r = torch.tensor([(time.perf_counter() - t0) * 1000.0], dtype=torch.float64, device=dev)
+    barrier()
+    if world > 1:
+        dist.all_reduce(t_r, op=dist.ReduceOp.MAX)
+    e2e_render = {"value": bpg * world * e2e_steps / (float(t_r.item()) / 1000.0), "unit": "frames/s",
+                  "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(bpg * 4 * H * H * 4),
+                  "what": "forward only: pinned host inputs -> H2D -> rasterize -> D2H of the RGBA images; host wall clock"}
+
     # ---- optional all-gather of the output images, reported separately
     gather_ms = None
     if world > 1:
@@ -413,11 +445,7 @@ def run_ours(args, rank, world, local_rank):
         "warmup": warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": value / (1000.0 / README_39K_MS) if args.workload == "c3" else None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": desc, "images_per_gpu": bpg, "global_batch": bpg * world, "faces": nf, "image_size": H,
-                   "params": "T=1 sigma=1e-5 gamma=1e-4 euclidean/softmax/prod K=16 near=1 far=100 fill_back",
-                   "parallelism": "batch-sharded dp%d, no data-path collective" % world,
-                   "l2": "256 MiB buffer written between timed steps (outside the event pairs)",
-                   "baseline_note": "vs_baseline = value / (1000/35.5 ms): README.md:69, GPU and batch unstated"},
+        "config": workload_config(args.workload, world),
         "step_ms": {"min": float(np.min(step_ms)), "median": float(np.median(step_ms)), "max": float(np.max(step_ms))},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
@@ -436,12 +464,14 @@ def run_ours(args, rank, world, local_rank):
         line["roofline_issue"] = issue
     if gather_ms is not None:
         line["allgather_images_ms"] = gather_ms
+    line["e2e_render"] = e2e_render
     if world == 1 and not args.no_cpu_baseline:
-        n_rows, HH, cores, times = time_oracle(args.workload, args.cpu_seconds, want_steps=1)
-        v = cpu_frames_per_s(n_rows, HH, times)
-        line["cpu_baseline"] = {
-            "value": v, "unit": "frames/s", "cores": cores, "kind": "port",
-            "sample": cpu_sample_text(n_rows, HH, nf, cores)}
+        # baselines run AFTER every timed region, in subprocesses: this process never imports oracle/
+        torch.cuda.empty_cache()
+        line["cpu_baseline"] = cpu_baseline_object(cpu_oracle(args.workload, args.cpu_seconds, steps=1))
+        if not args.no_reference_gpu:
+            line["reference_gpu"] = _run_json([os.path.join("oracle", "ref_gpu_bench.py"), "--kind", "softras", "--faces", str(nf),
+                                               "--image-size", str(H), "--batch", str(bpg)], timeout=300)
     print(json.dumps(line), flush=True)
 
 
@@ -451,14 +481,13 @@ def run_nmr(args, rank, world, local_rank):
     import torch
     from jrender_b200 import _lib
     from jrender_b200.n3mr import RasterizeFunction
-    from tests.util import nmr_scene
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     L = _lib.lib()
     nf, H, bpg, desc = WORKLOADS[args.workload]
-    faces_h, tex_h = nmr_scene(nf, batch=1, ts=2)
-    # one mesh, bpg cameras: rotate the azimuth per image like build_inputs does for SoftRas
     from jrender_b200 import workloads as wl
+    faces_h, tex_h = wl.nmr_scene(nf, batch=1, ts=2)
+    # one mesh, bpg cameras: rotate the azimuth per image like build_inputs does for SoftRas
     v, f = wl.sphere_by_faces(nf)
     eyes = np.asarray([wl.get_points_from_angles(2.732, 30.0, 360.0 * (rank * bpg + b) / (bpg * world)) for b in range(bpg)], np.float32)
     cam = wl.perspective(wl.look_at(np.repeat(v[None], bpg, 0), eyes), 30.0)
@@ -502,13 +531,18 @@ def run_nmr(args, rank, world, local_rank):
     alg = bpg * (36 * P + 2 * (36 + 12 * ts ** 3) * nf2)
     peak, src = peaks()
     tot = float(np.sum(ms))
+    ref_gpu = None
+    if world == 1 and not args.no_reference_gpu:
+        torch.cuda.empty_cache()
+        ref_gpu = _run_json([os.path.join("oracle", "ref_gpu_bench.py"), "--kind", "nmr", "--faces", str(nf), "--image-size", str(H),
+                             "--batch", str(bpg), "--reps", "3"], timeout=600)
     print(json.dumps({
         "metric": "nmr_fwd_bwd_frames_per_s_1024px_39k_faces", "value": bpg * args.steps / (tot / 1000.0), "unit": "frames/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": tot / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": desc, "mode": "rgb", "texture_size": ts, "l2": "256 MiB flush between steps"},
         "step_ms": {"min": float(np.min(ms)), "median": float(np.median(ms)), "max": float(np.max(ms))},
-        "gpu_launches": int(launches), "kernels": kern,
+        "gpu_launches": int(launches), "kernels": kern, "reference_gpu": ref_gpu,
         "roofline_step": {"algorithmic_bytes_per_step": int(alg), "achieved_gbs": alg / (tot / args.steps / 1000.0) / 1e9,
                           "frac": alg / (tot / args.steps / 1000.0) / 1e9 / peak, "peak_source": src}}), flush=True)
 

@@ -115,3 +115,14 @@ def random_triangles(batch, num_faces, seed=0, zmin=1.5, zmax=4.0, scale=0.5, te
     fv = np.concatenate([xy, z], axis=3).astype(np.float32)
     tex = rng.random((batch, num_faces, texture_size, 3), dtype=np.float32)
     return np.ascontiguousarray(fv), tex
+
+
+def nmr_scene(num_faces=280, batch=1, ts=2, fill_back=True, seed=1):
+    """faces [B,nf(x2),3,3] and textures [B,nf(x2),ts,ts,ts,3] the way N3mrRasterizer.render_rgb builds
+    them (jrender/renderer/dr/n3mr/rasterizer.py:83-88): reversed-winding copies appended, textures permuted."""
+    fv, _ = make_scene(num_faces, batch=batch)
+    tex = np.random.default_rng(seed).random((batch, fv.shape[1], ts, ts, ts, 3), dtype=np.float32)
+    if fill_back:
+        fv = np.concatenate([fv, fv[:, :, ::-1]], axis=1)
+        tex = np.concatenate([tex, tex.transpose(0, 1, 4, 3, 2, 5)], axis=1)
+    return np.ascontiguousarray(fv), np.ascontiguousarray(tex)

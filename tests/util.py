@@ -52,15 +52,8 @@ def rel_err(a, b):
 
 
 def nmr_scene(num_faces=280, batch=1, ts=2, fill_back=True, seed=1):
-    """faces [B,nf(x2),3,3] and textures [B,nf(x2),ts,ts,ts,3] the way N3mrRasterizer.render_rgb builds
-    them (rasterizer.py:83-88): reversed-winding copies appended, textures permuted."""
     from jrender_b200 import workloads as wl
-    fv, _ = wl.make_scene(num_faces, batch=batch)
-    tex = np.random.default_rng(seed).random((batch, fv.shape[1], ts, ts, ts, 3), dtype=np.float32)
-    if fill_back:
-        fv = np.concatenate([fv, fv[:, :, ::-1]], axis=1)
-        tex = np.concatenate([tex, tex.transpose(0, 1, 4, 3, 2, 5)], axis=1)
-    return np.ascontiguousarray(fv), np.ascontiguousarray(tex)
+    return wl.nmr_scene(num_faces, batch=batch, ts=ts, fill_back=fill_back, seed=seed)
 
 
 def run_nmr_cuda(faces, textures, image_size, near=0.1, far=100.0, eps=1e-3, background_color=(0, 0, 0),
