@@ -54,7 +54,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-reference-gpu", action="store_true", help="skip the reference-CUDA-kernels-on-this-GPU leg")
     ap.add_argument("--option", action="append", default=[], metavar="NAME=VALUE",
-                    help="b200r_set_option() knob for A/B runs, e.g. --option nmr_bwd_unroll=2")
+                    help="b200r_set_option() knob for A/B runs, e.g. --option softras_exact_tail=1")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU-baseline sample time")
     return ap.parse_args()
 

@@ -186,8 +186,7 @@ B200R_API unsigned long long b200r_launch_count(void);
  *   "softras_exact_tail"     1 = the reference's double-precision sigmoid / alpha-product tails bit for bit;
  *                            0 (default) = the same expressions in fp32 for the default euclidean+softmax
  *                            mode (<= 1 ulp on D; all index / depth outputs are identical either way)
- *   "softras_bwd_variant"    0 = warp union walk + scalar atomics, 1 = per-lane walk + 16-byte atomics (default)
- *   "nmr_bwd_unroll"         pixels per lane per trip of the NMR edge scans: 1 (default), 2 or 4 */
+ *   "softras_bwd_variant"    0 = warp union walk + scalar atomics, 1 = per-lane walk + 16-byte atomics (default) */
 B200R_API int b200r_set_option(const char* name, int value);
 
 /* Per-kernel device timing (CUDA events recorded on the launch stream around every kernel

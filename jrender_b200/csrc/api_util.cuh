@@ -6,7 +6,6 @@
 int b200r_fail(int code, const char* fmt, ...);            // records message, returns code
 int b200r_cuda_fail(cudaError_t e, const char* what);      // records message, returns (int)e
 void b200r_count_launch(void);
-int b200r_option_nmr_bwd_unroll();                        // b200r_set_option("nmr_bwd_unroll")
 
 #include "../../include/b200raster.h"  // kernel ids B200R_K_* for b200r_profile_read
 #define B200R_K_COUNT 16

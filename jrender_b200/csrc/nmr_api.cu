@@ -122,26 +122,27 @@ int b200r_nmr_backward(const float* faces, const int32_t* face_index_map, const 
         const size_t need = b200r_nmr_backward_scratch_bytes(B, is);
         if (!scratch || scratch_bytes < need)
             return b200r_fail(B200R_EWORKSPACE, "b200r_nmr_backward: scratch %zu < required %zu bytes", scratch_bytes, need);
-        float4* ph = reinterpret_cast<float4*>(scratch);
-        float4* pv = ph + (size_t)B * is * is * 2;
-        {
-            B200rProfScope prof(B200R_K_NMR_PACK, st);
-            k_nmr_pack<<<dim3((is + 31) / 32, (is + 31) / 32, B), 256, 0, st>>>(rgb_map, alpha_map, grad_rgb_map, grad_alpha_map, ph, pv, is,
-                                                                              return_rgb ? 1 : 0, return_alpha ? 1 : 0);
-        }
-        e = cudaGetLastError();
-        if (e != cudaSuccess) return b200r_cuda_fail(e, "k_nmr_pack");
+        const int mode = (return_rgb ? 1 : 0) | (return_alpha ? 2 : 0);
+        const size_t fl = mode == 1 ? 4 : (mode == 2 ? 2 : 8);   // floats per packed record (K9Rec<MODE>::FL)
+        float* ph = reinterpret_cast<float*>(scratch);
+        float* pv = ph + (size_t)B * is * is * fl;
         const long warps = (long)B * nf;
-        B200rProfScope prof(B200R_K_NMR_BWD_PIXEL, st);
-#define B200R_LAUNCH_K9(U)                                                                                              \
-    k_nmr_backward_pixel_map<U><<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(faces, face_index_map, rgb_map, alpha_map, \
-                                                                            grad_rgb_map, grad_alpha_map, ph, pv,      \
-                                                                            grad_faces, B, nf, is, eps,                \
-                                                                            return_rgb ? 1 : 0, return_alpha ? 1 : 0)
-        const int unroll = b200r_option_nmr_bwd_unroll();
-        if (unroll >= 4) B200R_LAUNCH_K9(4);
-        else if (unroll >= 2) B200R_LAUNCH_K9(2);
-        else B200R_LAUNCH_K9(1);
+#define B200R_LAUNCH_K9(MODE)                                                                                                          \
+    {                                                                                                                                  \
+        {                                                                                                                              \
+            B200rProfScope prof(B200R_K_NMR_PACK, st);                                                                                 \
+            k_nmr_pack<MODE><<<dim3((is + 31) / 32, (is + 31) / 32, B), 256, 0, st>>>(rgb_map, alpha_map, grad_rgb_map, grad_alpha_map, \
+                                                                                    ph, pv, is);                                      \
+        }                                                                                                                              \
+        e = cudaGetLastError();                                                                                                        \
+        if (e != cudaSuccess) return b200r_cuda_fail(e, "k_nmr_pack");                                                                 \
+        B200rProfScope prof(B200R_K_NMR_BWD_PIXEL, st);                                                                                \
+        k_nmr_backward_pixel_map<MODE><<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(faces, face_index_map, rgb_map, alpha_map, ph, pv,  \
+                                                                                   grad_faces, B, nf, is, eps);                       \
+    }
+        if (mode == 3) B200R_LAUNCH_K9(3)
+        else if (mode == 1) B200R_LAUNCH_K9(1)
+        else B200R_LAUNCH_K9(2)
 #undef B200R_LAUNCH_K9
     }
     e = cudaGetLastError();

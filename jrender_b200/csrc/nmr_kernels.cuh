@@ -314,43 +314,63 @@ k_nmr_forward(const NmrParams P, const NmrRec* __restrict__ recs, const uint2* _
 }
 
 // ---------------------------------------------------------------- K9 prologue: packed pixel records
-// K9's scans read (rgb, grad_rgb, alpha, grad_alpha) of long pixel runs: along x for axis 1 and
-// along y for axis 0.  Reading four separate maps, and columns with a stride of a whole image
-// row, made the first version of the backward 20x slower than its instruction count warrants.
-// This kernel gathers the 8 floats of every pixel into one 32-byte record and writes them twice:
-// row-major (ph[b][y][x]) and column-major (pv[b][x][y]), so that both scan directions read
-// consecutive 32-byte sectors.  32x32 tile transpose through shared memory.
+// K9's scans evaluate, for long pixel runs (along x for axis 1, along y for axis 0),
+//     diff_grad = sum_k (map_k - ref_k) * grad_k            (k over r, g, b and/or alpha; ref = the sample's in / out pixel)
+// which is  A - sum_k ref_k * grad_k  with the per-pixel moment  A = sum_k map_k * grad_k.  This kernel stores (A, grad)
+// per pixel -- 16 bytes for rgb (A, gr, gg, gb), 8 for alpha (A, ga), 32 for both -- twice: row-major (ph[b][y][x]) and
+// column-major (pv[b][x][y]), so both scan directions read consecutive records.  (Reading the four maps separately, and
+// columns with a stride of a whole image row, made the first version of the backward 20x slower than its instruction
+// count warrants; 32-byte (rgb, grad, alpha, grad) records were the second version: the scans then ran at the L1's
+// bandwidth, which this halves.)  32x32 tile transpose through shared memory.
+// MODE 1: rgb, 2: alpha, 3: both.  FL = floats per record (4, 2, 8).
+template <int MODE>
+struct K9Rec {
+    static constexpr int FL = (MODE == 1) ? 4 : ((MODE == 2) ? 2 : 8);
+};
+
+template <int MODE>
 __global__ void __launch_bounds__(256)
 k_nmr_pack(const float* __restrict__ rgb_map, const float* __restrict__ alpha_map, const float* __restrict__ grad_rgb_map,
-           const float* __restrict__ grad_alpha_map, float4* __restrict__ ph, float4* __restrict__ pv, int is,
-           int return_rgb, int return_alpha) {
-    __shared__ float4 s[32][33][2];
+           const float* __restrict__ grad_alpha_map, float* __restrict__ ph, float* __restrict__ pv, int is) {
+    constexpr int FL = K9Rec<MODE>::FL;
+    __shared__ float s[32][33][FL];
     const int b = blockIdx.z, x0 = blockIdx.x * 32, y0 = blockIdx.y * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const size_t img = (size_t)b * is * is;
     for (int r = ty; r < 32; r += 8) {
         const int x = x0 + tx, y = y0 + r;
-        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), c = make_float4(0.f, 0.f, 0.f, 0.f);
+        float v[FL];
+#pragma unroll
+        for (int k = 0; k < FL; k++) v[k] = 0.f;
         if (x < is && y < is) {
             const size_t i = img + (size_t)y * is + x;
-            if (return_rgb) {
-                a.x = __ldg(rgb_map + i * 3 + 0); a.y = __ldg(rgb_map + i * 3 + 1); a.z = __ldg(rgb_map + i * 3 + 2);
-                a.w = __ldg(grad_rgb_map + i * 3 + 0); c.x = __ldg(grad_rgb_map + i * 3 + 1); c.y = __ldg(grad_rgb_map + i * 3 + 2);
+            float A = 0.f;
+            if (MODE & 1) {
+                const float g0 = __ldg(grad_rgb_map + i * 3 + 0), g1 = __ldg(grad_rgb_map + i * 3 + 1), g2 = __ldg(grad_rgb_map + i * 3 + 2);
+                A = __fmaf_rn(__ldg(rgb_map + i * 3 + 0), g0, A);
+                A = __fmaf_rn(__ldg(rgb_map + i * 3 + 1), g1, A);
+                A = __fmaf_rn(__ldg(rgb_map + i * 3 + 2), g2, A);
+                v[1] = g0; v[2] = g1; v[3] = g2;
             }
-            if (return_alpha) { c.z = __ldg(alpha_map + i); c.w = __ldg(grad_alpha_map + i); }
-            ph[i * 2] = a;
-            ph[i * 2 + 1] = c;
+            if (MODE & 2) {
+                const float ga = __ldg(grad_alpha_map + i);
+                A = __fmaf_rn(__ldg(alpha_map + i), ga, A);
+                v[(MODE == 2) ? 1 : 4] = ga;
+            }
+            v[0] = A;
+#pragma unroll
+            for (int k = 0; k < FL; k++) ph[i * FL + k] = v[k];
         }
-        s[r][tx][0] = a;
-        s[r][tx][1] = c;
+#pragma unroll
+        for (int k = 0; k < FL; k++) s[r][tx][k] = v[k];
     }
     __syncthreads();
     for (int r = ty; r < 32; r += 8) {
         const int x = x0 + r, y = y0 + tx;   // pv[b][x][y] <- pixel (y, x) = s[y - y0][x - x0]
         if (x < is && y < is) {
             const size_t j = img + (size_t)x * is + y;
-            pv[j * 2] = s[tx][r][0];
-            pv[j * 2 + 1] = s[tx][r][1];
+#pragma unroll
+            for (int k = 0; k < FL; k++) pv[j * FL + k] = s[tx][r][k];
         }
     }
 }
@@ -372,31 +392,88 @@ __device__ __forceinline__ float rcp_approx(float x) {
     return r;
 }
 
-// One (edge, axis) pass of the reference's per-face loop (:386-608).  The six passes of a face
-// run as a real loop (not unrolled): the body is long and six copies of it thrash the
-// instruction cache.
+__device__ __forceinline__ float k9_sel3(int i, float a, float b, float c) { return i == 0 ? a : (i == 1 ? b : c); }
+
+// One line scan of K9 (:486-520 outwards / :556-601 inwards): lanes take consecutive pixels d1_from + lane, + 32, ...
+// of the packed row `prow` (k_nmr_pack) and add their  -diff_grad / dist  terms to acc0 / acc1.
+//   OWNER  inward scan: only pixels whose face_index_map entry is this face count (:573)
+//   BOTH   both vertex terms present (p[1][0] != d0 and p[0][0] != d0, :508/:513): the common, branch-free flavour
+// The loop is the whole cost of the kernel (the outward scan runs to the image border for every edge sample), so it
+// is kept to one record load and ~20 arithmetic instructions per 32 pixels: pointers and the pixel coordinate
+// advance by constants, the `diff_grad <= 0` skip is a select (a NaN still propagates like the reference's
+// `continue` would let it), products are fused (sums of ~10^2..10^3 terms, compared at 2e-5 relative).
+// ref = (r, g, b, alpha) of the sample's in-pixel (outward scan) / out-pixel (inward scan).
+template <int MODE, bool OWNER, bool BOTH>
+__device__ __forceinline__ void k9_scan(const float* __restrict__ prow, const int* __restrict__ fim, long fim_stride,
+                                        int d1_from, int d1_to, int lane, int fn, float r0, float r1, float r2, float ra,
+                                        float d1_cross, float k0, float k1, bool has0, bool has1, float eps,
+                                        float& acc0, float& acc1) {
+    constexpr int FL = K9Rec<MODE>::FL;
+    const float* __restrict__ p = prow + (long)(d1_from + lane) * FL;
+    const int* __restrict__ o = OWNER ? fim + (long)(d1_from + lane) * fim_stride : nullptr;
+    float d1f = (float)(d1_from + lane);   // exact below 2^24
+    for (int left = d1_to - d1_from - lane; left >= 0; left -= 32) {
+        float diff;
+        if (MODE == 1) {
+            const float4 q = __ldg(reinterpret_cast<const float4*>(p));
+            diff = q.x - __fmaf_rn(r2, q.w, __fmaf_rn(r1, q.z, r0 * q.y));
+        } else if (MODE == 2) {
+            const float2 q = __ldg(reinterpret_cast<const float2*>(p));
+            diff = q.x - ra * q.y;
+        } else {
+            const float4 q = __ldg(reinterpret_cast<const float4*>(p));
+            const float ga = __ldg(p + 4);
+            diff = q.x - __fmaf_rn(ra, ga, __fmaf_rn(r2, q.w, __fmaf_rn(r1, q.z, r0 * q.y)));
+        }
+        bool mine = true;
+        if (OWNER) { mine = __ldg(o) == fn; o += 32 * fim_stride; }
+        p += 32 * FL;
+        const float d = (mine && !(diff <= 0.f)) ? diff : 0.f;   // :503 / :587 `if (diff_grad <= 0) continue`
+        const float delta = d1f - d1_cross;   // (d1 - d1_cross), one rounding like the reference's
+        d1f += 32.f;
+        if (BOTH || has0) {
+            float dist = delta * k0;
+            dist = (0.f < dist) ? dist + eps : dist - eps;      // :510
+            acc0 = __fmaf_rn(-d, rcp_approx(dist), acc0);
+        }
+        if (BOTH || has1) {
+            float dist = delta * k1;
+            dist = (0.f < dist) ? dist + eps : dist - eps;      // :515
+            acc1 = __fmaf_rn(-d, rcp_approx(dist), acc1);
+        }
+    }
+}
+
+// K9 (backward_pixel_map_cuda_kernel, n3mr/cuda/rasterize.py:351-610): warp per (batch, face).  The six (edge, axis)
+// passes of a face run as a real loop (six inlined copies thrash the instruction cache).  Per pass the three slopes
+// of :423 / :529-533 are divided once (the reference re-divides per d0 with the same operands: same bits), the
+// per-sample quotients that only scale `dist` use the approximate reciprocal, and the two scans are the tight loops
+// of k9_scan.  d1_cross / d0_cross2 -- which pick pixels through floor / ceil -- keep the reference's exact,
+// unfused arithmetic.
 #ifndef B200R_K9_MINB
-#define B200R_K9_MINB 6   // resident 256-thread CTAs per SM for the single-pixel-per-trip scan (40 registers; measured best of 4/5/6/8)
+#define B200R_K9_MINB 6   // resident 256-thread CTAs per SM (40 registers; with the 32-byte records: 7.10 ms at C4 against 7.33 at 5 and 7.68 at 4 -- the scans are latency-bound)
 #endif
-template <int U>
-__global__ void __launch_bounds__(256, U == 1 ? B200R_K9_MINB : 1)
+template <int MODE>
+__global__ void __launch_bounds__(256, B200R_K9_MINB)
 k_nmr_backward_pixel_map(const float* __restrict__ faces, const int* __restrict__ face_index_map,
                          const float* __restrict__ rgb_map, const float* __restrict__ alpha_map,
-                         const float* __restrict__ grad_rgb_map, const float* __restrict__ grad_alpha_map,
-                         const float4* __restrict__ ph, const float4* __restrict__ pv,
-                         float* __restrict__ grad_faces, int batch_size, int num_faces, int is, float eps,
-                         int return_rgb, int return_alpha) {
+                         const float* __restrict__ ph, const float* __restrict__ pv,
+                         float* __restrict__ grad_faces, int batch_size, int num_faces, int is, float eps) {
+    constexpr int FL = K9Rec<MODE>::FL;
     const int lane = threadIdx.x & 31;
     const long i = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (i >= (long)batch_size * num_faces) return;
     const int bn = (int)(i / num_faces);
     const int fn = (int)(i % num_faces);
     const float* __restrict__ face = faces + i * 9;
-    {
-        const float x0 = __ldg(face + 0), y0 = __ldg(face + 1), x1 = __ldg(face + 3), y1 = __ldg(face + 4);
-        const float x2 = __ldg(face + 6), y2 = __ldg(face + 7);
-        if ((y2 - y0) * (x1 - x0) < (y1 - y0) * (x2 - x0)) return;  // :377 (zeros stay)
-    }
+    float fx[3], fy[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) { fx[k] = __ldg(face + 3 * k); fy[k] = __ldg(face + 3 * k + 1); }
+    if ((fy[2] - fy[0]) * (fx[1] - fx[0]) < (fy[1] - fy[0]) * (fx[2] - fx[0])) return;  // :377 (zeros stay)
+    // pixel-space vertices, pp[num][dim] = 0.5 * (face * is + is - 1)  (:389-393)
+    float px[3], py[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) { px[k] = 0.5f * (fx[k] * is + is - 1); py[k] = 0.5f * (fy[k] * is + is - 1); }
 
     float gacc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // [vertex*2 + (0:x, 1:y)]
     const float ndc_scale = 2.f / (float)is;
@@ -406,99 +483,64 @@ k_nmr_backward_pixel_map(const float* __restrict__ faces, const int* __restrict_
     for (int pass = 0; pass < 6; pass++) {
         const int edge_num = pass >> 1, axis = pass & 1;
         const int pi0 = edge_num, pi1 = (edge_num == 2) ? 0 : edge_num + 1, pi2 = (edge_num == 0) ? 2 : edge_num - 1;
-        // p[num][dim] = 0.5 * (face[3 * pi_num + (dim + axis) % 2] * is + is - 1)   (:389-399)
-        const float p00 = 0.5f * (__ldg(face + 3 * pi0 + axis) * is + is - 1), p01 = 0.5f * (__ldg(face + 3 * pi0 + (axis ^ 1)) * is + is - 1);
-        const float p10 = 0.5f * (__ldg(face + 3 * pi1 + axis) * is + is - 1), p11 = 0.5f * (__ldg(face + 3 * pi1 + (axis ^ 1)) * is + is - 1);
-        const float p20 = 0.5f * (__ldg(face + 3 * pi2 + axis) * is + is - 1), p21 = 0.5f * (__ldg(face + 3 * pi2 + (axis ^ 1)) * is + is - 1);
+        // p[num][dim] = pp[num][(dim + axis) % 2]   (:396-401)
+        const float ax0 = k9_sel3(pi0, px[0], px[1], px[2]), ay0 = k9_sel3(pi0, py[0], py[1], py[2]);
+        const float ax1 = k9_sel3(pi1, px[0], px[1], px[2]), ay1 = k9_sel3(pi1, py[0], py[1], py[2]);
+        const float ax2 = k9_sel3(pi2, px[0], px[1], px[2]), ay2 = k9_sel3(pi2, py[0], py[1], py[2]);
+        const float p00 = axis ? ay0 : ax0, p01 = axis ? ax0 : ay0;
+        const float p10 = axis ? ay1 : ax1, p11 = axis ? ax1 : ay1;
+        const float p20 = axis ? ay2 : ax2, p21 = axis ? ax2 : ay2;
         int direction;
         if (axis == 0) direction = (p00 < p10) ? -1 : 1;
         else direction = (p00 < p10) ? 1 : -1;
         const int d0_from = (int)fmax((double)ceilf(fminf(p00, p10)), 0.);
         const int d0_to = (int)fmin((double)fmaxf(p00, p10), is - 1.);
-        // packed records: axis 1 scans rows of ph, axis 0 scans rows of pv; in both the record
-        // of (d0, d1) sits at img + d0 * is + d1
-        const float4* __restrict__ pk = ((axis == 0) ? pv : ph) + img * 2;
+        if (d0_from > d0_to) continue;
+        const float slope01 = (p11 - p01) / (p10 - p00);   // :423
+        const float slope02 = (p21 - p01) / (p20 - p00);   // :530
+        const float slope21 = (p11 - p21) / (p10 - p20);   // :533
+        const float span = p10 - p00;
+        // packed records: axis 1 scans rows of ph, axis 0 scans rows of pv; in both the record of (d0, d1) sits at
+        // (img + d0 * is + d1) * FL
+        const float* __restrict__ pk = ((axis == 0) ? pv : ph) + img * FL;
+        const long fim_stride = (axis == 0) ? is : 1;
         float acc0 = 0.f, acc1 = 0.f;  // contributions to vertex pi0 / pi1, coordinate (1 - axis)
         for (int d0 = d0_from; d0 <= d0_to; d0++) {
-            const float d1_cross = (p11 - p01) / (p10 - p00) * (d0 - p00) + p01;
+            const float d0f = (float)d0;
+            const float d1_cross = slope01 * (d0f - p00) + p01;
             const int d1_in = (0 < direction) ? (int)floorf(d1_cross) : (int)ceilf(d1_cross);
             const int d1_out = d1_in + direction;
             if (d1_in < 0 || is <= d1_in) continue;
             if (d1_out < 0 || is <= d1_out) continue;
-            const float4* __restrict__ prow = pk + (long)d0 * is * 2;
-            const float4 ia = __ldg(prow + d1_in * 2), ic = __ldg(prow + d1_in * 2 + 1);
-            const float4 oa = __ldg(prow + d1_out * 2), oc = __ldg(prow + d1_out * 2 + 1);
-            const bool has0 = p10 != d0, has1 = p00 != d0;
-            const float q0 = (p10 - p00) / (p10 - d0);
-            const float q1 = (p10 - p00) / (d0 - p00);
-            // pixel -> NDC: the reference's (float)((double)(q * delta) * 2. / is) is formed as
-            // delta * (q * (2 / is)) -- a few ulp on a quantity that is then offset by eps and
-            // inverted approximately (see rcp_approx); the sign test `0 < dist` is unaffected
-            const float k0 = q0 * ndc_scale, k1 = q1 * ndc_scale;
-            const long map_index_in = (axis == 0) ? img + (long)d1_in * is + d0 : img + (long)d0 * is + d1_in;
-            const bool visible = __ldg(face_index_map + map_index_in) == fn;
-            float d0_cross2;
-            if ((d0 - p00) * (d0 - p20) < 0.f) d0_cross2 = (p21 - p01) / (p20 - p00) * (d0 - p00) + p01;
-            else d0_cross2 = (p11 - p21) / (p10 - p20) * (d0 - p20) + p21;
-            const int in_limit = (0 < direction) ? (int)ceilf(d0_cross2) : (int)floorf(d0_cross2);
+            const float* __restrict__ prow = pk + (long)d0 * is * FL;
+            const bool has0 = p10 != d0f, has1 = p00 != d0f;
+            // pixel -> NDC: the reference's (float)((double)(q * delta) * 2. / is) is formed as delta * (q * (2 / is)); q by
+            // approximate reciprocal -- a few ulp on a quantity that is then offset by eps and inverted approximately
+            const float k0 = span * rcp_approx(p10 - d0f) * ndc_scale, k1 = span * rcp_approx(d0f - p00) * ndc_scale;
             const long fim_base = (axis == 0) ? img + d0 : img + (long)d0 * is;
-            const long fim_stride = (axis == 0) ? is : 1;
-
-#pragma unroll 1
-            for (int scan = 0; scan < 2; scan++) {
-                // scan 0: outwards from the edge (:461-521), only if the face owns the inside pixel;
-                // scan 1: inwards up to the opposite edge (:523-602), pixels owned by the face
-                int lim, start;
-                float r0, r1, r2, ra;
-                if (scan == 0) {
-                    if (!visible) continue;
-                    lim = (0 < direction) ? is - 1 : 0;
-                    start = d1_out;
-                    r0 = ia.x; r1 = ia.y; r2 = ia.z; ra = ic.z;
-                } else {
-                    lim = in_limit;
-                    start = d1_in;
-                    r0 = oa.x; r1 = oa.y; r2 = oa.z; ra = oc.z;
-                }
-                const int d1_from = max(min(start, lim), 0);
-                const int d1_to = min(max(start, lim), is - 1);
-                // U pixels per lane per trip, every load issued before the first use: the scan is
-                // latency-bound (one dependent L1/L2 round trip per trip), not bandwidth-bound
-                float d1f = (float)(d1_from + lane);  // exact below 2^24
-                for (int d1b = d1_from + lane; d1b <= d1_to; d1b += 32 * U, d1f += 32.f * U) {
-                    float4 qa[U], qc[U];
-                    int owner[U];
-#pragma unroll
-                    for (int u = 0; u < U; u++) {
-                        const int d1 = min(d1b + 32 * u, d1_to);  // clamped: always a valid address
-                        owner[u] = (scan == 1) ? __ldg(face_index_map + fim_base + (long)d1 * fim_stride) : fn;
-                        qa[u] = __ldg(prow + d1 * 2);
-                        qc[u] = __ldg(prow + d1 * 2 + 1);
-                    }
-#pragma unroll
-                    for (int u = 0; u < U; u++) {
-                        const int d1 = d1b + 32 * u;
-                        if (d1 > d1_to || owner[u] != fn) continue;
-                        float diff_grad = 0.f;
-                        if (return_alpha) diff_grad += (qc[u].z - ra) * qc[u].w;
-                        if (return_rgb) {
-                            diff_grad += (qa[u].x - r0) * qa[u].w;
-                            diff_grad += (qa[u].y - r1) * qc[u].x;
-                            diff_grad += (qa[u].z - r2) * qc[u].y;
-                        }
-                        if (diff_grad <= 0.f) continue;
-                        const float delta = (d1f + 32.f * u) - d1_cross;
-                        if (has0) {
-                            float dist = delta * k0;
-                            dist = (0.f < dist) ? dist + eps : dist - eps;
-                            acc0 = __fmaf_rn(-diff_grad, rcp_approx(dist), acc0);
-                        }
-                        if (has1) {
-                            float dist = delta * k1;
-                            dist = (0.f < dist) ? dist + eps : dist - eps;
-                            acc1 = __fmaf_rn(-diff_grad, rcp_approx(dist), acc1);
-                        }
-                    }
+            const long idx_in = fim_base + (long)d1_in * fim_stride, idx_out = fim_base + (long)d1_out * fim_stride;
+            const bool visible = __ldg(face_index_map + idx_in) == fn;
+            if (visible) {   // outwards from the edge to the image border (:461-521); reference colour = the in-pixel's
+                float r0 = 0.f, r1 = 0.f, r2 = 0.f, ra = 0.f;
+                if (MODE & 1) { r0 = __ldg(rgb_map + idx_in * 3); r1 = __ldg(rgb_map + idx_in * 3 + 1); r2 = __ldg(rgb_map + idx_in * 3 + 2); }
+                if (MODE & 2) ra = __ldg(alpha_map + idx_in);
+                const int lim = (0 < direction) ? is - 1 : 0;
+                const int d1_from = max(min(d1_out, lim), 0), d1_to = min(max(d1_out, lim), is - 1);
+                if (has0 && has1) k9_scan<MODE, false, true>(prow, nullptr, 0, d1_from, d1_to, lane, fn, r0, r1, r2, ra, d1_cross, k0, k1, true, true, eps, acc0, acc1);
+                else k9_scan<MODE, false, false>(prow, nullptr, 0, d1_from, d1_to, lane, fn, r0, r1, r2, ra, d1_cross, k0, k1, has0, has1, eps, acc0, acc1);
+            }
+            {   // inwards up to the opposite edge, pixels owned by the face (:523-602); reference colour = the out-pixel's
+                float d0_cross2;
+                if ((d0f - p00) * (d0f - p20) < 0.f) d0_cross2 = slope02 * (d0f - p00) + p01;
+                else d0_cross2 = slope21 * (d0f - p20) + p21;
+                const int lim = (0 < direction) ? (int)ceilf(d0_cross2) : (int)floorf(d0_cross2);
+                const int d1_from = max(min(d1_in, lim), 0), d1_to = min(max(d1_in, lim), is - 1);
+                if (d1_from <= d1_to) {
+                    float r0 = 0.f, r1 = 0.f, r2 = 0.f, ra = 0.f;
+                    if (MODE & 1) { r0 = __ldg(rgb_map + idx_out * 3); r1 = __ldg(rgb_map + idx_out * 3 + 1); r2 = __ldg(rgb_map + idx_out * 3 + 2); }
+                    if (MODE & 2) ra = __ldg(alpha_map + idx_out);
+                    k9_scan<MODE, true, false>(prow, face_index_map + fim_base, fim_stride, d1_from, d1_to, lane, fn, r0, r1, r2, ra,
+                                               d1_cross, k0, k1, has0, has1, eps, acc0, acc1);
                 }
             }
         }

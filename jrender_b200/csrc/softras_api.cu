@@ -18,10 +18,7 @@ std::atomic<int> g_fwd_persistent{1};  // 0: one CTA per tile, 1: persistent gri
 std::atomic<int> g_exact_tail{0};      // 1: reference's double-precision sigmoid / alpha tails bit for bit; 0: fp32 tails (<= 1 ulp)
 std::atomic<int> g_bwd_variant{1};     // 0: warp union walk + scalar atomics, 1: per-lane walk + 16-byte vector atomics
 std::atomic<int> g_fwd_warps{1};       // warps per forward CTA: 8 (16x16 tile), 2 (16x4), 1 (8x4, warp-autonomous; default)
-std::atomic<int> g_nmr_bwd_unroll{1};  // pixels per lane per trip in the NMR edge scans (1, 2 or 4)
 }  // namespace
-
-int b200r_option_nmr_bwd_unroll() { return g_nmr_bwd_unroll.load(); }
 
 int b200r_sm_count() {
     static int n = 0;
@@ -76,18 +73,13 @@ const char* b200r_version(void) { return "b200raster 0.1 (sm_100a)"; }
 
 int b200r_set_option(const char* name, int value) {
     if (!name) return b200r_fail(B200R_EINVAL, "b200r_set_option: NULL name");
-    if (!strcmp(name, "softras_fwd_variant")) { g_fwd_variant.store(value ? 1 : 0); return 0; }
+    if (!strcmp(name, "softras_fwd_variant")) { g_fwd_variant.store(value < 0 ? 0 : (value > 2 ? 2 : value)); return 0; }
     if (!strcmp(name, "softras_fwd_persistent")) { g_fwd_persistent.store(value ? 1 : 0); return 0; }
     if (!strcmp(name, "softras_exact_tail")) { g_exact_tail.store(value ? 1 : 0); return 0; }
     if (!strcmp(name, "softras_bwd_variant")) { g_bwd_variant.store(value ? 1 : 0); return 0; }
     if (!strcmp(name, "softras_fwd_warps")) {
         if (value != 1 && value != 2 && value != 8) return b200r_fail(B200R_EINVAL, "softras_fwd_warps must be 1, 2 or 8");
         g_fwd_warps.store(value);
-        return 0;
-    }
-    if (!strcmp(name, "nmr_bwd_unroll")) {
-        if (value != 1 && value != 2 && value != 4) return b200r_fail(B200R_EINVAL, "nmr_bwd_unroll must be 1, 2 or 4");
-        g_nmr_bwd_unroll.store(value);
         return 0;
     }
     return b200r_fail(B200R_EINVAL, "b200r_set_option: unknown option '%s'", name);

@@ -70,7 +70,7 @@ struct FwdSmem {
     FaceRecS rec[FwdCfg<NW>::CHUNK];                     // reused as the output staging area
     int ids[FwdCfg<NW>::CHUNK + FwdCfg<NW>::UNR * FwdCfg<NW>::NT];  // pending tile-face ids, ascending
     unsigned char wlist[NW][FwdCfg<NW>::CHUNK];          // per-warp sub-list (indices into rec[])
-    uint32_t lmask[16];                                  // 1-warp CTAs: per staged record, the lanes whose pixel it covers
+    uint32_t lmask[32];                                  // 1-warp CTAs: per staged record, the lanes whose pixel it covers
     int s_warp[NW];
     int s_tile;
 };
@@ -477,7 +477,7 @@ k_softras_forward(const SoftRasParams P, const FaceRec* __restrict__ recs, const
                     if constexpr (B200R_FWD_MASKLIST && CHUNK <= 32) {
                         // the list is a bit mask over the staged records (ascending record = ascending face id)
                         unsigned mask = 0u;
-                        if constexpr (B200R_FWD_LANEMASK && NW == 1 && CHUNK == 16) {
+                        if constexpr (B200R_FWD_LANEMASK && NW == 1 && (CHUNK == 16 || CHUNK == 32)) {
                             // Transposed build: lane j turns record j's rectangle, clipped to the 8x4 block, into the
                             // 32-bit set of covered lanes (a column mask replicated over the covered rows); every lane
                             // then picks its own bit out of the 16 words (4 broadcast LDS.128).  ~40 instructions per
@@ -493,10 +493,10 @@ k_softras_forward(const SoftRasParams P, const FaceRec* __restrict__ recs, const
                                     lm = (cols * 0x01010101u) & rows;
                                 }
                             }
-                            if (lane < 16) S.lmask[lane] = lm;
+                            if (lane < CHUNK) S.lmask[lane] = lm;
                             __syncwarp();
 #pragma unroll
-                            for (int q = 0; q < 4; q++) {
+                            for (int q = 0; q < CHUNK / 4; q++) {
                                 const uint4 m4 = reinterpret_cast<const uint4*>(S.lmask)[q];
                                 mask |= ((m4.x >> lane) & 1u) << (4 * q + 0);
                                 mask |= ((m4.y >> lane) & 1u) << (4 * q + 1);

@@ -129,10 +129,11 @@ class FlattenLoss(nn.Module):
 
     def forward(self, vertices, eps=1e-6):
         batch_size = vertices.shape[0]
-        # the kernel dereferences the module's index buffers and indexes vertices with them: they must live on the
-        # input's device and the mesh must have every vertex the table names; anything else takes the index_select
-        # path below, which raises torch's own device-mismatch / index-out-of-range errors
-        if self.fused and _fusable(vertices) and self.e32.device == vertices.device and vertices.shape[1] >= self.nv_min:
+        if vertices.shape[1] < self.nv_min:   # checked on the host: a device-side index assert would poison the CUDA context
+            raise IndexError("FlattenLoss: the edge table names vertex %d but vertices has only %d" % (self.nv_min - 1, vertices.shape[1]))
+        # the kernel dereferences the module's index buffers: they must live on the input's device, otherwise the
+        # index_select path below raises torch's own device-mismatch error
+        if self.fused and _fusable(vertices) and self.e32.device == vertices.device:
             L = _lib.lib()
             E = int(self.v0s.shape[0])
 

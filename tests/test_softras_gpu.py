@@ -272,7 +272,7 @@ def test_against_reference_kernels_on_gpu(cuda_device, nfaces, H, min_same, grad
         assert np.abs(a[m] - b[m]).sum() / np.abs(a[m]).sum() <= grad_l1, k
 
 
-@pytest.mark.parametrize("warps,variant,persistent", [(8, 0, 0), (8, 0, 1), (8, 1, 0), (2, 1, 1), (1, 1, 1), (1, 1, 0)])
+@pytest.mark.parametrize("warps,variant,persistent", [(8, 0, 0), (8, 0, 1), (8, 1, 0), (2, 1, 1), (1, 1, 1), (1, 1, 0), (1, 2, 1), (1, 2, 0)])
 def test_every_forward_configuration_gives_identical_results(cuda_device, warps, variant, persistent):
     """Tile shape (16x16 / 16x4 / 8x4 warp-autonomous), per-lane lists and the persistent LPT queue are
     pure scheduling choices: all outputs must be bit-identical to the default configuration's."""

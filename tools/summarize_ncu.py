@@ -22,13 +22,18 @@ def main():
     tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
     os.makedirs("profiles", exist_ok=True)
     rep = "gpurun_out/prof_softras.ncu-rep"
+    title = "bench.py c3 workload, 4 images 1024^2, 39 200 faces"
+    name_out = "ncu_full_softras"
+    if len(sys.argv) > 3:      # python tools/summarize_ncu.py <tag> <report.ncu-rep> <name> ["title"]
+        rep, name_out = sys.argv[2], sys.argv[3]
+        title = sys.argv[4] if len(sys.argv) > 4 else rep
     if os.path.exists(rep):
         raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
         rows = list(csv.reader(io.StringIO(raw)))
         hdr, units = rows[0], rows[1]
         ki = hdr.index("Kernel Name")
-        with open("profiles/%s_ncu_full_softras.md" % tag, "w") as f:
-            f.write("# ncu --set full --clock-control none (bench.py c3 workload, 4 images 1024^2, 39 200 faces)\n\n")
+        with open("profiles/%s_%s.md" % (tag, name_out), "w") as f:
+            f.write("# ncu --set full --clock-control none (%s)\n\n" % title)
             f.write("Per-launch values under the profiler (serialised, cold caches): use for SHARES and pipe/stall structure, not for bench numbers.\n\n")
             for r in rows[2:]:
                 name = re.sub(r"\(.*", "", r[ki])
@@ -37,7 +42,9 @@ def main():
                     if re.search(KEEP, h):
                         f.write("| %s | %s | %s |\n" % (h, r[i], units[i]))
                 f.write("\n")
-        print("wrote profiles/%s_ncu_full_softras.md" % tag)
+        print("wrote profiles/%s_%s.md" % (tag, name_out))
+        if len(sys.argv) > 3:
+            return
     lc = "gpurun_out/launches.csv"
     if os.path.exists(lc):
         lines = [l for l in open(lc) if l.startswith('"')]
