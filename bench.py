@@ -40,7 +40,11 @@ WORKLOADS = {
     # Laplacian + flatten losses) at 512^2; one "step" = one optimisation iteration over all views
     "c5": (3280, 512, 120, "C5: demo2-deform geometry optimisation loop, 3280-face sphere -> ellipsoid silhouettes, 512x512, 120 views/iteration"),
     "c4": (39200, 1024, 16, "C4: NMR (n3mr) fwd+bwd 1024x1024, UV sphere 39200 faces (78400 with fill_back), ts=2, 16 images/GPU"),
+    # BASELINE.json configs[0] as demo1-render.py runs it: spot cow (5856 faces), texture_res 5 (T=25) baked from spot_texture.png,
+    # 256x256, one view per render, forward only, image read back to the host
+    "c1": (5856, 256, 1, "C1: demo1-render, spot cow 5856 faces, T=25 baked textures, 256x256, 1 view per render (forward + D2H)"),
 }
+ASSETS = os.path.join(ROOT, "baseline", "_ref", "assets", "data")   # staged by tools/stage_assets.py where /root/reference exists
 README_39K_MS = 35.5  # Jrender SoftRas 39k faces, 1024^2, hardware/batch unstated
 
 
@@ -559,12 +563,19 @@ def run_deform(args, rank, world, local_rank):
     nf, H, views, desc = WORKLOADS["c5"]
     iters = max(8, args.steps)
     out = {}
+    src = {}
+    staged = all(os.path.exists(os.path.join(ASSETS, f)) for f in ("source.npy", "camera.npy", "obj/sphere/sphere_1352.obj"))
+    if staged:   # demo2-deform.py:50-55 literally: sphere_1352.obj template, data/source.npy silhouettes (64^2, nearest-upsampled), data/camera.npy
+        src = dict(filename_input=os.path.join(ASSETS, "source.npy"), camera_input=os.path.join(ASSETS, "camera.npy"),
+                   template_mesh=os.path.join(ASSETS, "obj/sphere/sphere_1352.obj"))
+        desc = "C5: demo2-deform as configured (sphere_1352.obj -> data/source.npy silhouettes, data/camera.npy), 512x512, 120 views/iteration"
     for mode in ("eager", "cuda_graph"):
         l0 = L.b200r_launch_count()
         r = demo2_deform.run(iters=iters, image_size=H, batch_size=views, verbose=False, cuda_graph=(mode == "cuda_graph"),
-                             device=str(dev))
+                             device=str(dev), **src)
         out[mode] = {"ms_per_iter": r["device_ms_per_iter"], "host_ms_per_iter": r["ms_per_iter"], "first_iou": r["first_iou"],
-                     "final_iou": r["final_iou"], "library_launches": int(L.b200r_launch_count() - l0)}
+                     "final_iou": r["final_iou"], "library_launches": int(L.b200r_launch_count() - l0),
+                     "iou_history": [[int(i), round(float(v), 4)] for i, _, v in r["history"]]}
     if rank != 0:
         return
     best = min(out.values(), key=lambda d: d["ms_per_iter"])
@@ -574,6 +585,69 @@ def run_deform(args, rank, world, local_rank):
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": desc, "optimizer": "Adam(0.01, betas=(0.5, 0.99))", "sigma_val": 1e-4, "mode": "silhouettes"},
         "modes": out, "gpu_launches": out["eager"]["library_launches"]}), flush=True)
+
+
+def run_render(args, rank, world, local_rank):
+    """Secondary workload: BASELINE config C1, demo1-render.py:21-45 -- load the spot cow with texture_res 5 (GPU texture bake),
+    render one view per call while the camera orbits (azimuth += 4 degrees), read every image back to the host."""
+    import ctypes as C
+    import torch
+    import jrender_b200 as jr
+    from jrender_b200 import _lib
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    L = _lib.lib()
+    nf, H, bpg, desc = WORKLOADS["c1"]
+    obj = os.path.join(ASSETS, "obj", "spot", "spot_triangulated.obj")
+    if not os.path.exists(obj):
+        if rank == 0:
+            print(json.dumps({"metric": "demo1_render_frames_per_s_256px", "unavailable": "reference assets not staged (tools/stage_assets.py needs /root/reference)"}))
+        return
+    t0 = time.perf_counter()
+    mesh = jr.Mesh.from_obj(obj, load_texture=True, texture_res=5, texture_type='surface', dr_type='softras').to(dev)
+    load_s = time.perf_counter() - t0
+    renderer = jr.Renderer(dr_type='softras')
+    host = torch.empty((1, 4, H, H), dtype=torch.float32).pin_memory()
+
+    def frame(az):
+        mesh.reset_()
+        renderer.transform.set_eyes_from_angles(2.732, 30, az)
+        with torch.no_grad():
+            rgb = renderer.render_mesh(mesh, mode='rgb')
+        host.copy_(rgb, non_blocking=True)
+    for k in range(max(3, args.warmup)):
+        frame(4.0 * k)
+    torch.cuda.synchronize(dev)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    l0 = L.b200r_launch_count()
+    t0 = time.perf_counter()
+    for k, (a, b) in enumerate(ev):
+        a.record(); frame(4.0 * k); b.record()
+    torch.cuda.synchronize(dev)
+    wall = time.perf_counter() - t0
+    launches = L.b200r_launch_count() - l0
+    ms = [a.elapsed_time(b) for a, b in ev]
+    L.b200r_profile_reset(); L.b200r_profile_enable(1)
+    for k in range(5):
+        frame(4.0 * k)
+    torch.cuda.synchronize(dev); L.b200r_profile_enable(0)
+    kern = {}
+    for kid, name in [(15, "k_surface_lighting"), (11, "k_project_faces"), (0, "k_face_setup"), (1, "k_coarse_bin"), (4, "k_tile_order"), (2, "k_softras_forward")]:
+        t, n = C.c_double(0), C.c_longlong(0)
+        L.b200r_profile_read(kid, C.byref(t), C.byref(n))
+        kern[name] = {"avg_ms": t.value / max(1, n.value), "launches_per_step": n.value / 5}
+    if rank != 0:
+        return
+    cover = float((host[0, 3] > 0.5).float().mean())
+    print(json.dumps({
+        "metric": "demo1_render_frames_per_s_256px", "value": args.steps / wall, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(3, args.warmup), "ms_per_step": 1000.0 * wall / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "reference assets (baseline/_ref/assets)",
+        "config": {"workload": desc, "params": "Renderer(dr_type='softras') defaults: sigma 1e-5, gamma 1e-4, ambient 0.5 + directional 0.5, fill_back"},
+        "device_ms_per_frame": {"min": float(np.min(ms)), "median": float(np.median(ms)), "max": float(np.max(ms))},
+        "what": "host wall clock over the loop: mesh.reset_ + set_eyes + lighting + transform + rasterize (forward) + D2H of the image, one view per call",
+        "load_and_bake_s": load_s, "alpha_coverage": cover, "gpu_launches": int(launches), "kernels": kern,
+        "e2e": {"value": args.steps / wall, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 4 * H * H * 4}}), flush=True)
 
 
 def main():
@@ -596,6 +670,8 @@ def main():
     try:
         if args.workload == "c4":
             run_nmr(args, rank, world, local_rank)
+        elif args.workload == "c1":
+            run_render(args, rank, world, local_rank)
         elif args.workload == "c5":
             run_deform(args, rank, world, local_rank)
         else:

@@ -177,6 +177,35 @@ B200R_API int b200r_laplacian_loss(const float* vertices, const int32_t* neighbo
 
 /* Launch counter: number of kernels this library has launched in this process
  * (bench.py reports the delta over the timed region as "gpu_launches"). */
+/* ---- texture baking -------------------------------------------------------------
+ * Replaces _load_textures_for_softras / load_textures_cuda_kernel (jrender/io/utils/load_textures.py:3-101):
+ * image [H, W, 3] f32 (already flipped vertically by the caller, _load_obj_for_softras.py:136), faces_uv [nf, 3, 2],
+ * is_update [nf] int32, textures [nf, R*R, 3] updated in place where is_update != 0.  Device pointers. */
+B200R_API int b200r_bake_textures_softras(const float* image, const float* faces_uv, const int32_t* is_update, float* textures,
+                                          int nf, int texture_res, int image_height, int image_width, void* stream);
+
+/* ---- fused surface-mode lighting of the pre-raster stage -------------------------
+ * Replaces Lighting.execute with light_mode='surface', no normal map, no SSS, one directional light:
+ *   jrender/renderer/lighting/lighting.py:186-204, ambient_lighting.py:4-9, directional_lighting.py:54-135
+ *   (diffuse branch, and the Cook-Torrance branch when with_specular and eye / metallic / roughness are given),
+ *   surface normals of jrender/structures/mesh.py:213-229.
+ * vertices [vertices_batch, nv, 3] world space, faces [faces_batch, nf, 3] int32, textures / out_textures
+ * [B, nf, T, 3] (T = texture_res^2, or ts^3 for n3mr), metallic / roughness [B, nf, Tm] or NULL, eye [eye_batch, 3]
+ * (eye_batch 0: none).  Batches of 1 broadcast.  ambient_color, directional_color, direction: HOST pointers to 3 floats
+ * (direction already normalised).  backward overwrites grad_textures [B, nf, T, 3] and grad_vertices
+ * [vertices_batch, nv, 3] (NULL: not needed). */
+B200R_API int b200r_surface_lighting_forward(const float* vertices, const int32_t* faces, const float* textures, const float* metallic,
+                                             const float* roughness, const float* eye, float* out_textures, int B, int vertices_batch,
+                                             int faces_batch, int eye_batch, int nv, int nf, int T, int Tm, float ambient_intensity,
+                                             const float* ambient_color, float directional_intensity, const float* directional_color,
+                                             const float* direction, int with_specular, void* stream);
+B200R_API int b200r_surface_lighting_backward(const float* vertices, const int32_t* faces, const float* textures, const float* metallic,
+                                              const float* roughness, const float* eye, const float* grad_out, float* grad_textures,
+                                              float* grad_vertices, int B, int vertices_batch, int faces_batch, int eye_batch, int nv,
+                                              int nf, int T, int Tm, float ambient_intensity, const float* ambient_color,
+                                              float directional_intensity, const float* directional_color, const float* direction,
+                                              int with_specular, void* stream);
+
 B200R_API unsigned long long b200r_launch_count(void);
 
 /* Tuning knobs (process-wide; results are identical for every setting except softras_exact_tail):
@@ -195,7 +224,8 @@ B200R_API int b200r_set_option(const char* name, int value);
 enum { B200R_K_FACE_SETUP = 0, B200R_K_COARSE_BIN = 1, B200R_K_SOFTRAS_FWD = 2, B200R_K_SOFTRAS_BWD = 3,
        B200R_K_TILE_ORDER = 4, B200R_K_NMR_SETUP = 5, B200R_K_NMR_FWD = 6, B200R_K_NMR_BWD_PIXEL = 7,
        B200R_K_NMR_BWD_MAPS = 8, B200R_K_SOFTRAS_BWD_FINALIZE = 9, B200R_K_NMR_PACK = 10,
-       B200R_K_PROJECT_FWD = 11, B200R_K_PROJECT_BWD = 12, B200R_K_FLATTEN_LOSS = 13, B200R_K_LAPLACIAN_LOSS = 14 };
+       B200R_K_PROJECT_FWD = 11, B200R_K_PROJECT_BWD = 12, B200R_K_FLATTEN_LOSS = 13, B200R_K_LAPLACIAN_LOSS = 14,
+       B200R_K_LIGHTING = 15, B200R_K_BAKE = 16 };
 B200R_API void b200r_profile_enable(int on);
 B200R_API void b200r_profile_reset(void);
 B200R_API int b200r_profile_read(int kernel, double* total_ms, long long* launches);

@@ -7,7 +7,7 @@ camera / lighting / mesh / loss classes so that reference scripts port by changi
 """
 from ._lib import B200RasterError  # noqa: F401
 from .softras import SoftRasterizeFunction, SoftRasterizer, soft_rasterize  # noqa: F401
-from .mesh import Mesh, face_vertices  # noqa: F401
+from .mesh import Mesh, face_vertices, join_meshes_as_scene  # noqa: F401
 from .transform import (Transform, LookAt, Look, Projection, look_at, look, perspective, orthogonal,  # noqa: F401
                         projection, get_points_from_angles)
 from .lighting import Lighting, AmbientLighting, DirectionalLighting  # noqa: F401

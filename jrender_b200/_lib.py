@@ -67,6 +67,12 @@ def lib():
     L.b200r_flatten_loss.argtypes = [_P] * 7 + [_I, _I, _I, _F, _P]
     L.b200r_laplacian_loss.restype = _I
     L.b200r_laplacian_loss.argtypes = [_P] * 6 + [_I, _I, _I, _P]
+    L.b200r_surface_lighting_forward.restype = _I
+    L.b200r_surface_lighting_forward.argtypes = [_P] * 7 + [_I] * 8 + [_F, _P, _F, _P, _P, _I, _P]
+    L.b200r_surface_lighting_backward.restype = _I
+    L.b200r_surface_lighting_backward.argtypes = [_P] * 9 + [_I] * 8 + [_F, _P, _F, _P, _P, _I, _P]
+    L.b200r_bake_textures_softras.restype = _I
+    L.b200r_bake_textures_softras.argtypes = [_P, _P, _P, _P, _I, _I, _I, _I, _P]
     L.b200r_set_option.restype = _I
     L.b200r_set_option.argtypes = [C.c_char_p, _I]
     _lib = L

@@ -8,7 +8,7 @@ int b200r_cuda_fail(cudaError_t e, const char* what);      // records message, r
 void b200r_count_launch(void);
 
 #include "../../include/b200raster.h"  // kernel ids B200R_K_* for b200r_profile_read
-#define B200R_K_COUNT 16
+#define B200R_K_COUNT 24
 
 // When profiling is enabled (b200r_profile_enable(1)) each launch is bracketed by a pair of
 // CUDA events recorded on the launch stream; otherwise these are no-ops.

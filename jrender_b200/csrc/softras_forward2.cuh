@@ -64,15 +64,16 @@ __device__ __forceinline__ void f2_mbar_wait(unsigned long long* bar, uint32_t p
 // async-proxy writes of the next bulk copies
 __device__ __forceinline__ void f2_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-struct Fwd2Smem {
-    FaceRecS rec[B200R_F2_R];                    // staged records; reused as the output staging area
+struct __align__(16) Fwd2Smem {
+    FaceRecS rec[B200R_F2_R];                    // staged records (16-byte aligned: bulk-copy destination); reused as the output staging area
+    __align__(16) uint32_t lmask[B200R_F2_R];    // per staged record: the lanes (pixels) inside its rectangle (read as uint4)
+    __align__(16) float2 res[B200R_F2_PMAX];     // pair -> (D, zp);  D == -1: the pair contributes nothing (:333/:337/:343)
     unsigned long long mbar;
     int ids[B200R_F2_R + 4 * 32];                // pending block-face ids, ascending
-    uint32_t lmask[B200R_F2_R];                  // per staged record: the lanes (pixels) inside its rectangle
     unsigned short plist[B200R_F2_PMAX];         // pair -> (record slot << 5) | lane, pixel-major
     unsigned short ilist[B200R_F2_PMAX];         // pairs set aside for the "strictly inside" distance path
-    float2 res[B200R_F2_PMAX];                   // pair -> (D, zp);  D == -1: the pair contributes nothing (:333/:337/:343)
 };
+static_assert(sizeof(Fwd2Smem) % 16 == 0, "the top-K depth lists behind Fwd2Smem are read with 16-byte loads");
 
 static inline size_t fwd2_smem_bytes(int K) {
     const size_t b = sizeof(Fwd2Smem) + (size_t)32 * (fwd_qz_stride(K) + K) * 4;

@@ -45,38 +45,31 @@ def _imread_rgb01(path):
     return img.astype(np.float32) / 255.
 
 
-def bake_textures_for_softras(image, faces_uv, textures, is_update):
-    """numpy restatement of load_textures_cuda_kernel (load_textures.py:11-69).
+def bake_textures_for_softras(image, faces_uv, textures, is_update, device=None):
+    """_load_textures_for_softras (load_textures.py:3-101) through the CUDA kernel b200r_bake_textures_softras.
 
-    image [H,W,3] (already flipped vertically by the caller), faces_uv [nf,3,2],
-    textures [nf,R*R,3] (returned updated where is_update != 0)."""
-    nf, T = textures.shape[:2]
-    R = int(np.sqrt(T))
-    H, W = image.shape[:2]
-    wy, wx = np.divmod(np.arange(T), R)
-    lower = (wx + wy) < R
-    w0 = np.where(lower, (wx + 1. / 3.) / R, ((R - 1. - wx) + 2. / 3.) / R).astype(np.float32)
-    w1 = np.where(lower, (wy + 1. / 3.) / R, ((R - 1. - wy) + 2. / 3.) / R).astype(np.float32)
-    w2 = (1. - w0.astype(np.float64) - w1.astype(np.float64)).astype(np.float32)
-    f = faces_uv.astype(np.float32)
-    pos_x = ((f[:, None, 0, 0] * w0 + f[:, None, 1, 0] * w1 + f[:, None, 2, 0] * w2) * np.float32(W - 1)).astype(np.float32)
-    pos_y = ((f[:, None, 0, 1] * w0 + f[:, None, 1, 1] * w1 + f[:, None, 2, 1] * w2) * np.float32(H - 1)).astype(np.float32)
-    ix, iy = pos_x.astype(np.int64), pos_y.astype(np.int64)       # C truncation; UVs are >= 0
-    wx1 = pos_x - ix
-    wx0 = 1 - wx1
-    wy1 = pos_y - iy
-    wy0 = 1 - wy1
-    flat = image.reshape(-1, 3)
-    n = flat.shape[0]
-    iy1 = (pos_y + 1).astype(np.int64)
+    image [H,W,3] (already flipped vertically by the caller), faces_uv [nf,3,2], textures [nf,R*R,3], is_update [nf]:
+    numpy arrays or tensors; returns a CUDA float32 tensor [nf,R*R,3] (updated where is_update != 0).
+    There is no CPU implementation in the product (oracle/bake.py is the checker)."""
+    import ctypes as C
+    from . import _lib
+    if not torch.cuda.is_available():
+        raise _lib.B200RasterError("texture baking runs on the GPU (b200r_bake_textures_softras); there is no CPU fallback")
+    dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
 
-    def px(yy, xx):  # the reference indexes the flat buffer without clamping; keep in-bounds here
-        return flat[np.clip(yy * W + xx, 0, n - 1)]
-    c = (px(iy, ix) * (wx0 * wy0)[..., None] + px(iy1, ix) * (wx0 * wy1)[..., None] +
-         px(iy, ix + 1) * (wx1 * wy0)[..., None] + px(iy1, ix + 1) * (wx1 * wy1)[..., None]).astype(np.float32)
-    out = textures.copy()
-    m = np.asarray(is_update) != 0
-    out[m] = c[m]
+    def dv(x, dtype):
+        t = x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x))
+        return t.to(device=dev, dtype=dtype).contiguous()
+    img, uv, upd = dv(image, torch.float32), dv(faces_uv, torch.float32), dv(is_update, torch.int32)
+    out = dv(textures, torch.float32).clone()
+    nf, T = out.shape[:2]
+    R = int(round(float(np.sqrt(T))))
+    if R * R != T or uv.shape != (nf, 3, 2) or img.dim() != 3 or img.shape[2] != 3 or upd.shape != (nf,):
+        raise ValueError("bake_textures_for_softras: image [H,W,3], faces_uv [nf,3,2], textures [nf,R*R,3], is_update [nf]")
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().b200r_bake_textures_softras(
+            C.c_void_p(img.data_ptr()), C.c_void_p(uv.data_ptr()), C.c_void_p(upd.data_ptr()), C.c_void_p(out.data_ptr()),
+            nf, R, img.shape[0], img.shape[1], C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "b200r_bake_textures_softras")
     return out
 
 
@@ -112,6 +105,8 @@ def load_textures(filename_obj, filename_mtl, texture_res):
     for material_name, filename_texture in texture_filenames.items():
         image = _imread_rgb01(os.path.join(os.path.dirname(filename_obj), filename_texture))[::-1, :, :]
         textures = bake_textures_for_softras(np.ascontiguousarray(image), faces_uv, textures, (names == material_name).astype(np.int32))
+    if isinstance(textures, torch.Tensor):   # baked on the GPU; loaders hand back host arrays like the geometry
+        textures = textures.cpu().numpy()
     return textures
 
 

@@ -1,5 +1,5 @@
-"""Lighting (host-side mirror in PyTorch; O(nf) elementwise work before the rasterizer, no
-custom kernels -- SURVEY.md section 2.1 marks it "next / out of scope for kernels").
+"""Lighting: the surface-mode path (the renderer's default) runs as ONE fused kernel forward and one backward
+(csrc/lighting_api.cu); everything else is the op-by-op PyTorch mirror below.
 
 Mirrors jrender/renderer/lighting/{ambient_lighting,directional_lighting,lighting}.py for the
 paths the rasterizer demos use: ambient + directional light in 'surface' and 'vertex' modes,
@@ -7,9 +7,13 @@ including the Cook-Torrance specular branch the reference takes by default
 (Mesh.with_specular defaults to True, structures/mesh.py:74).  Normal-mapped meshes
 (surface_ResNormals), SSS and the Gbuffer debug modes are not mirrored.
 """
+import ctypes as C
+
 import torch
 from torch import nn
 import torch.nn.functional as F
+
+from . import _lib
 
 
 _CONST = {}
@@ -114,6 +118,61 @@ def directional_lighting(diffuseLight, specularLight, normals, light_intensity=0
     return [diffuseLight, specularLight]
 
 
+def _f3(x):
+    """3 host floats as a ctypes array (light colours / direction are Python constants in the reference's API)."""
+    if isinstance(x, torch.Tensor):
+        x = x.detach().cpu().tolist()
+    x = [float(v) for v in x]
+    if len(x) != 3:
+        raise ValueError("expected 3 components, got %r" % (x,))
+    return (C.c_float * 3)(*x)
+
+
+class _FusedSurfaceLighting(torch.autograd.Function):
+    """clamp(textures * diffuse + specular, 0, 1) with diffuse / specular from the face normals: b200r_surface_lighting_*."""
+
+    @staticmethod
+    def forward(ctx, vertices, textures, faces, metallic, roughness, eye, params):
+        dev = vertices.device
+        v = vertices.contiguous()
+        tx = textures.contiguous()
+        B, nf = tx.shape[0], tx.shape[1]
+        T = tx[0, 0].numel() // 3
+        Tm = 0 if metallic is None else metallic[0, 0].numel()
+        out = torch.empty_like(tx)
+        amb_i, amb_c, dir_i, dir_c, direction, with_spec = params
+        args = (B, v.shape[0], faces.shape[0], 0 if eye is None else eye.shape[0], v.shape[1], nf, T, Tm,
+                float(amb_i), _f3(amb_c), float(dir_i), _f3(dir_c), _f3(direction), int(bool(with_spec)))
+        with torch.cuda.device(dev):
+            st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            p = lambda t: C.c_void_p(0 if t is None else t.data_ptr())   # noqa: E731
+            _lib.check(_lib.lib().b200r_surface_lighting_forward(p(v), p(faces), p(tx), p(metallic), p(roughness), p(eye), p(out), *args, st),
+                       "b200r_surface_lighting_forward")
+        ctx.save_for_backward(v, tx, faces, metallic, roughness, eye)
+        ctx.args = args
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        v, tx, faces, metallic, roughness, eye = ctx.saved_tensors
+        dev = v.device
+        g = grad_out.contiguous()
+        gt = torch.empty_like(tx)
+        gv = torch.empty_like(v) if ctx.needs_input_grad[0] else None
+        with torch.cuda.device(dev):
+            st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            p = lambda t: C.c_void_p(0 if t is None else t.data_ptr())   # noqa: E731
+            _lib.check(_lib.lib().b200r_surface_lighting_backward(p(v), p(faces), p(tx), p(metallic), p(roughness), p(eye), p(g), p(gt), p(gv),
+                                                                  *ctx.args, st), "b200r_surface_lighting_backward")
+        return gv, (gt if ctx.needs_input_grad[1] else None), None, None, None, None, None
+
+
+def _normalized_direction(d):
+    """F.normalize(light_direction, dim=0, eps=1e-12) on the host, in float32 like the mirror."""
+    t = torch.tensor([float(x) for x in (d.detach().cpu().tolist() if isinstance(d, torch.Tensor) else d)], dtype=torch.float32)
+    return F.normalize(t, dim=0, eps=1e-12).tolist()
+
+
 class AmbientLighting(nn.Module):
     def __init__(self, light_intensity=0.5, light_color=(1, 1, 1)):
         super(AmbientLighting, self).__init__()
@@ -160,9 +219,53 @@ class Lighting(nn.Module):
         self.ambient = AmbientLighting(intensity_ambient, color_ambient)
         self.directionals = nn.ModuleList([DirectionalLighting(intensity_directionals, color_directionals, directions)])
 
+    fused = True   # CUDA float32 surface-mode inputs take the one-launch kernel (b200r_surface_lighting_forward)
+
+    def _fusable(self, mesh, eyes):
+        tx, v = mesh.textures, mesh.vertices
+        if not (self.fused and len(self.directionals) == 1 and tx.is_cuda and v.is_cuda and tx.device == v.device):
+            return False
+        if tx.dtype != torch.float32 or v.dtype != torch.float32 or tx.dim() not in (4, 6) or tx.shape[-1] != 3:
+            return False
+        if mesh.faces.device != v.device or mesh.faces.dim() != 3 or mesh.faces.shape[1] != tx.shape[1]:
+            return False
+        d = self.directionals[0]
+        for c in (self.ambient.light_color, d.light_color, d.light_direction):
+            n = c.numel() if isinstance(c, torch.Tensor) else len(c)
+            if n != 3:   # per-batch light colours / directions: op-by-op path
+                return False
+        for t in (mesh.metallic_textures, mesh.roughness_textures):
+            if t is not None and (t.requires_grad or t.device != v.device or t.dtype != torch.float32
+                                  or t.shape[:2] != tx.shape[:2] or t.shape[-1] != 1):
+                return False
+        if isinstance(eyes, torch.Tensor) and eyes.requires_grad:
+            return False
+        return True
+
+    def _fused_surface(self, mesh, eyes):
+        v = mesh.vertices
+        d = self.directionals[0]
+        eye = None
+        spec = bool(mesh.with_specular) and eyes is not None and mesh.metallic_textures is not None and mesh.roughness_textures is not None
+        if spec:
+            eye = _t(eyes, v).reshape(-1, 3).contiguous()
+            if eye.shape[0] not in (1, mesh.textures.shape[0]):
+                return None
+        faces = mesh.faces if mesh.faces.dtype == torch.int32 else mesh.faces.int()
+        params = (self.ambient.light_intensity, self.ambient.light_color, d.light_intensity, d.light_color,
+                  _normalized_direction(d.light_direction), spec)
+        return _FusedSurfaceLighting.apply(v, mesh.textures, faces.contiguous(),
+                                           mesh.metallic_textures.contiguous() if spec else None,
+                                           mesh.roughness_textures.contiguous() if spec else None, eye, params)
+
     def forward(self, mesh, eyes=None):
         if self.Gbuffer == "albedo":
             return mesh
+        if self.light_mode == 'surface' and self._fusable(mesh, eyes):
+            lit = self._fused_surface(mesh, eyes)
+            if lit is not None:
+                mesh.textures = lit
+                return mesh
         if self.light_mode == 'surface':
             diffuseLight = torch.zeros(mesh.faces.shape, dtype=torch.float32, device=mesh.vertices.device)
             specularLight = torch.zeros_like(diffuseLight)

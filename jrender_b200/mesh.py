@@ -229,6 +229,16 @@ class Mesh(object):
             textures = None
         return cls(vertices, faces, textures, texture_res, texture_type, dr_type=dr_type, with_SSS=with_SSS)
 
+    def save_obj(self, filename_obj, save_texture=False, texture_res_out=16):
+        """structures/mesh.py:330-338.  Geometry only: the texture-atlas export (io/save_obj.py:9-29, a separate CUDA
+        kernel of the reference) is outside this repo's scope."""
+        if self.batch_size != 1:
+            raise ValueError('Could not save when batch size >= 1')
+        if save_texture:
+            raise NotImplementedError("save_obj(save_texture=True): texture-atlas export is not part of the rasterizer hot path")
+        from .io import save_obj
+        save_obj(filename_obj, self.vertices[0], self.faces[0])
+
     def to(self, device):
         self._vertices = self.vertices.to(device)
         self._projector = None
@@ -242,3 +252,23 @@ class Mesh(object):
 
     def cuda(self):
         return self.to(torch.device("cuda"))
+
+
+def join_meshes_as_scene(meshes, include_texture=True):
+    """structures/mesh.py:345-374: one mesh whose vertices / faces (/ textures) are the inputs' concatenated along the
+    vertex / face axis, face indices shifted by the running vertex count."""
+    verts = [m.vertices for m in meshes]
+    faces, shift = [], 0
+    for m in meshes:
+        faces.append(m.faces + shift)
+        shift += m.vertices.shape[1]
+    vert, face = torch.cat(verts, dim=1), torch.cat(faces, dim=1)
+    if not include_texture:
+        return Mesh(vert, face)
+    # a Mesh built without textures carries all-ones defaults here (the reference keeps None): treat "every mesh has
+    # textures" as the textured case, exactly like the reference when all inputs were given textures
+    first = meshes[0]
+    if not all(m.dr_type == first.dr_type and m.texture_type == first.texture_type for m in meshes):
+        raise ValueError("Inconsistent textures in join_meshes_as_scene (dr_type or texture_type).")
+    tex = torch.cat([m.textures for m in meshes], dim=1)
+    return Mesh(vertices=vert, faces=face, textures=tex, texture_type=first.texture_type, dr_type=first.dr_type)

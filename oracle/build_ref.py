@@ -274,6 +274,21 @@ extern "C" int ref_nmr_backward_depth_map(const float* faces, const float* depth
 '''
 
 
+LAUNCH_BAKE = r'''
+// ---- launcher: restates cuda_src of _load_textures_for_softras (io/utils/load_textures.py:71-98)
+extern "C" int ref_bake_textures_softras(const float* image, const float* faces, const int32_t* is_update, float* textures,
+                                         int nf, int texture_res, int image_height, int image_width) {
+    const size_t texture_size = (size_t)nf * texture_res * texture_res * 3;   // textures->num
+    const int threads = 1024;
+    const dim3 blocks((unsigned)((texture_size / 3 - 1) / threads + 1));
+    load_textures_cuda_kernel<float32><<<blocks, threads>>>(image, faces, is_update, textures, texture_size, (size_t)texture_res,
+                                                            (size_t)image_height, (size_t)image_width);
+    cudaError_t e = cudaDeviceSynchronize();
+    return (int)(e != cudaSuccess ? e : cudaGetLastError());
+}
+'''
+
+
 def generate():
     os.makedirs(OUT, exist_ok=True)
     base = os.path.join(REFERENCE, "jrender/renderer/dr/softras/cuda")
@@ -296,6 +311,8 @@ def generate():
     files.append(("ref_nmr_k10.cu", PREAMBLE + hdr + LAUNCH_NMR_K10))
     hdr = _capture(nmr, "backward_depth_map", 7, extra=[64])
     files.append(("ref_nmr_k11.cu", PREAMBLE + hdr + LAUNCH_NMR_K11))
+    hdr = _capture(os.path.join(REFERENCE, "jrender/io/utils/load_textures.py"), "_load_textures_for_softras", 4)
+    files.append(("ref_bake.cu", PREAMBLE + hdr + LAUNCH_BAKE))
     paths = []
     for name, text in files:
         p = os.path.join(OUT, name)

@@ -115,11 +115,39 @@ def nmr_main(out_dir, report):
         print(json.dumps(r), flush=True)
 
 
+def bake_main(out_dir):
+    """Reference texture-bake kernel (io/utils/load_textures.py:3-101 via oracle/build_ref.py) on seeded inputs ->
+    ref_gpu_bake_random40_R5.npz; prints the difference to the numpy oracle (oracle/bake.py)."""
+    import ctypes as C
+    from oracle import bake as obake
+    rng = np.random.default_rng(7)
+    nf, R, H, W = 40, 5, 24, 40
+    image = rng.random((H, W, 3), dtype=np.float32)
+    uv = rng.uniform(0.02, 0.95, (nf, 3, 2)).astype(np.float32)
+    upd = (rng.random(nf) > 0.2).astype(np.int32)
+    tex0 = np.full((nf, R * R, 3), 0.5, np.float32)
+    L = ref_gpu.lib()
+    L.ref_bake_textures_softras.restype = C.c_int
+    L.ref_bake_textures_softras.argtypes = [C.c_void_p] * 4 + [C.c_int] * 4
+    dev = torch.device("cuda:0")
+    t = [torch.from_numpy(a).to(dev) for a in (image, uv, upd, tex0)]
+    rc = L.ref_bake_textures_softras(*[C.c_void_p(x.data_ptr()) for x in t], nf, R, H, W)
+    assert rc == 0, rc
+    ref = t[3].cpu().numpy()
+    cpu = obake.bake_textures_for_softras(image, uv, tex0, upd)
+    np.savez_compressed(os.path.join(out_dir, "ref_gpu_bake_random40_R5.npz"), image=image, faces_uv=uv, is_update=upd, textures_in=tex0,
+                        textures=ref, provenance=json.dumps(dict(gpu=torch.cuda.get_device_name(0), source="jrender/io/utils/load_textures.py:3-101 via oracle/build_ref.py")))
+    print(json.dumps(dict(name="bake_random40_R5", max_abs_vs_oracle=float(np.abs(ref - cpu).max()))), flush=True)
+
+
 def main():
     import torch
     out_dir = os.path.join("gpurun_out", "golden")
     os.makedirs(out_dir, exist_ok=True)
     report = []
+    if "--bake-only" in sys.argv:
+        bake_main(out_dir)
+        return
     if "--nmr-only" in sys.argv:
         nmr_main(out_dir, report)
         json.dump(report, open(os.path.join(out_dir, "report_nmr.json"), "w"), indent=1)

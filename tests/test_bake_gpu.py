@@ -1,0 +1,77 @@
+"""GPU tests of the texture-bake kernel (csrc/bake_api.cu <- jrender/io/utils/load_textures.py:3-101) and of BASELINE
+config C1 as the reference configures it (demo1-render.py:21-45: spot cow, 5856 faces, texture_res 5, 256^2).
+
+Tolerances: bake vs the numpy oracle 2e-6 absolute (same formulas unfused on both sides; image values in [0, 1]); vs the
+reference's own kernel on a B200 (tests/golden/ref_gpu_bake_random40_R5.npz) 1e-5 (its build contracts a*b+c).
+C1: top-K ids bit-exact, colours 2e-6, gradients 2e-5 of max -- the SoftRas parity bar (tests/test_softras_gpu.py).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import jrender_b200 as jr
+from oracle import bake as obake
+from oracle import softras as osr
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = os.path.join(ROOT, "tests", "golden")
+SPOT = os.path.join(ROOT, "baseline", "_ref", "assets", "data", "obj", "spot", "spot_triangulated.obj")
+
+
+def test_bake_kernel_matches_oracle_and_reference_kernel(cuda_device):
+    from jrender_b200.io import bake_textures_for_softras
+    rng = np.random.default_rng(3)
+    for nf, R, H, W in ((40, 5, 24, 40), (257, 1, 7, 9), (33, 4, 64, 64)):
+        image = rng.random((H, W, 3), dtype=np.float32)
+        uv = rng.uniform(0.0, 1.0, (nf, 3, 2)).astype(np.float32)      # includes taps on the last row / column
+        upd = (rng.random(nf) > 0.3).astype(np.int32)
+        tex0 = rng.random((nf, R * R, 3), dtype=np.float32)
+        got = bake_textures_for_softras(image, uv, tex0, upd, device=cuda_device).cpu().numpy()
+        ref = obake.bake_textures_for_softras(image, uv, tex0, upd)
+        assert np.abs(got - ref).max() <= 2e-6
+        assert np.array_equal(got[upd == 0], tex0[upd == 0])
+    p = os.path.join(G, "ref_gpu_bake_random40_R5.npz")
+    if os.path.exists(p):
+        g = np.load(p)
+        got = bake_textures_for_softras(g["image"], g["faces_uv"], g["textures_in"], g["is_update"], device=cuda_device).cpu().numpy()
+        assert np.abs(got - g["textures"]).max() <= 1e-5
+
+
+@pytest.mark.skipif(not os.path.exists(SPOT), reason="reference assets not staged (python -m tools.stage_assets where /root/reference exists)")
+def test_c1_spot_render_as_demo1_against_oracle(cuda_device):
+    """demo1-render.py: Mesh.from_obj(load_texture=True, texture_res=5) -> Renderer(dr_type='softras') -> render_mesh('rgb').
+    The rasterizer's inputs (projected face vertices, lit T=25 textures) are taken from the pipeline and handed to the
+    CPU oracle; forward compared in full, backward on every 16th row."""
+    mesh = jr.Mesh.from_obj(SPOT, load_texture=True, texture_res=5, texture_type='surface', dr_type='softras').to(cuda_device)
+    assert mesh.faces.shape[1] == 5856 and tuple(mesh.textures.shape) == (1, 5856, 25, 3)
+    renderer = jr.Renderer(dr_type='softras')
+    renderer.transform.set_eyes_from_angles(2.732, 30, 0)
+    mesh.reset_()
+    tex_leaf = mesh.textures.detach().clone().requires_grad_(True)
+    mesh.textures = tex_leaf
+    img = renderer.render_mesh(mesh, mode='rgb')
+    assert tuple(img.shape) == (1, 4, 256, 256)
+    fv = mesh.face_vertices.detach().cpu().numpy()
+    lit = mesh.textures.detach().cpu().numpy()
+    assert 0.05 < float((img[0, 3] > 0.5).float().mean()) < 0.6 and float(lit.std()) > 0.05     # the cow is there, textured
+    P = osr.Params(image_size=256)
+    ref = osr.forward(fv, lit, P)
+    fn = jr.SoftRasterizeFunction(image_size=256)
+    fvt = torch.from_numpy(fv).to(cuda_device).requires_grad_(True)
+    txt = torch.from_numpy(lit).to(cuda_device).requires_grad_(True)
+    sc, ag, ids = fn.raw(fvt, txt)
+    assert np.array_equal(ids.cpu().numpy(), ref["faces_id_buffer"])
+    assert np.abs(sc.detach().cpu().numpy() - ref["soft_colors"]).max() <= 2e-6
+    assert np.abs(img.detach().cpu().numpy() - ref["soft_colors"]).max() <= 2e-6      # the Renderer returned the same image
+    g = np.zeros((1, 4, 256, 256), np.float32)
+    g[:, :, ::16] = np.random.default_rng(1).uniform(-1, 1, (1, 4, 16, 256)).astype(np.float32)
+    sc.backward(torch.from_numpy(g).to(cuda_device))
+    rgf, rgt = osr.backward(fv, lit, ref, g, P, accumulate_double=True, row_stride=16)
+    assert np.abs(fvt.grad.cpu().numpy() - rgf).max() <= 2e-5 * np.abs(rgf).max()
+    assert np.abs(txt.grad.cpu().numpy() - rgt).max() <= 2e-5 * np.abs(rgt).max()
+    # gradient reaches the un-lit texture leaf through the fused lighting kernel
+    img.backward(torch.from_numpy(g).to(cuda_device))
+    assert tex_leaf.grad is not None and float(tex_leaf.grad.abs().max()) > 0

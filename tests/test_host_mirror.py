@@ -106,7 +106,7 @@ def test_obj_roundtrip_and_texture_bake(tmp_path):
     v2, f2 = jr.load_obj(p)
     assert np.allclose(v2.numpy(), v, atol=1e-6) and np.array_equal(f2.numpy(), f)
     # texture bake: a constant image bakes to that constant; a horizontal ramp to the texel's u
-    from jrender_b200.io import bake_textures_for_softras
+    from oracle.bake import bake_textures_for_softras   # the CPU checker; the product bakes on the GPU (tests/test_bake_gpu.py)
     img = np.full((16, 32, 3), 0.25, np.float32)
     uv = np.random.default_rng(0).uniform(0.05, 0.9, (10, 3, 2)).astype(np.float32)
     out = bake_textures_for_softras(img, uv, np.ones((10, 9, 3), np.float32), np.ones(10, np.int32))
