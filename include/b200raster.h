@@ -61,11 +61,15 @@ enum { B200R_TEX_SURFACE = 0, B200R_TEX_VERTEX = 1 };
 B200R_API const char* b200r_version(void);
 B200R_API const char* b200r_last_error(void);
 
-/* Bytes of device scratch the SoftRas forward needs for (batch, num_faces, image_size).
- * The same buffer must be handed to the backward (it holds the per-face records the
- * reference keeps in `faces_info`, soft_rasterize.py:62,101, and a gradient-accumulator region the
- * backward uses as scratch). */
+/* Device memory of one forward / backward pair, in two caller-allocated blocks:
+ *   state      b200r_softras_state_bytes(batch, num_faces): written by the forward, handed to the backward -- the per-face
+ *              records (what the reference keeps in `faces_info`, soft_rasterize.py:62,101) and the backward's gradient
+ *              accumulator.  208 bytes per (batch, face).
+ *   workspace  b200r_softras_workspace_bytes(batch, num_faces, image_size): transient scratch of the forward only (binning
+ *              lists with capacity num_faces per 64-pixel bin so that nothing can overflow, tile queue); free to be
+ *              released or reused once the forward has been enqueued. */
 B200R_API size_t b200r_softras_workspace_bytes(int batch_size, int num_faces, int image_size);
+B200R_API size_t b200r_softras_state_bytes(int batch_size, int num_faces);
 
 /* SoftRas forward.
  *   face_vertices  [B, nf, 3, 3]  NDC x,y (+y up) and camera-space z per vertex
@@ -79,7 +83,8 @@ B200R_API size_t b200r_softras_workspace_bytes(int batch_size, int num_faces, in
  * Background colour is always 0, as in the reference (the op memsets soft_colors). */
 B200R_API int b200r_softras_forward(const float* face_vertices, const float* textures,
                           float* soft_colors, float* aggrs_info, int32_t* faces_id_buffer,
-                          float* faces_info, void* workspace, size_t workspace_bytes,
+                          float* faces_info, void* state, size_t state_bytes,
+                          void* workspace, size_t workspace_bytes,
                           int batch_size, int num_faces, int texture_size, int image_size,
                           int max_faces_per_pixel, float near, float far, float eps,
                           float sigma_val, float gamma_val, float dist_eps_logit,
@@ -90,8 +95,33 @@ B200R_API int b200r_softras_forward(const float* face_vertices, const float* tex
  * are overwritten (zeroed inside, then accumulated). */
 B200R_API int b200r_softras_backward(const float* face_vertices, const float* textures,
                            const float* soft_colors, const float* aggrs_info,
-                           const int32_t* faces_id_buffer, void* workspace,
-                           size_t workspace_bytes, const float* grad_soft_colors,
+                           const int32_t* faces_id_buffer, void* state,
+                           size_t state_bytes, const float* grad_soft_colors,
+                           float* grad_face_vertices, float* grad_textures,
+                           int batch_size, int num_faces, int texture_size, int image_size,
+                           int max_faces_per_pixel, float near, float far, float eps,
+                           float sigma_val, float gamma_val, float dist_eps_logit,
+                           int dist_func, int rgb_func, int alpha_func, int texture_type,
+                           int double_side, void* stream);
+
+/* Anti-aliased flavours: replace SoftRasterizer.execute's "render at 2 x image_size, then
+ * 2x2 mean-pool" (jrender/renderer/dr/softras/rasterizer.py:45,54-55) without the extra passes.  image_size is the
+ * SUPERSAMPLED size (even).  forward_aa additionally writes pooled_colors [B,4,image_size/2,image_size/2], the 2x2 means of
+ * soft_colors, from the forward kernel's output staging (soft_colors is still written: the backward reads it);
+ * backward_aa takes grad_pooled_colors [B,4,image_size/2,image_size/2] and forms avg_pool2d's backward (grad / 4 at each
+ * of the four source pixels) while loading, instead of materialising a 4x larger gradient tensor. */
+B200R_API int b200r_softras_forward_aa(const float* face_vertices, const float* textures, float* soft_colors,
+                           float* pooled_colors, float* aggrs_info, int32_t* faces_id_buffer, float* faces_info,
+                           void* state, size_t state_bytes, void* workspace, size_t workspace_bytes,
+                           int batch_size, int num_faces, int texture_size, int image_size,
+                           int max_faces_per_pixel, float near, float far, float eps,
+                           float sigma_val, float gamma_val, float dist_eps_logit,
+                           int dist_func, int rgb_func, int alpha_func, int texture_type,
+                           int double_side, void* stream);
+B200R_API int b200r_softras_backward_aa(const float* face_vertices, const float* textures,
+                           const float* soft_colors, const float* aggrs_info,
+                           const int32_t* faces_id_buffer, void* state,
+                           size_t state_bytes, const float* grad_pooled_colors,
                            float* grad_face_vertices, float* grad_textures,
                            int batch_size, int num_faces, int texture_size, int image_size,
                            int max_faces_per_pixel, float near, float far, float eps,
@@ -209,13 +239,12 @@ B200R_API int b200r_surface_lighting_backward(const float* vertices, const int32
 B200R_API unsigned long long b200r_launch_count(void);
 
 /* Tuning knobs (process-wide; results are identical for every setting except softras_exact_tail):
- *   "softras_fwd_variant"    0 = warp-uniform face loop, 1 = per-lane face lists (default)
+ *   "softras_fwd_variant"    1 = lanes walk private face lists in lock-step (default), 2 = two-phase (compacted pair
+ *                            list + TMA record staging; measured slower at C3 / C5, kept selectable for A/B)
  *   "softras_fwd_persistent" 0 = one CTA per tile, 1 = persistent grid + tile queue (default)
- *   "softras_fwd_warps"      warps per forward CTA: 8 (16x16 tiles), 2 (16x4), 1 (8x4, warp-autonomous)
  *   "softras_exact_tail"     1 = the reference's double-precision sigmoid / alpha-product tails bit for bit;
  *                            0 (default) = the same expressions in fp32 for the default euclidean+softmax
- *                            mode (<= 1 ulp on D; all index / depth outputs are identical either way)
- *   "softras_bwd_variant"    0 = warp union walk + scalar atomics, 1 = per-lane walk + 16-byte atomics (default) */
+ *                            mode (<= 1 ulp on D; all index / depth outputs are identical either way) */
 B200R_API int b200r_set_option(const char* name, int value);
 
 /* Per-kernel device timing (CUDA events recorded on the launch stream around every kernel

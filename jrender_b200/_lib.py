@@ -39,10 +39,16 @@ def lib():
     L.b200r_launch_count.restype = C.c_ulonglong
     L.b200r_softras_workspace_bytes.restype = C.c_size_t
     L.b200r_softras_workspace_bytes.argtypes = [_I, _I, _I]
+    L.b200r_softras_state_bytes.restype = C.c_size_t
+    L.b200r_softras_state_bytes.argtypes = [_I, _I]
     L.b200r_softras_forward.restype = _I
-    L.b200r_softras_forward.argtypes = [_P, _P, _P, _P, _P, _P, _P, C.c_size_t] + _SOFTRAS_SCALARS
+    L.b200r_softras_forward.argtypes = [_P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P, C.c_size_t] + _SOFTRAS_SCALARS
     L.b200r_softras_backward.restype = _I
     L.b200r_softras_backward.argtypes = [_P, _P, _P, _P, _P, _P, C.c_size_t, _P, _P, _P] + _SOFTRAS_SCALARS
+    L.b200r_softras_forward_aa.restype = _I
+    L.b200r_softras_forward_aa.argtypes = [_P, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P, C.c_size_t] + _SOFTRAS_SCALARS
+    L.b200r_softras_backward_aa.restype = _I
+    L.b200r_softras_backward_aa.argtypes = [_P, _P, _P, _P, _P, _P, C.c_size_t, _P, _P, _P] + _SOFTRAS_SCALARS
     L.b200r_profile_enable.restype = None
     L.b200r_profile_enable.argtypes = [_I]
     L.b200r_profile_reset.restype = None

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libb200raster.so")
-SOURCES = ["softras_api.cu", "softras_fwd_nw8.cu", "softras_fwd_nw2.cu", "softras_fwd_nw1.cu", "softras_bwd.cu",
+SOURCES = ["softras_api.cu", "softras_fwd.cu", "softras_bwd.cu",
            "nmr_api.cu", "preraster_api.cu", "mesh_loss_api.cu", "lighting_api.cu", "bake_api.cu", "api_util.cu", "debug_api.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]

@@ -47,11 +47,18 @@ struct SoftRasParams {
     int coarse_px;  // coarse bin edge in pixels (multiple of B200R_TILE)
     int ncs;        // coarse bins per image side
     int queue_len;    // persistent scheduler: entries of tile_order (>= tiles; holes are -1)
+    int aa;           // backward: grad_soft_colors is the gradient of the 2x2-mean-pooled image [B,4,is/2,is/2] (anti-aliasing prologue)
 };
 
-// Workspace carve-up (all offsets 256-byte aligned).
+// Device memory of one forward / backward pair, in two caller-allocated blocks (all offsets 256-byte aligned):
+//   state     kept from the forward to the backward: the face records and the backward's gradient accumulator
+//             (B*nf*208 bytes -- the reference keeps faces_info, 108 bytes per face, for the same purpose)
+//   workspace transient scratch of the forward only (binning lists, tile queue): may be freed / reused as soon as the
+//             forward has been enqueued
 struct SoftRasWorkspace {
-    FaceRec* recs;       // [B*nf]
+    FaceRec* recs;       // [B*nf]                                                               (state)
+    float* gacc;         // [B*nf][12] backward gradient accumulator (3 x float4 per face)        (state)
+    size_t state_bytes;
     uint2* rects;        // [B*nf]  (rect_x, rect_r) copy for the binning scans
     uint2* chunk_rects;  // [B*ceil(nf/256)] union rectangle of each run of 256 consecutive faces
     int* coarse_cnt;     // [B*ncs*ncs]
@@ -59,8 +66,7 @@ struct SoftRasWorkspace {
     int* counters;       // [256] scheduler state, zeroed per launch: [0] queue head, [64..127] cost histogram, [128..191] scatter cursors
     int* tile_cost;      // [B*max_tiles] (pixel, face) pairs per forward tile (smallest tile 8x4)
     int* tile_order;     // [B*max_tiles] tile ids, most expensive first
-    float* gacc;         // [B*nf][12] backward gradient accumulator (3 x float4 per face)
-    size_t bytes;
+    size_t bytes;        // of the workspace block
 };
 
 static inline size_t b200r_align256(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -74,14 +80,19 @@ static inline void b200r_geometry(int image_size, int* ntx, int* coarse_px, int*
     *ncs = (image_size + *coarse_px - 1) / *coarse_px;
 }
 
-static inline SoftRasWorkspace b200r_carve(void* base, int B, int nf, int image_size) {
+static inline SoftRasWorkspace b200r_carve(void* state, void* base, int B, int nf, int image_size) {
     int ntx, cpx, ncs;
     b200r_geometry(image_size, &ntx, &cpx, &ncs);
     SoftRasWorkspace w;
     size_t off = 0;
-    char* p = (char*)base;
+    char* p = (char*)state;
     w.recs = (FaceRec*)(p + off);
     off += b200r_align256((size_t)B * nf * sizeof(FaceRec));
+    w.gacc = (float*)(p + off);
+    off += b200r_align256((size_t)B * nf * 12 * sizeof(float));
+    w.state_bytes = off;
+    off = 0;
+    p = (char*)base;
     w.rects = (uint2*)(p + off);
     off += b200r_align256((size_t)B * nf * sizeof(uint2));
     w.chunk_rects = (uint2*)(p + off);
@@ -97,9 +108,15 @@ static inline SoftRasWorkspace b200r_carve(void* base, int B, int nf, int image_
     off += b200r_align256((size_t)B * max_tiles * sizeof(int));
     w.tile_order = (int*)(p + off);
     off += b200r_align256((size_t)B * max_tiles * sizeof(int));
-    w.gacc = (float*)(p + off);
-    off += b200r_align256((size_t)B * nf * 12 * sizeof(float));
     w.bytes = off;
+    return w;
+}
+
+// Both regions in ONE block (state first): the NMR path keeps its records only for the duration of the forward.
+static inline SoftRasWorkspace b200r_carve_single(void* base, int B, int nf, int image_size) {
+    const size_t sb = b200r_carve(nullptr, nullptr, B, nf, image_size).state_bytes;
+    SoftRasWorkspace w = b200r_carve(base, (char*)base + sb, B, nf, image_size);
+    w.bytes += sb;
     return w;
 }
 

@@ -24,7 +24,7 @@ extern "C" {
 
 size_t b200r_nmr_workspace_bytes(int batch_size, int num_faces, int image_size) {
     if (batch_size <= 0 || num_faces <= 0 || image_size <= 0) return 0;
-    return b200r_carve(nullptr, batch_size, num_faces, image_size).bytes;  // NmrRec (128 B) fits the 160 B slots
+    return b200r_carve_single(nullptr, batch_size, num_faces, image_size).bytes;  // NmrRec (128 B) fits the 160 B slots
 }
 
 int b200r_nmr_forward(const float* faces, const float* textures, int32_t* face_index_map, float* weight_map,
@@ -40,7 +40,7 @@ int b200r_nmr_forward(const float* faces, const float* textures, int32_t* face_i
         return b200r_fail(B200R_EINVAL, "b200r_nmr_forward: return_rgb needs textures, rgb_map, sampling maps and texture_size > 0");
     if (return_alpha && !alpha_map) return b200r_fail(B200R_EINVAL, "b200r_nmr_forward: return_alpha needs alpha_map");
     if (return_depth && !face_inv_map) return b200r_fail(B200R_EINVAL, "b200r_nmr_forward: return_depth needs face_inv_map");
-    const SoftRasWorkspace W = b200r_carve(workspace, B, nf, is);
+    const SoftRasWorkspace W = b200r_carve_single(workspace, B, nf, is);
     if (workspace_bytes < W.bytes)
         return b200r_fail(B200R_EWORKSPACE, "b200r_nmr_forward: workspace %zu < required %zu bytes", workspace_bytes, W.bytes);
     NmrParams P;

@@ -16,8 +16,6 @@ namespace {
 std::atomic<int> g_fwd_variant{1};     // 0: warp-uniform face loop, 1: per-lane face lists
 std::atomic<int> g_fwd_persistent{1};  // 0: one CTA per tile, 1: persistent grid + atomic tile queue
 std::atomic<int> g_exact_tail{0};      // 1: reference's double-precision sigmoid / alpha tails bit for bit; 0: fp32 tails (<= 1 ulp)
-std::atomic<int> g_bwd_variant{1};     // 0: warp union walk + scalar atomics, 1: per-lane walk + 16-byte vector atomics
-std::atomic<int> g_fwd_warps{1};       // warps per forward CTA: 8 (16x16 tile), 2 (16x4), 1 (8x4, warp-autonomous; default)
 }  // namespace
 
 int b200r_sm_count() {
@@ -56,9 +54,9 @@ SoftRasParams make_params(int B, int nf, int T, int is, int K, float near_, floa
     P.near_ = near_; P.far_ = far_; P.eps = eps; P.sigma = sigma; P.gamma = gamma; P.dist_eps = dist_eps;
     P.dist_func = dist; P.rgb_func = rgb; P.alpha_func = alpha; P.tex_type = tex; P.double_side = double_side ? 1 : 0;
     b200r_geometry(is, &P.ntx, &P.coarse_px, &P.ncs);
-    const int nw = g_fwd_warps.load();
-    P.ftw = nw == 1 ? 8 : 16;
-    P.fth = nw == 8 ? 16 : 4;
+    P.ftw = 8;   // forward blocks: one warp on 8x4 pixels
+    P.fth = 4;
+    P.aa = 0;
     P.fntx = (is + P.ftw - 1) / P.ftw;
     P.fnty = (is + P.fth - 1) / P.fth;
     P.queue_len = P.fntx * P.fnty * B;  // cost tiles == forward tiles: no holes
@@ -76,32 +74,33 @@ int b200r_set_option(const char* name, int value) {
     if (!strcmp(name, "softras_fwd_variant")) { g_fwd_variant.store(value < 0 ? 0 : (value > 2 ? 2 : value)); return 0; }
     if (!strcmp(name, "softras_fwd_persistent")) { g_fwd_persistent.store(value ? 1 : 0); return 0; }
     if (!strcmp(name, "softras_exact_tail")) { g_exact_tail.store(value ? 1 : 0); return 0; }
-    if (!strcmp(name, "softras_bwd_variant")) { g_bwd_variant.store(value ? 1 : 0); return 0; }
-    if (!strcmp(name, "softras_fwd_warps")) {
-        if (value != 1 && value != 2 && value != 8) return b200r_fail(B200R_EINVAL, "softras_fwd_warps must be 1, 2 or 8");
-        g_fwd_warps.store(value);
-        return 0;
-    }
     return b200r_fail(B200R_EINVAL, "b200r_set_option: unknown option '%s'", name);
 }
 
 size_t b200r_softras_workspace_bytes(int batch_size, int num_faces, int image_size) {
     if (batch_size <= 0 || num_faces <= 0 || image_size <= 0) return 0;
-    return b200r_carve(nullptr, batch_size, num_faces, image_size).bytes;
+    return b200r_carve(nullptr, nullptr, batch_size, num_faces, image_size).bytes;
 }
 
-int b200r_softras_forward(const float* face_vertices, const float* textures, float* soft_colors,
-                          float* aggrs_info, int32_t* faces_id_buffer, float* faces_info, void* workspace,
-                          size_t workspace_bytes, int B, int nf, int T, int is, int K, float near_, float far_,
-                          float eps, float sigma_val, float gamma_val, float dist_eps_logit, int dist_func,
-                          int rgb_func, int alpha_func, int texture_type, int double_side, void* stream) {
+size_t b200r_softras_state_bytes(int batch_size, int num_faces) {
+    if (batch_size <= 0 || num_faces <= 0) return 0;
+    return b200r_carve(nullptr, nullptr, batch_size, num_faces, 16).state_bytes;
+}
+
+static int softras_forward_impl(const float* face_vertices, const float* textures, float* soft_colors,
+                                float* aggrs_info, int32_t* faces_id_buffer, float* faces_info, float* pooled, void* state,
+                                size_t state_bytes, void* workspace, size_t workspace_bytes, int B, int nf, int T, int is, int K, float near_, float far_,
+                                float eps, float sigma_val, float gamma_val, float dist_eps_logit, int dist_func,
+                                int rgb_func, int alpha_func, int texture_type, int double_side, void* stream) {
     int rc = validate("b200r_softras_forward", B, nf, T, is, K, dist_func, rgb_func, alpha_func, texture_type, sigma_val, gamma_val);
     if (rc) return rc;
-    if (!face_vertices || !textures || !soft_colors || !aggrs_info || !faces_id_buffer || !workspace)
+    if (!face_vertices || !textures || !soft_colors || !aggrs_info || !faces_id_buffer || !workspace || !state)
         return b200r_fail(B200R_EINVAL, "b200r_softras_forward: NULL pointer argument");
-    const SoftRasWorkspace W = b200r_carve(workspace, B, nf, is);
+    const SoftRasWorkspace W = b200r_carve(state, workspace, B, nf, is);
     if (workspace_bytes < W.bytes)
         return b200r_fail(B200R_EWORKSPACE, "b200r_softras_forward: workspace %zu < required %zu bytes", workspace_bytes, W.bytes);
+    if (state_bytes < W.state_bytes)
+        return b200r_fail(B200R_EWORKSPACE, "b200r_softras_forward: state %zu < required %zu bytes", state_bytes, W.state_bytes);
     const SoftRasParams P = make_params(B, nf, T, is, K, near_, far_, eps, sigma_val, gamma_val, dist_eps_logit,
                                         dist_func, rgb_func, alpha_func, texture_type, double_side);
     cudaStream_t st = (cudaStream_t)stream;
@@ -137,36 +136,79 @@ int b200r_softras_forward(const float* face_vertices, const float* textures, flo
 
     {
         const int variant = g_fwd_variant.load(), persistent = g_fwd_persistent.load(), exact = g_exact_tail.load();
-        const int nw = g_fwd_warps.load();
-        if (nw == 1) e = b200r_launch_forward_nw1(P, W, textures, soft_colors, aggrs_info, faces_id_buffer, variant, persistent, exact, st);
-        else if (nw == 2) e = b200r_launch_forward_nw2(P, W, textures, soft_colors, aggrs_info, faces_id_buffer, variant, persistent, exact, st);
-        else e = b200r_launch_forward_nw8(P, W, textures, soft_colors, aggrs_info, faces_id_buffer, variant, persistent, exact, st);
+        e = b200r_launch_forward(P, W, textures, soft_colors, aggrs_info, faces_id_buffer, pooled, variant, persistent, exact, st);
     }
     if (e != cudaSuccess) return b200r_cuda_fail(e, "k_softras_forward");
     return 0;
 }
 
+int b200r_softras_forward(const float* face_vertices, const float* textures, float* soft_colors,
+                          float* aggrs_info, int32_t* faces_id_buffer, float* faces_info, void* state, size_t state_bytes,
+                          void* workspace, size_t workspace_bytes, int B, int nf, int T, int is, int K, float near_, float far_,
+                          float eps, float sigma_val, float gamma_val, float dist_eps_logit, int dist_func,
+                          int rgb_func, int alpha_func, int texture_type, int double_side, void* stream) {
+    return softras_forward_impl(face_vertices, textures, soft_colors, aggrs_info, faces_id_buffer, faces_info, nullptr, state,
+                                state_bytes, workspace, workspace_bytes, B, nf, T, is, K, near_, far_, eps, sigma_val, gamma_val, dist_eps_logit, dist_func,
+                                rgb_func, alpha_func, texture_type, double_side, stream);
+}
+
+int b200r_softras_forward_aa(const float* face_vertices, const float* textures, float* soft_colors, float* pooled_colors,
+                             float* aggrs_info, int32_t* faces_id_buffer, float* faces_info, void* state, size_t state_bytes,
+                             void* workspace, size_t workspace_bytes, int B, int nf, int T, int is, int K, float near_, float far_,
+                             float eps, float sigma_val, float gamma_val, float dist_eps_logit, int dist_func,
+                             int rgb_func, int alpha_func, int texture_type, int double_side, void* stream) {
+    if (!pooled_colors) return b200r_fail(B200R_EINVAL, "b200r_softras_forward_aa: NULL pooled_colors");
+    if (is & 1) return b200r_fail(B200R_EINVAL, "b200r_softras_forward_aa: supersampled image_size %d is odd", is);
+    return softras_forward_impl(face_vertices, textures, soft_colors, aggrs_info, faces_id_buffer, faces_info, pooled_colors, state,
+                                state_bytes, workspace, workspace_bytes, B, nf, T, is, K, near_, far_, eps, sigma_val, gamma_val, dist_eps_logit, dist_func,
+                                rgb_func, alpha_func, texture_type, double_side, stream);
+}
+
+static int softras_backward_impl(const float* face_vertices, const float* textures, const float* soft_colors,
+                                 const float* aggrs_info, const int32_t* faces_id_buffer, void* state,
+                                 size_t state_bytes, const float* grad_soft_colors, int grad_is_pooled, float* grad_face_vertices,
+                                 float* grad_textures, int B, int nf, int T, int is, int K, float near_, float far_,
+                                 float eps, float sigma_val, float gamma_val, float dist_eps_logit, int dist_func,
+                                 int rgb_func, int alpha_func, int texture_type, int double_side, void* stream) {
+    int rc = validate("b200r_softras_backward", B, nf, T, is, K, dist_func, rgb_func, alpha_func, texture_type, sigma_val, gamma_val);
+    if (rc) return rc;
+    if (!face_vertices || !textures || !soft_colors || !aggrs_info || !faces_id_buffer || !state ||
+        !grad_soft_colors || !grad_face_vertices || !grad_textures)
+        return b200r_fail(B200R_EINVAL, "b200r_softras_backward: NULL pointer argument");
+    const SoftRasWorkspace W = b200r_carve(state, nullptr, B, nf, is);   // the backward reads the records and owns the accumulator
+    if (state_bytes < W.state_bytes)
+        return b200r_fail(B200R_EWORKSPACE, "b200r_softras_backward: state %zu < required %zu bytes", state_bytes, W.state_bytes);
+    SoftRasParams P = make_params(B, nf, T, is, K, near_, far_, eps, sigma_val, gamma_val, dist_eps_logit,
+                                  dist_func, rgb_func, alpha_func, texture_type, double_side);
+    P.aa = grad_is_pooled ? 1 : 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = b200r_launch_backward(P, W, textures, soft_colors, aggrs_info, faces_id_buffer, grad_soft_colors,
+                                          grad_face_vertices, grad_textures, g_exact_tail.load(), st);
+    if (e != cudaSuccess) return b200r_cuda_fail(e, "k_softras_backward");
+    return 0;
+}
+
 int b200r_softras_backward(const float* face_vertices, const float* textures, const float* soft_colors,
-                           const float* aggrs_info, const int32_t* faces_id_buffer, void* workspace,
-                           size_t workspace_bytes, const float* grad_soft_colors, float* grad_face_vertices,
+                           const float* aggrs_info, const int32_t* faces_id_buffer, void* state,
+                           size_t state_bytes, const float* grad_soft_colors, float* grad_face_vertices,
                            float* grad_textures, int B, int nf, int T, int is, int K, float near_, float far_,
                            float eps, float sigma_val, float gamma_val, float dist_eps_logit, int dist_func,
                            int rgb_func, int alpha_func, int texture_type, int double_side, void* stream) {
-    int rc = validate("b200r_softras_backward", B, nf, T, is, K, dist_func, rgb_func, alpha_func, texture_type, sigma_val, gamma_val);
-    if (rc) return rc;
-    if (!face_vertices || !textures || !soft_colors || !aggrs_info || !faces_id_buffer || !workspace ||
-        !grad_soft_colors || !grad_face_vertices || !grad_textures)
-        return b200r_fail(B200R_EINVAL, "b200r_softras_backward: NULL pointer argument");
-    const SoftRasWorkspace W = b200r_carve(workspace, B, nf, is);
-    if (workspace_bytes < W.bytes)
-        return b200r_fail(B200R_EWORKSPACE, "b200r_softras_backward: workspace %zu < required %zu bytes", workspace_bytes, W.bytes);
-    const SoftRasParams P = make_params(B, nf, T, is, K, near_, far_, eps, sigma_val, gamma_val, dist_eps_logit,
-                                        dist_func, rgb_func, alpha_func, texture_type, double_side);
-    cudaStream_t st = (cudaStream_t)stream;
-    cudaError_t e = b200r_launch_backward(P, W, textures, soft_colors, aggrs_info, faces_id_buffer, grad_soft_colors,
-                                          grad_face_vertices, grad_textures, g_bwd_variant.load(), g_exact_tail.load(), st);
-    if (e != cudaSuccess) return b200r_cuda_fail(e, "k_softras_backward");
-    return 0;
+    return softras_backward_impl(face_vertices, textures, soft_colors, aggrs_info, faces_id_buffer, state, state_bytes,
+                                 grad_soft_colors, 0, grad_face_vertices, grad_textures, B, nf, T, is, K, near_, far_, eps, sigma_val,
+                                 gamma_val, dist_eps_logit, dist_func, rgb_func, alpha_func, texture_type, double_side, stream);
+}
+
+int b200r_softras_backward_aa(const float* face_vertices, const float* textures, const float* soft_colors,
+                              const float* aggrs_info, const int32_t* faces_id_buffer, void* state,
+                              size_t state_bytes, const float* grad_pooled_colors, float* grad_face_vertices,
+                              float* grad_textures, int B, int nf, int T, int is, int K, float near_, float far_,
+                              float eps, float sigma_val, float gamma_val, float dist_eps_logit, int dist_func,
+                              int rgb_func, int alpha_func, int texture_type, int double_side, void* stream) {
+    if (is & 1) return b200r_fail(B200R_EINVAL, "b200r_softras_backward_aa: supersampled image_size %d is odd", is);
+    return softras_backward_impl(face_vertices, textures, soft_colors, aggrs_info, faces_id_buffer, state, state_bytes,
+                                 grad_pooled_colors, 1, grad_face_vertices, grad_textures, B, nf, T, is, K, near_, far_, eps, sigma_val,
+                                 gamma_val, dist_eps_logit, dist_func, rgb_func, alpha_func, texture_type, double_side, stream);
 }
 
 }  // extern "C"

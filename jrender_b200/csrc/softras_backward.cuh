@@ -190,9 +190,11 @@ __device__ __forceinline__ void pair_gradient(const FaceRec* rec, int fn, const 
     }
 }
 
+// aa: grad_soft_colors is the gradient of the 2x2 mean-pooled image [B,4,is/2,is/2]; avg_pool2d's backward hands every
+// one of the four source pixels grad / 4 (rasterizer.py:54-55), formed here instead of by a pass over a 4x larger tensor.
 __device__ __forceinline__ void load_pixel(BwdPixel& px, const float* __restrict__ soft_colors,
                                            const float* __restrict__ aggrs_info, const float* __restrict__ grad_soft_colors,
-                                           int b, size_t pn, size_t npix, bool valid) {
+                                           int b, size_t pn, size_t npix, bool valid, int aa = 0, int row = 0, int col = 0, int is = 0) {
 #pragma unroll
     for (int k = 0; k < 4; k++) { px.g[k] = 0.f; px.oc[k] = 0.f; }
     px.softmax_sum = 1.f;
@@ -200,7 +202,12 @@ __device__ __forceinline__ void load_pixel(BwdPixel& px, const float* __restrict
     if (valid) {
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            px.g[k] = __ldg(grad_soft_colors + ((size_t)b * 4 + k) * npix + pn);
+            if (aa) {
+                const int hp = is >> 1;
+                px.g[k] = __ldg(grad_soft_colors + (((size_t)b * 4 + k) * hp + (row >> 1)) * hp + (col >> 1)) / 4.f;
+            } else {
+                px.g[k] = __ldg(grad_soft_colors + ((size_t)b * 4 + k) * npix + pn);
+            }
             px.oc[k] = __ldg(soft_colors + ((size_t)b * 4 + k) * npix + pn);
         }
         px.softmax_sum = __ldg(aggrs_info + ((size_t)b * 2 + 0) * npix + pn);
@@ -235,7 +242,7 @@ __device__ __forceinline__ void merge_same_face(int& key, float gv[9], float gt[
     if (same && !lower) key = -1;
 }
 
-// ---------------------------------------------------------------- VARIANT 1: per-lane walk + vector atomics
+// ---------------------------------------------------------------- per-lane walk + vector atomics
 template <int DIST, int RGB, bool EXACT>
 __global__ void __launch_bounds__(B200R_TILE_THREADS, B200R_BWD_MINB)
 k_softras_backward_lane(const SoftRasParams P, const FaceRec* __restrict__ recs, const float* __restrict__ textures,
@@ -269,7 +276,7 @@ k_softras_backward_lane(const SoftRasParams P, const FaceRec* __restrict__ recs,
     BwdPixel px;
     px.xp = b200r_pix_coord(pxi, is);
     px.yp = b200r_pix_coord(is - 1 - row, is);
-    load_pixel(px, soft_colors, aggrs_info, grad_soft_colors, b, pn, npix, has_list);
+    load_pixel(px, soft_colors, aggrs_info, grad_soft_colors, b, pn, npix, has_list, P.aa, row, pxi, is);
     const float nmf = P.near_ - P.far_;
     const float r_nmf = rcp_refined(nmf);
     const bool s_nmf = midrange(nmf);
@@ -365,113 +372,6 @@ k_softras_bwd_finalize(const float* __restrict__ gacc, float* __restrict__ grad_
     if (tex_in_acc) {
         float* t = grad_textures + (size_t)i * 3;
         t[0] = v2.y; t[1] = v2.z; t[2] = v2.w;
-    }
-}
-
-// ---------------------------------------------------------------- VARIANT 0: warp union walk
-template <int DIST, int RGB>
-__global__ void __launch_bounds__(B200R_TILE_THREADS, 2)
-k_softras_backward(const SoftRasParams P, const FaceRec* __restrict__ recs, const float* __restrict__ textures,
-                   const float* __restrict__ soft_colors, const float* __restrict__ aggrs_info,
-                   const int* __restrict__ ids_in, const float* __restrict__ grad_soft_colors,
-                   float* __restrict__ grad_faces, float* __restrict__ grad_textures) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    int* s_id = reinterpret_cast<int*>(smem_raw);                                     // [K][256]
-    float* s_wrec = reinterpret_cast<float*>(s_id + (size_t)P.K * B200R_TILE_THREADS);  // [8][40]
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int is = P.is, nf = P.nf, K = P.K, T = P.T;
-    const int b = blockIdx.y;
-    const int tx = blockIdx.x % P.ntx, ty = blockIdx.x / P.ntx;
-    const int pxi = tx * B200R_TILE + (warp & 1) * 8 + (lane & 7);
-    const int row = ty * B200R_TILE + (warp >> 1) * 4 + (lane >> 3);
-    const bool valid = pxi < is && row < is;
-    const size_t npix = (size_t)is * is;
-    const size_t pn = (size_t)row * is + pxi;
-    DivConst dc;
-    dc.init(P);
-
-    // ---- load + insertion-sort this pixel's ids (ascending; list ends at the first -1, :1236)
-    int n = 0;
-    if (valid) {
-        const int* src = ids_in + (size_t)b * K * npix + pn;
-        for (int k = 0; k < K; k++) {
-            const int v = __ldg(src + (size_t)k * npix);
-            if (v < 0) break;
-            int j = n;
-            while (j > 0) {
-                const int u = s_id[(j - 1) * B200R_TILE_THREADS + tid];
-                if (u <= v) break;
-                s_id[j * B200R_TILE_THREADS + tid] = u;
-                --j;
-            }
-            s_id[j * B200R_TILE_THREADS + tid] = v;
-            ++n;
-        }
-    }
-    // warp-uniform early out for empty blocks
-    if (__ballot_sync(0xffffffffu, n > 0) == 0u) return;
-
-    BwdPixel px;
-    px.xp = b200r_pix_coord(pxi, is);
-    px.yp = b200r_pix_coord(is - 1 - row, is);
-    load_pixel(px, soft_colors, aggrs_info, grad_soft_colors, b, pn, npix, valid);
-    const float nmf = P.near_ - P.far_;
-    const float r_nmf = rcp_refined(nmf);
-    const bool s_nmf = midrange(nmf);
-
-    const FaceRec* brecs = recs + (size_t)b * nf;
-    const float* btex = textures + (size_t)b * nf * T * 3;
-    float* bgf = grad_faces + (size_t)b * nf * 9;
-    float* bgt = grad_textures + (size_t)b * nf * T * 3;
-    FaceRec* wrec = reinterpret_cast<FaceRec*>(s_wrec + warp * 40);
-
-    int p = 0;
-    int cur = (p < n) ? s_id[tid] : 0x7fffffff;
-    while (true) {
-        const int fn = __reduce_min_sync(0xffffffffu, cur);
-        if (fn == 0x7fffffff) break;
-        // stage the record for the warp: one 4-byte word per lane (+8)
-        __syncwarp();
-        reinterpret_cast<uint32_t*>(wrec)[lane] = __ldg(reinterpret_cast<const uint32_t*>(brecs + fn) + lane);
-        if (lane < 8) reinterpret_cast<uint32_t*>(wrec)[32 + lane] = __ldg(reinterpret_cast<const uint32_t*>(brecs + fn) + 32 + lane);
-        __syncwarp();
-        const bool mine = (cur == fn);
-
-        float gv[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // [k*3 + l]
-        float gt[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // T==1: [k]; vertex: [j*3+k]
-        if (mine) {
-            int texel;
-            DivGuard guard;
-            guard.ok = true;
-            pair_gradient<DIST, RGB, true, false>(wrec, fn, px, P, dc, nmf, r_nmf, s_nmf, btex + (size_t)fn * T * 3, gv, gt, texel, guard);
-            if (RGB != 2 && P.tex_type == 0 && T > 1) {  // per-lane texel: scalar atomics, not reduced
-#pragma unroll
-                for (int k = 0; k < 3; k++) atomicAdd(bgt + ((size_t)fn * T + texel) * 3 + k, gt[k]);
-                gt[0] = gt[1] = gt[2] = 0.f;
-            }
-            ++p;
-            cur = (p < n) ? s_id[p * B200R_TILE_THREADS + tid] : 0x7fffffff;
-        }
-
-        // ---- warp reduction + one set of atomics per (warp, face)
-#pragma unroll
-        for (int c = 0; c < 9; c++) gv[c] = warp_sum(gv[c]);
-        const int ngt = (P.tex_type == 1) ? 9 : (T == 1 ? 3 : 0);
-        if (RGB != 2) {
-#pragma unroll
-            for (int c = 0; c < 9; c++)
-                if (c < ngt) gt[c] = warp_sum(gt[c]);
-        }
-        if (lane == 0) {
-#pragma unroll
-            for (int c = 0; c < 9; c++) atomicAdd(bgf + (size_t)fn * 9 + c, gv[c]);
-            if (RGB != 2) {
-#pragma unroll
-                for (int c = 0; c < 9; c++)
-                    if (c < ngt) atomicAdd(bgt + (size_t)fn * T * 3 + c, gt[c]);
-            }
-        }
     }
 }
 

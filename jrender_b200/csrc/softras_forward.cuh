@@ -294,6 +294,18 @@ __device__ __forceinline__ void shade_pair(const FaceRec* rec, PixState& st, con
     else shade_face<DIST, RGB, NT, EXACT>(rec, st, P, dc, xp, yp, threshold, s_qz, s_qid, tid, btex);
 }
 
+// Anti-aliasing epilogue (SoftRasterizer.execute renders at 2x and mean-pools 2x2, rasterizer.py:45,54-55): the 2x2 means
+// of one 8x4 block's four colour planes, straight from the block's output staging area s_out[ch][32] (row-major 8x4) to
+// pooled [B,4,is/2,is/2].  Lane -> (plane, pooled row, pooled column); a quarter warp writes 16 contiguous bytes.
+// Summation order and the division are avg_pool2d's (window scanned row-major, sum / 4).
+__device__ __forceinline__ void store_pooled_8x4(const float* s_out, float* __restrict__ pooled, int b, int tx0, int tr0, int is, int lane) {
+    const int ch = lane >> 3, pr = (lane >> 2) & 1, pc = lane & 3;
+    const float* s = s_out + ch * 32 + (2 * pr) * 8 + 2 * pc;
+    const float v = (((s[0] + s[1]) + s[8]) + s[9]) / 4.f;
+    const int hp = is >> 1, orow = (tr0 >> 1) + pr, ocol = (tx0 >> 1) + pc;
+    if (orow < hp && ocol < hp) pooled[(((size_t)b * 4 + ch) * hp + orow) * hp + ocol] = v;
+}
+
 __device__ __forceinline__ bool pixel_in_rect(const FaceRec* rec, int px, int row) {
     const uint32_t rx = rec->rect_x, rr = rec->rect_r;
     const uint32_t x0 = rx & 0xffffu, r0 = rr & 0xffffu;
@@ -306,7 +318,7 @@ k_softras_forward(const SoftRasParams P, const FaceRec* __restrict__ recs, const
                   const int* __restrict__ coarse_cnt, const int* __restrict__ coarse_ids,
                   const float* __restrict__ textures, float* __restrict__ soft_colors,
                   float* __restrict__ aggrs_info, int* __restrict__ ids_out, int* tile_counter,
-                  const int* __restrict__ tile_order) {
+                  const int* __restrict__ tile_order, float* __restrict__ pooled) {
     constexpr int NW = WX * WY, NT = 32 * NW, CHUNK = FwdCfg<NW>::CHUNK, UNR = FwdCfg<NW>::UNR;
     constexpr int TW = 8 * WX, TH = 4 * WY;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -567,6 +579,7 @@ k_softras_forward(const SoftRasParams P, const FaceRec* __restrict__ recs, const
         s_out[4 * NT + tpix] = g0;
         s_out[5 * NT + tpix] = g1;
         cta_sync<NW>();
+        if (NW == 1 && pooled != nullptr) store_pooled_8x4(s_out, pooled, b, tx0, tr0, is, lane);
         if ((is & 3) == 0) {
             constexpr int QPR = TW / 4;  // float4 per tile row
             for (int j = tid; j < 6 * TH * QPR; j += NT) {

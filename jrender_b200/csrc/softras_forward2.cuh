@@ -209,7 +209,7 @@ k_softras_forward2(const SoftRasParams P, const FaceRec* __restrict__ recs, cons
                    const int* __restrict__ coarse_cnt, const int* __restrict__ coarse_ids,
                    const float* __restrict__ textures, float* __restrict__ soft_colors,
                    float* __restrict__ aggrs_info, int* __restrict__ ids_out, int* tile_counter,
-                   const int* __restrict__ tile_order) {
+                   const int* __restrict__ tile_order, float* __restrict__ pooled) {
     constexpr int R = B200R_F2_R, PMAX = B200R_F2_PMAX, UNR = 4, TW = 8, TH = 4, NT = 32;
     static_assert(R <= 32 && PMAX >= 32 * 8 && PMAX <= 32 * R, "round geometry");
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -470,6 +470,7 @@ k_softras_forward2(const SoftRasParams P, const FaceRec* __restrict__ recs, cons
         s_out[4 * NT + lane] = g0;
         s_out[5 * NT + lane] = g1;
         __syncwarp();
+        if (pooled != nullptr) store_pooled_8x4(s_out, pooled, b, tx0, tr0, is, lane);   // anti-aliasing epilogue
         if ((is & 3) == 0) {
             constexpr int QPR = TW / 4;  // float4 per block row
             for (int j = lane; j < 6 * TH * QPR; j += NT) {

@@ -1,4 +1,4 @@
-// softras_fwd_nw1.cu -- forward kernel instantiations for the 1x1 warp layout (8x4 pixel tiles).
+// softras_fwd.cu -- forward kernel instantiations (one-warp CTAs on 8x4 pixel blocks) and their launcher.
 #include <atomic>
 
 #include "api_util.cuh"
@@ -11,7 +11,7 @@ using namespace b200r;
 namespace {
 template <int DIST, int RGB, int VARIANT, bool EXACT>
 cudaError_t launch_v(const SoftRasParams& P, const SoftRasWorkspace& W, const float* textures, float* soft_colors,
-                     float* aggrs_info, int32_t* ids, int persistent, cudaStream_t st) {
+                     float* aggrs_info, int32_t* ids, float* pooled, int persistent, cudaStream_t st) {
     constexpr int WX = 1, WY = 1, NW = WX * WY, NT = 32 * NW;
     const size_t smem = fwd_smem_bytes<NW>(P.K, VARIANT);
     // attribute + occupancy are host calls: queried once per (instantiation, smem size)
@@ -43,7 +43,7 @@ cudaError_t launch_v(const SoftRasParams& P, const SoftRasWorkspace& W, const fl
     {
         B200rProfScope prof(B200R_K_SOFTRAS_FWD, st);
         k_softras_forward<DIST, RGB, VARIANT, WX, WY, EXACT><<<grid, NT, smem, st>>>(
-            P, W.recs, W.rects, W.coarse_cnt, W.coarse_ids, textures, soft_colors, aggrs_info, ids, counter, W.tile_order);
+            P, W.recs, W.rects, W.coarse_cnt, W.coarse_ids, textures, soft_colors, aggrs_info, ids, counter, W.tile_order, pooled);
     }
     return cudaGetLastError();
 }
@@ -51,7 +51,7 @@ cudaError_t launch_v(const SoftRasParams& P, const SoftRasWorkspace& W, const fl
 // two-phase kernel (softras_forward2.cuh).  Function attributes and occupancy are per DEVICE: cached per ordinal.
 template <int DIST, int RGB, bool EXACT>
 cudaError_t launch_v2(const SoftRasParams& P, const SoftRasWorkspace& W, const float* textures, float* soft_colors,
-                      float* aggrs_info, int32_t* ids, int persistent, cudaStream_t st) {
+                      float* aggrs_info, int32_t* ids, float* pooled, int persistent, cudaStream_t st) {
     constexpr int MAXDEV = 64;
     const size_t smem = fwd2_smem_bytes(P.K);
     static std::atomic<size_t> cfg_smem[MAXDEV];
@@ -87,21 +87,21 @@ cudaError_t launch_v2(const SoftRasParams& P, const SoftRasWorkspace& W, const f
     {
         B200rProfScope prof(B200R_K_SOFTRAS_FWD, st);
         k_softras_forward2<DIST, RGB, EXACT><<<grid, 32, smem, st>>>(
-            P, W.recs, W.rects, W.coarse_cnt, W.coarse_ids, textures, soft_colors, aggrs_info, ids, counter, W.tile_order);
+            P, W.recs, W.rects, W.coarse_cnt, W.coarse_ids, textures, soft_colors, aggrs_info, ids, counter, W.tile_order, pooled);
     }
     return cudaGetLastError();
 }
 }  // namespace
 
-cudaError_t b200r_launch_forward_nw1(const SoftRasParams& P, const SoftRasWorkspace& W, const float* textures, float* soft_colors,
-                                     float* aggrs_info, int32_t* ids, int variant, int persistent, int exact, cudaStream_t st) {
+cudaError_t b200r_launch_forward(const SoftRasParams& P, const SoftRasWorkspace& W, const float* textures, float* soft_colors,
+                                 float* aggrs_info, int32_t* ids, float* pooled, int variant, int persistent, int exact, cudaStream_t st) {
     cudaError_t e = cudaSuccess;
     if (variant == 2) {   // two-phase kernel
         // fp32 tails + optimistic divisions only for the default euclidean distance; the other modes keep the exact tails
-        B200R_DISPATCH_DIST_RGB((e = (D == 2 && !exact) ? launch_v2<D, R, (D != 2)>(P, W, textures, soft_colors, aggrs_info, ids, persistent, st)
-                                                        : launch_v2<D, R, true>(P, W, textures, soft_colors, aggrs_info, ids, persistent, st)))
+        B200R_DISPATCH_DIST_RGB((e = (D == 2 && !exact) ? launch_v2<D, R, (D != 2)>(P, W, textures, soft_colors, aggrs_info, ids, pooled, persistent, st)
+                                                        : launch_v2<D, R, true>(P, W, textures, soft_colors, aggrs_info, ids, pooled, persistent, st)))
         return e;
     }
-    B200R_DISPATCH_DIST_RGB((e = (D == 2 && !exact) ? launch_v<D, R, 1, (D != 2)>(P, W, textures, soft_colors, aggrs_info, ids, persistent, st) : launch_v<D, R, 1, true>(P, W, textures, soft_colors, aggrs_info, ids, persistent, st)))
+    B200R_DISPATCH_DIST_RGB((e = (D == 2 && !exact) ? launch_v<D, R, 1, (D != 2)>(P, W, textures, soft_colors, aggrs_info, ids, pooled, persistent, st) : launch_v<D, R, 1, true>(P, W, textures, soft_colors, aggrs_info, ids, pooled, persistent, st)))
     return e;
 }

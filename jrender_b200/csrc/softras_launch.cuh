@@ -1,5 +1,5 @@
-// softras_launch.cuh -- launchers implemented in separate translation units (one per forward
-// warp layout, one for the backward) so that the template instantiations compile in parallel.
+// softras_launch.cuh -- launchers implemented in separate translation units (forward, backward) so that the template
+// instantiations compile in parallel.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -7,15 +7,12 @@
 #include "common.cuh"
 
 int b200r_sm_count();
-cudaError_t b200r_launch_forward_nw8(const SoftRasParams& P, const SoftRasWorkspace& W, const float* textures, float* soft_colors,
-                                     float* aggrs_info, int32_t* ids, int variant, int persistent, int exact, cudaStream_t st);
-cudaError_t b200r_launch_forward_nw2(const SoftRasParams& P, const SoftRasWorkspace& W, const float* textures, float* soft_colors,
-                                     float* aggrs_info, int32_t* ids, int variant, int persistent, int exact, cudaStream_t st);
-cudaError_t b200r_launch_forward_nw1(const SoftRasParams& P, const SoftRasWorkspace& W, const float* textures, float* soft_colors,
-                                     float* aggrs_info, int32_t* ids, int variant, int persistent, int exact, cudaStream_t st);
+// pooled: optional [B,4,is/2,is/2] 2x2 mean of soft_colors written by the forward (anti-aliasing epilogue), or nullptr
+cudaError_t b200r_launch_forward(const SoftRasParams& P, const SoftRasWorkspace& W, const float* textures, float* soft_colors,
+                                 float* aggrs_info, int32_t* ids, float* pooled, int variant, int persistent, int exact, cudaStream_t st);
 cudaError_t b200r_launch_backward(const SoftRasParams& P, const SoftRasWorkspace& W, const float* textures,
                                   const float* soft_colors, const float* aggrs_info, const int32_t* ids,
-                                  const float* grad_soft_colors, float* grad_faces, float* grad_textures, int variant,
+                                  const float* grad_soft_colors, float* grad_faces, float* grad_textures,
                                   int exact, cudaStream_t st);
 
 #define B200R_DISPATCH_DIST_RGB(CALL)                               \

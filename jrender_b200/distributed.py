@@ -46,3 +46,55 @@ def all_gather_images(images, batch_size=None):
     parts = [torch.empty_like(pad) for _ in range(world)]
     dist.all_gather(parts, pad)
     return torch.cat([p[:s] for p, s in zip(parts, sizes)], dim=0)
+
+
+class OverlappedImageGather:
+    """The optional all-gather of the output images, issued PER CHUNK of the rank's batch on a side stream so that
+    it hides behind the rasterization of the following chunks (and, when the caller only collects the images, behind
+    the backward pass): at C3 the blocking gather is 0.8 ms of a 1.4 ms step on 8 GPUs.
+
+        g = OverlappedImageGather(images_per_rank=4, image_shape=(4, 1024, 1024), device=dev)
+        for i in range(4):
+            img_i = rasterize(chunk i)              # [1, 4, H, W] on the current stream
+            g.push(i, img_i)                        # side stream: wait for img_i, all-gather it, place it
+        full = g.result()                           # [world * 4, 4, H, W]; the current stream waits for the side stream
+
+    Sample r * images_per_rank + i of the result is chunk i of rank r, i.e. the same order all_gather_images gives.
+    Equal shards only.  On CPU tensors (gloo, tests) the calls run synchronously.  Without a process group the result
+    is the concatenation of the local chunks."""
+
+    def __init__(self, images_per_rank, image_shape, device, dtype=torch.float32, chunk=1):
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.n, self.chunk = int(images_per_rank), int(chunk)
+        if self.n % self.chunk:
+            raise ValueError("images_per_rank %d is not a multiple of chunk %d" % (self.n, self.chunk))
+        self.device = torch.device(device)
+        self.out = torch.empty((self.world, self.n) + tuple(image_shape), dtype=dtype, device=self.device)
+        self.cuda = self.device.type == "cuda"
+        self.side = torch.cuda.Stream(self.device) if self.cuda else None
+        self.tmp = [torch.empty((self.world * self.chunk,) + tuple(image_shape), dtype=dtype, device=self.device)
+                    for _ in range(self.n // self.chunk)] if self.world > 1 else None   # rank-major, like all_gather_images
+
+    def push(self, index, images):
+        """images: chunk number `index` of this rank, [chunk, *image_shape], produced on the current stream."""
+        lo = index * self.chunk
+        images = images.detach()
+        if self.world == 1:
+            self.out[0, lo:lo + self.chunk].copy_(images)
+            return
+        if not self.cuda:
+            dist.all_gather_into_tensor(self.tmp[index], images.contiguous())
+            self.out[:, lo:lo + self.chunk].copy_(self.tmp[index].view((self.world, self.chunk) + tuple(self.out.shape[2:])))
+            return
+        self.side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self.side):
+            src = images.contiguous()
+            src.record_stream(self.side)
+            dist.all_gather_into_tensor(self.tmp[index], src)
+            # rank-major [world, chunk] block into its column of the [world, images_per_rank] result
+            self.out[:, lo:lo + self.chunk].copy_(self.tmp[index].view((self.world, self.chunk) + tuple(self.out.shape[2:])))
+
+    def result(self):
+        if self.cuda and self.world > 1:
+            torch.cuda.current_stream(self.device).wait_stream(self.side)
+        return self.out.view((self.world * self.n,) + tuple(self.out.shape[2:]))

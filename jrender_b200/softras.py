@@ -60,17 +60,30 @@ class _SoftRasterizeOp(torch.autograd.Function):
             aggrs_info = torch.empty((B, 2, H, H), dtype=torch.float32, device=dev)
             faces_id_buffer = torch.empty((B, K, H, H), dtype=torch.int32, device=dev)
             faces_info = torch.empty((B, nf, 27), dtype=torch.float32, device=dev) if fn.return_faces_info else None
+            # state: records + gradient accumulator, kept for the backward; workspace: binning scratch, released (back to
+            # the caching allocator) as soon as this call returns -- it is not part of the saved state
+            st_bytes = L.b200r_softras_state_bytes(B, nf)
+            state = torch.empty((st_bytes,), dtype=torch.uint8, device=dev)
             ws_bytes = L.b200r_softras_workspace_bytes(B, nf, H)
             workspace = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
             scal = fn._scalars(B, nf, T)
-            rc = L.b200r_softras_forward(
-                _ptr(fv), _ptr(tx), _ptr(soft_colors), _ptr(aggrs_info), _ptr(faces_id_buffer),
-                _ptr(faces_info) if faces_info is not None else None, _ptr(workspace), ws_bytes,
-                *scal, C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+            pooled = None
+            if getattr(fn, "pool2x2", False):   # anti-aliasing epilogue: the forward also writes the 2x2 means
+                pooled = torch.empty((B, 4, H // 2, H // 2), dtype=torch.float32, device=dev)
+                rc = L.b200r_softras_forward_aa(
+                    _ptr(fv), _ptr(tx), _ptr(soft_colors), _ptr(pooled), _ptr(aggrs_info), _ptr(faces_id_buffer),
+                    _ptr(faces_info) if faces_info is not None else None, _ptr(state), st_bytes, _ptr(workspace), ws_bytes,
+                    *scal, C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+            else:
+                rc = L.b200r_softras_forward(
+                    _ptr(fv), _ptr(tx), _ptr(soft_colors), _ptr(aggrs_info), _ptr(faces_id_buffer),
+                    _ptr(faces_info) if faces_info is not None else None, _ptr(state), st_bytes, _ptr(workspace), ws_bytes,
+                    *scal, C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
         _lib.check(rc, "b200r_softras_forward")
+        ctx.pool2x2 = pooled is not None
         ctx.scal = scal
-        ctx.ws_bytes = ws_bytes
-        ctx.save_for_backward(fv, tx, soft_colors, aggrs_info, faces_id_buffer, workspace)
+        ctx.st_bytes = st_bytes
+        ctx.save_for_backward(fv, tx, soft_colors, aggrs_info, faces_id_buffer, state)
         # The reference keeps these on the Function object (soft_rasterize.py:101); render2 reads
         # save_vars[4] = aggrs_info (render2/render2.py:306).  Detached aliases only: a strong
         # reference to the OUTPUT tensor from here would close the cycle
@@ -82,13 +95,15 @@ class _SoftRasterizeOp(torch.autograd.Function):
         # Without this, autograd hands the backward zero-filled "gradients" for aggrs_info and for the
         # int32 faces_id_buffer: a 268 MB (C3) / 2 GB (C5, 120 views) fill kernel per step for nothing.
         ctx.set_materialize_grads(False)
+        if pooled is not None:   # the pooled image is the differentiable output; the supersampled one is saved state
+            return pooled, aggrs_info, faces_id_buffer
         return soft_colors, aggrs_info, faces_id_buffer
 
     @staticmethod
     def backward(ctx, grad_soft_colors, _g1, _g2):
         if grad_soft_colors is None:   # soft_colors did not take part in the loss
             return None, None, None
-        fv, tx, soft_colors, aggrs_info, faces_id_buffer, workspace = ctx.saved_tensors
+        fv, tx, soft_colors, aggrs_info, faces_id_buffer, state = ctx.saved_tensors
         L = _lib.lib()
         dev = fv.device
         g = grad_soft_colors.contiguous()
@@ -97,9 +112,10 @@ class _SoftRasterizeOp(torch.autograd.Function):
         with torch.cuda.device(dev):
             grad_faces = torch.empty_like(fv)
             grad_textures = torch.empty_like(tx)
-            rc = L.b200r_softras_backward(
+            call = L.b200r_softras_backward_aa if ctx.pool2x2 else L.b200r_softras_backward   # g: pooled gradient under AA
+            rc = call(
                 _ptr(fv), _ptr(tx), _ptr(soft_colors), _ptr(aggrs_info), _ptr(faces_id_buffer),
-                _ptr(workspace), ctx.ws_bytes, _ptr(g), _ptr(grad_faces), _ptr(grad_textures),
+                _ptr(state), ctx.st_bytes, _ptr(g), _ptr(grad_faces), _ptr(grad_textures),
                 *ctx.scal, C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
         _lib.check(rc, "b200r_softras_backward")
         return grad_faces, grad_textures, None
@@ -138,6 +154,7 @@ class SoftRasterizeFunction(object):
         self.max_elems_per_bin = max_elems_per_bin
         self.max_faces_id = max_faces_per_pixel_for_grad
         self.return_faces_info = False
+        self.pool2x2 = False   # set by SoftRasterizer(anti_aliasing=True): return the 2x2 mean-pooled image (fused epilogue)
         self.save_vars = None
 
     def _scalars(self, B, nf, T):
@@ -219,6 +236,8 @@ class SoftRasterizer(nn.Module):
         self.max_elems_per_bin = max_elems_per_bin
         self.max_faces_per_pixel_for_grad = max_faces_per_pixel_for_grad
 
+    fused_antialiasing = True   # False: the reference's op sequence (full-size image, then avg_pool2d)
+
     def forward(self, mesh, mode=None):
         image_size = self.image_size * (2 if self.anti_aliasing else 1)
         # mode='silhouettes' returns images[:, 3] only (rasterizer.py:56-57).  Alpha and its gradient
@@ -226,16 +245,19 @@ class SoftRasterizer(nn.Module):
         # the backward is exactly 0), so the kernels run with the colour path compiled out
         # (B200R_RGB_NONE): same alpha, same gradients, no texture sampling / softmax.
         aggr_func_rgb = 'none' if mode == 'silhouettes' else self.aggr_func_rgb
-        images = soft_rasterize(mesh.face_vertices, mesh.face_textures, image_size,
-                                self.background_color, self.near, self.far,
-                                self.fill_back, self.eps,
-                                self.sigma_val, self.dist_func, self.dist_eps,
-                                self.gamma_val, aggr_func_rgb, self.aggr_func_alpha,
-                                self.texture_type, self.bin_size, self.max_elems_per_bin,
-                                self.max_faces_per_pixel_for_grad)
-
-        if self.anti_aliasing:
-            images = torch.nn.functional.avg_pool2d(images, kernel_size=2, stride=2)
+        args = (image_size, self.background_color, self.near, self.far, self.fill_back, self.eps,
+                self.sigma_val, self.dist_func, self.dist_eps, self.gamma_val, aggr_func_rgb, self.aggr_func_alpha,
+                self.texture_type, self.bin_size, self.max_elems_per_bin, self.max_faces_per_pixel_for_grad)
+        if self.anti_aliasing and self.fused_antialiasing and mesh.face_vertices.is_cuda:
+            # anti-aliasing (rasterizer.py:45,54-55: render at 2x, 2x2 mean): the forward kernel writes the pooled image
+            # from its output staging and the backward reads the pooled gradient (b200r_softras_forward_aa / _backward_aa)
+            fn = SoftRasterizeFunction(*args)
+            fn.pool2x2 = True
+            images = fn(mesh.face_vertices, mesh.face_textures)
+        else:
+            images = soft_rasterize(mesh.face_vertices, mesh.face_textures, *args)
+            if self.anti_aliasing:
+                images = torch.nn.functional.avg_pool2d(images, kernel_size=2, stride=2)
         if mode == 'silhouettes':
             return images[:, 3, :, :]
         elif mode == 'rgb':

@@ -119,6 +119,7 @@ def bake_main(out_dir):
     """Reference texture-bake kernel (io/utils/load_textures.py:3-101 via oracle/build_ref.py) on seeded inputs ->
     ref_gpu_bake_random40_R5.npz; prints the difference to the numpy oracle (oracle/bake.py)."""
     import ctypes as C
+    import torch
     from oracle import bake as obake
     rng = np.random.default_rng(7)
     nf, R, H, W = 40, 5, 24, 40

@@ -24,7 +24,8 @@ def lib():
 
 def test_header_declares_entry_points():
     syms = declared_symbols()
-    for s in ["b200r_softras_forward", "b200r_softras_backward", "b200r_softras_workspace_bytes",
+    for s in ["b200r_softras_forward", "b200r_softras_backward", "b200r_softras_workspace_bytes", "b200r_softras_state_bytes",
+              "b200r_softras_forward_aa", "b200r_softras_backward_aa", "b200r_surface_lighting_forward", "b200r_bake_textures_softras",
               "b200r_last_error", "b200r_launch_count", "b200r_profile_read"]:
         assert s in syms
 
@@ -40,8 +41,10 @@ def test_version_and_workspace_size(lib):
     small = lib.b200r_softras_workspace_bytes(1, 100, 64)
     big = lib.b200r_softras_workspace_bytes(4, 39200, 1024)
     assert 0 < small < big
-    # records (128 B) + rects (8 B) per face are the floor
-    assert big >= 4 * 39200 * 136
+    assert big >= 4 * 39200 * 8                       # rects (8 B) per face are the floor of the binning scratch
+    # what the backward keeps: 160-byte records + 48-byte accumulator rows, independent of the image size
+    st = lib.b200r_softras_state_bytes(4, 39200)
+    assert 4 * 39200 * 208 <= st <= 4 * 39200 * 208 + 1024 and lib.b200r_softras_state_bytes(0, 5) == 0
 
 
 def test_argument_validation_is_loud(lib):
@@ -49,11 +52,11 @@ def test_argument_validation_is_loud(lib):
     null = C.c_void_p(0)
     args_tail = (1.0, 100.0, 1e-3, 1e-5, 1e-4, 9.21, 2, 1, 2, 0, 1, null)
     # K > 64 violates the reference hard limit kMaxPointsPerPixel (cuda/soft_rasterize.py:16)
-    rc = lib.b200r_softras_forward(null, null, null, null, null, null, null, 0, 1, 10, 1, 64, 65, *args_tail)
+    rc = lib.b200r_softras_forward(null, null, null, null, null, null, null, 0, null, 0, 1, 10, 1, 64, 65, *args_tail)
     assert rc == -1 and b"max_faces_per_pixel" in lib.b200r_last_error()
-    rc = lib.b200r_softras_forward(null, null, null, null, null, null, null, 0, 1, 10, 1, 64, 16, *args_tail)
+    rc = lib.b200r_softras_forward(null, null, null, null, null, null, null, 0, null, 0, 1, 10, 1, 64, 16, *args_tail)
     assert rc == -1 and b"NULL" in lib.b200r_last_error()
-    rc = lib.b200r_softras_forward(null, null, null, null, null, null, null, 0, 1, 10, 2, 64, 16, *args_tail)
+    rc = lib.b200r_softras_forward(null, null, null, null, null, null, null, 0, null, 0, 1, 10, 2, 64, 16, *args_tail)
     assert rc == -1 and b"square" in lib.b200r_last_error()
     with pytest.raises(_lib.B200RasterError):
         _lib.check(rc, "b200r_softras_forward")

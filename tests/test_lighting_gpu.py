@@ -59,7 +59,7 @@ def test_fused_lighting_gradients_match_float64_autograd(cuda_device, spec, tex6
     for name, dtype, fused in (("fused", torch.float32, True), ("mirror64", torch.float64, False)):
         vt = torch.from_numpy(vb).to(cuda_device, dtype).requires_grad_(True)
         tt = torch.from_numpy(tex).to(cuda_device, dtype).requires_grad_(True)
-        m = jr.Mesh(vt, torch.from_numpy(f).to(cuda_device), textures=tt, dr_type='n3mr' if tex6 else 'softras',
+        m = jr.Mesh(vt, torch.from_numpy(f)[None].repeat(B, 1, 1).to(cuda_device), textures=tt, dr_type='n3mr' if tex6 else 'softras',
                     metallic_textures=torch.from_numpy(met).to(cuda_device, dtype), roughness_textures=torch.from_numpy(rou).to(cuda_device, dtype))
         m.with_specular = spec
         light = jr.Lighting(intensity_ambient=0.4, color_ambient=[1, 0.9, 0.8], intensity_directionals=0.7,
@@ -86,5 +86,5 @@ def test_renderer_uses_the_fused_lighting_and_counts_one_launch(cuda_device):
     n0 = L.b200r_launch_count()
     img = r(torch.from_numpy(v)[None].to(cuda_device), torch.from_numpy(f)[None].to(cuda_device), tex)
     torch.cuda.synchronize()
-    assert tuple(img.shape) == (1, 4, 64, 64) and float(img[:, :3].max()) > 0.2
+    assert tuple(img.shape) == (1, 3, 64, 64) and float(img.max()) > 0.2
     assert L.b200r_launch_count() - n0 >= 7   # lighting + projection + the raster pipeline, all through the C ABI

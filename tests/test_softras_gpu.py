@@ -272,48 +272,74 @@ def test_against_reference_kernels_on_gpu(cuda_device, nfaces, H, min_same, grad
         assert np.abs(a[m] - b[m]).sum() / np.abs(a[m]).sum() <= grad_l1, k
 
 
-@pytest.mark.parametrize("warps,variant,persistent", [(8, 0, 0), (8, 0, 1), (8, 1, 0), (2, 1, 1), (1, 1, 1), (1, 1, 0), (1, 2, 1), (1, 2, 0)])
-def test_every_forward_configuration_gives_identical_results(cuda_device, warps, variant, persistent):
-    """Tile shape (16x16 / 16x4 / 8x4 warp-autonomous), per-lane lists and the persistent LPT queue are
-    pure scheduling choices: all outputs must be bit-identical to the default configuration's."""
+@pytest.mark.parametrize("variant,persistent", [(1, 1), (1, 0), (2, 1), (2, 0)])
+def test_every_forward_configuration_gives_identical_results(cuda_device, variant, persistent):
+    """The two forward kernels (lanes walking private face lists / two-phase compacted pair list) and the persistent
+    cost-ordered queue are pure scheduling choices: all outputs must be bit-identical to the default configuration's."""
     from jrender_b200 import _lib
     fv, tex = wl.make_scene(3280, batch=2)
     P = osr.Params(image_size=200, sigma_val=3e-5)
     base = run_cuda(fv, tex, P, want_faces_info=False)
     try:
-        _lib.set_option("softras_fwd_warps", warps)
         _lib.set_option("softras_fwd_variant", variant)
         _lib.set_option("softras_fwd_persistent", persistent)
         got = run_cuda(fv, tex, P, want_faces_info=False)
+        # the pair budget of a two-phase round (large sigma: every staged face covers the whole block) and T > 1 textures
+        fv5, tex5 = wl.make_scene(280, batch=1, texture_res=3)
+        P5 = osr.Params(image_size=96, sigma_val=1e-3, gamma_val=1e-3)
+        got5 = run_cuda(fv5, tex5, P5, want_faces_info=False)
     finally:
-        _lib.set_option("softras_fwd_warps", 1)
         _lib.set_option("softras_fwd_variant", 1)
         _lib.set_option("softras_fwd_persistent", 1)
     for k in ("soft_colors", "aggrs_info", "faces_id_buffer"):
         assert np.array_equal(base[k], got[k]), k
     ref = run_oracle(fv, tex, P)
     assert np.array_equal(ref["faces_id_buffer"], got["faces_id_buffer"])
+    ref5 = run_oracle(fv5, tex5, P5)
+    assert np.array_equal(ref5["faces_id_buffer"], got5["faces_id_buffer"])
+    assert np.abs(ref5["soft_colors"] - got5["soft_colors"]).max() <= COLOR_ATOL
 
 
 @pytest.mark.parametrize("mode", [dict(), dict(aggr_func_rgb="hard"), dict(texture_type="vertex"),
                                   dict(dist_func="barycentric", aggr_func_alpha="sum")])
-def test_backward_variants_agree_with_oracle(cuda_device, mode):
-    """Union-walk (scalar atomics) and per-lane (16-byte vector atomics + finalize) backward kernels
-    evaluate the same per-pair arithmetic; both must match the oracle to the gradient tolerance."""
-    from jrender_b200 import _lib
+def test_backward_modes_agree_with_oracle(cuda_device, mode):
+    """The per-lane backward (16-byte vector atomics + finalize) in the texture / aggregation modes that take different
+    accumulation paths (T == 1 colour in the accumulator, texel-indexed and per-vertex texture gradients)."""
     tt = mode.get("texture_type", "surface")
     fv, tex = wl.make_scene(280, batch=2, texture_type=tt, texture_res=1)
-    P = osr.Params(image_size=96, sigma_val=3e-5, **mode)
-    try:
-        for variant in (0, 1):
-            _lib.set_option("softras_bwd_variant", variant)
-            check(fv, tex, P)
-        fv5, tex5 = wl.make_scene(280, batch=1, texture_res=3)
-        for variant in (0, 1):
-            _lib.set_option("softras_bwd_variant", variant)
-            check(fv5, tex5, osr.Params(image_size=64, aggr_func_rgb=mode.get("aggr_func_rgb", "softmax")))
-    finally:
-        _lib.set_option("softras_bwd_variant", 1)
+    check(fv, tex, osr.Params(image_size=96, sigma_val=3e-5, **mode))
+    fv5, tex5 = wl.make_scene(280, batch=1, texture_res=3)
+    check(fv5, tex5, osr.Params(image_size=64, aggr_func_rgb=mode.get("aggr_func_rgb", "softmax")))
+
+
+@pytest.mark.parametrize("mode", [None, "silhouettes", "rgb"])
+def test_fused_antialiasing_matches_the_unfused_op_sequence(cuda_device, mode):
+    """anti_aliasing=True: the forward's 2x2-mean epilogue and the backward's pooled-gradient prologue
+    (b200r_softras_forward_aa / _backward_aa) against render-at-2x + avg_pool2d + autograd (rasterizer.py:45,54-55)."""
+    import torch
+    from jrender_b200 import SoftRasterizer
+
+    class M:
+        pass
+    fv, tex = wl.make_scene(280, batch=2)
+    res = {}
+    for fused in (True, False):
+        m = M()
+        m.face_vertices = torch.from_numpy(fv).cuda().requires_grad_(True)
+        m.face_textures = torch.from_numpy(tex).cuda().requires_grad_(True)
+        r = SoftRasterizer(image_size=50, anti_aliasing=True, fill_back=True, sigma_val=3e-5)
+        r.fused_antialiasing = fused
+        out = r(m, mode)
+        outs = list(out) if isinstance(out, tuple) else [out]
+        rng = np.random.default_rng(4)
+        torch.autograd.backward(outs, [torch.from_numpy(rng.uniform(-1, 1, tuple(o.shape)).astype(np.float32)).cuda() for o in outs])
+        res[fused] = ([o.detach().cpu().numpy() for o in outs], m.face_vertices.grad.cpu().numpy(),
+                      None if m.face_textures.grad is None else m.face_textures.grad.cpu().numpy())
+    for a, b_ in zip(res[True][0], res[False][0]):
+        assert a.shape == b_.shape and np.abs(a - b_).max() <= 1e-7
+    assert np.abs(res[True][1] - res[False][1]).max() <= GRAD_RTOL * np.abs(res[False][1]).max()
+    if res[False][2] is not None and np.abs(res[False][2]).max() > 0:
+        assert np.abs(res[True][2] - res[False][2]).max() <= GRAD_RTOL * np.abs(res[False][2]).max()
 
 
 def test_exact_tail_option(cuda_device):

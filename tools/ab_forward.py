@@ -46,20 +46,14 @@ def main():
         SoftRasterizeFunction(image_size=H)(fv, tex).backward(grad)
 
     res = {"workload": desc}
-    for warps, variant, persistent in ((8, 0, 0), (8, 1, 1), (2, 1, 1), (1, 1, 1)):
-        _lib.set_option("softras_fwd_warps", warps)
+    for variant, persistent in ((1, 1), (1, 0), (2, 1)):
         _lib.set_option("softras_fwd_variant", variant)
         _lib.set_option("softras_fwd_persistent", persistent)
         for _ in range(3):
             step()
-        res["warps%d_variant%d_persistent%d" % (warps, variant, persistent)] = kernel_times(L, 10, step)
-    _lib.set_option("softras_fwd_warps", 1)
-    for bv in (0, 1):
-        _lib.set_option("softras_bwd_variant", bv)
-        for _ in range(3):
-            step()
-        res["bwd_variant%d" % bv] = kernel_times(L, 10, step)
-    _lib.set_option("softras_bwd_variant", 1)
+        res["variant%d_persistent%d" % (variant, persistent)] = kernel_times(L, 10, step)
+    _lib.set_option("softras_fwd_variant", 1)
+    _lib.set_option("softras_fwd_persistent", 1)
     print(json.dumps(res), flush=True)
 
     from oracle import ref_gpu, softras as osr
