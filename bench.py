@@ -632,7 +632,8 @@ def run_deform(args, rank, world, local_rank):
     print(json.dumps({
         "metric": "demo2_deform_views_per_s_512px", "value": views * 1000.0 / best["ms_per_iter"], "unit": "frames/s",
         "n_gpus": world, "steps": iters, "warmup": 3, "ms_per_step": best["ms_per_iter"], "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "reference assets (baseline/_ref/assets)" if staged else "synthetic",
         "config": {"workload": desc, "optimizer": "Adam(0.01, betas=(0.5, 0.99))", "sigma_val": 1e-4, "mode": "silhouettes"},
         "modes": out, "gpu_launches": out["eager"]["library_launches"]}), flush=True)
 
@@ -657,7 +658,7 @@ def run_render(args, rank, world, local_rank):
     mesh = jr.Mesh.from_obj(obj, load_texture=True, texture_res=5, texture_type='surface', dr_type='softras').to(dev)
     load_s = time.perf_counter() - t0
     renderer = jr.Renderer(dr_type='softras')
-    host = torch.empty((1, 4, H, H), dtype=torch.float32).pin_memory()
+    host = torch.empty((1, 3, H, H), dtype=torch.float32).pin_memory()   # mode='rgb' returns images[:, :3]
 
     def frame(az):
         mesh.reset_()
@@ -688,7 +689,7 @@ def run_render(args, rank, world, local_rank):
         kern[name] = {"avg_ms": t.value / max(1, n.value), "launches_per_step": n.value / 5}
     if rank != 0:
         return
-    cover = float((host[0, 3] > 0.5).float().mean())
+    cover = float((host[0].sum(0) > 0.05).float().mean())
     print(json.dumps({
         "metric": "demo1_render_frames_per_s_256px", "value": args.steps / wall, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": 1000.0 * wall / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -696,8 +697,8 @@ def run_render(args, rank, world, local_rank):
         "config": {"workload": desc, "params": "Renderer(dr_type='softras') defaults: sigma 1e-5, gamma 1e-4, ambient 0.5 + directional 0.5, fill_back"},
         "device_ms_per_frame": {"min": float(np.min(ms)), "median": float(np.median(ms)), "max": float(np.max(ms))},
         "what": "host wall clock over the loop: mesh.reset_ + set_eyes + lighting + transform + rasterize (forward) + D2H of the image, one view per call",
-        "load_and_bake_s": load_s, "alpha_coverage": cover, "gpu_launches": int(launches), "kernels": kern,
-        "e2e": {"value": args.steps / wall, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 4 * H * H * 4}}), flush=True)
+        "load_and_bake_s": load_s, "lit_pixel_fraction": cover, "gpu_launches": int(launches), "kernels": kern,
+        "e2e": {"value": args.steps / wall, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 3 * H * H * 4}}), flush=True)
 
 
 def main():

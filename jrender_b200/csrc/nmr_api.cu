@@ -1,4 +1,5 @@
 // nmr_api.cu -- C ABI entry points for the NMR (dr_type='n3mr') path (see include/b200raster.h).
+#include <atomic>
 #include <cmath>
 #include <cstring>
 
@@ -9,12 +10,16 @@
 using namespace b200r;
 
 namespace {
+// SM count of the CURRENT device (cached per ordinal: one process may drive several GPUs)
 int nmr_sm_count() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
+    static std::atomic<int> cache[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const int slot = (dev >= 0 && dev < 64) ? dev : 63;
+    int n = cache[slot].load();
+    if (n == 0 || dev >= 64) {
         if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cache[slot].store(n);
     }
     return n;
 }

@@ -2,27 +2,18 @@
 // forward_soft_rasterize_cuda_kernel, cuda/soft_rasterize.py:243-456 and
 // cuda/soft_rasterize_coarse_to_fine.py:513-761).
 //
-// One CTA of WX*WY warps processes (8*WX)x(4*WY) pixel tiles, one thread = one pixel, each warp
-// owns an 8x4 sub-rectangle.  <WX,WY> = <2,4> is the classic 16x16 tile; <1,1> makes every
-// warp an autonomous 8x4 worker with no CTA-wide barrier at all, which removes the
-// intra-CTA imbalance (a warp whose block sits on a mesh pole has 10x the work of its
-// neighbours) at the price of every warp filtering the coarse list itself.
-// Per tile the CTA walks its coarse bin's face list (ascending face id),
-// keeps the faces whose check_border rectangle touches the tile (ordered ballot compaction),
-// stages their 160-byte records in shared memory in rounds, and every warp narrows
-// the round to the faces touching its 8x4 footprint.  Then
-//   VARIANT 0: the warp walks that list in lock-step; a lane works when its pixel lies in
-//              the face's rectangle (~50 % lane utilisation on small triangles);
-//   VARIANT 1: every lane first compacts ITS OWN list of faces (indices in shared memory)
-//              and the lanes then walk their private lists in lock-step, so all lanes work
-//              until the shortest lists run out.
-// Either way each pixel visits its faces in ascending id exactly like the reference's
-// `for (fn = 0; fn < nf; fn++)` (:311), minus the faces check_border would skip.
+// One warp = one CTA = an autonomous worker on 8x4 pixel blocks, one lane per pixel, no CTA-wide barrier anywhere: a
+// warp sitting on a mesh pole (10x the work of its neighbours) stalls nobody.  (16x16 and 16x4 multi-warp CTAs were the
+// first two versions; stall_barrier was their top stall reason.)  Per block the warp walks its coarse bin's face list
+// (ascending face id), keeps the faces whose check_border rectangle touches the block (ordered ballot compaction), stages
+// their 160-byte records in shared memory 16 at a time, every lane marks the staged faces that cover ITS pixel in a
+// private 16-bit mask, and the lanes then walk their masks in lock-step (lowest bit = lowest face id): each pixel visits
+// its faces in ascending id exactly like the reference's `for (fn = 0; fn < nf; fn++)` (:311), minus the faces
+// check_border would skip.
 //
-// Scheduling: `tile_counter == nullptr` -> one CTA per tile (blockIdx); otherwise a
-// persistent grid pulls tiles from an atomic queue ordered by descending cost (number of
-// (pixel, face) pairs per tile, computed by k_coarse_bin and bucket-sorted by k_tile_order):
-// tiles at poles / silhouettes of a mesh can cost 10x the mean and must start first.
+// Scheduling: `tile_counter == nullptr` -> one CTA per block (blockIdx); otherwise a persistent grid pulls blocks from an
+// atomic queue ordered by descending cost (number of (pixel, face) pairs per block, computed by k_coarse_bin and
+// bucket-sorted by k_tile_order): blocks at poles / silhouettes of a mesh can cost 10x the mean and must start first.
 #pragma once
 #include "softras_math.cuh"
 #include "softras_setup.cuh"
@@ -38,59 +29,60 @@ struct __align__(16) FaceRecS {
     uint4 pad;
 };
 
-#ifndef B200R_FWD_MASKLIST
-#define B200R_FWD_MASKLIST 1   // 1-warp CTAs: a lane's private face list is a bit mask in a register, not bytes in shared memory
-#endif
-#ifndef B200R_FWD_LANEMASK
-#define B200R_FWD_LANEMASK 1   // 1-warp CTAs: build the per-lane face masks by transposing per-record lane masks
-#endif
-#ifndef B200R_FWD_CHUNK1
-#define B200R_FWD_CHUNK1 16   // records staged per round by a 1-warp CTA
+#ifndef B200R_FWD_TMA
+#define B200R_FWD_TMA 0       // 1: records staged by cp.async.bulk (TMA) + mbarrier instead of LDG -> registers -> STS
 #endif
 #ifndef B200R_FWD_MINB1
-#define B200R_FWD_MINB1 24    // resident 1-warp CTAs per SM the register allocation must allow
-#endif
-#ifndef B200R_FWD_MINB1_SIL
-// Silhouette instantiations (RGB none) have their own occupancy target because ptxas' register allocation differs:
-// while the pair loop still spilled at the 80-register cap, 20 CTAs/SM (96 registers) was 18 % faster on the C5
-// forward; after the register-pressure work (guards seeded with consts_ok, mask lists) 24 wins again
-// (1.83 vs 2.22 ms, 60 views), as it always did for the colour instantiations (C3: 0.873 vs 0.910 ms).
-#define B200R_FWD_MINB1_SIL 24
+#define B200R_FWD_MINB1 24    // resident one-warp CTAs per SM the register allocation must allow (80 registers)
 #endif
 
-template <int NW>
-struct FwdCfg {
-    static constexpr int NT = 32 * NW;
-    static constexpr int CHUNK = NW >= 8 ? 128 : (NW >= 2 ? 64 : B200R_FWD_CHUNK1);  // staged faces per round (index fits uint8)
-    static constexpr int UNR = NW >= 8 ? 1 : (NW >= 2 ? 2 : 4);         // coarse entries filtered per thread per pass
-};
-
-template <int NW>
-struct FwdSmem {
-    FaceRecS rec[FwdCfg<NW>::CHUNK];                     // reused as the output staging area
-    int ids[FwdCfg<NW>::CHUNK + FwdCfg<NW>::UNR * FwdCfg<NW>::NT];  // pending tile-face ids, ascending
-    unsigned char wlist[NW][FwdCfg<NW>::CHUNK];          // per-warp sub-list (indices into rec[])
-    uint32_t lmask[32];                                  // 1-warp CTAs: per staged record, the lanes whose pixel it covers
-    int s_warp[NW];
-    int s_tile;
-};
-
-template <int NW>
-__device__ __forceinline__ void cta_sync() {
-    if (NW == 1) __syncwarp();
-    else __syncthreads();
+// ---- mbarrier / bulk-copy (TMA) helpers ------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t f2_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void f2_mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(f2_smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
+__device__ __forceinline__ void f2_mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(f2_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void f2_bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(f2_smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(f2_smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void f2_mbar_wait(unsigned long long* bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done)
+                     : "r"(f2_smem_u32(bar)), "r"(parity)
+                     : "memory");
+    } while (!done);
+}
+// generic-proxy accesses to shared memory (the previous round's reads, the output staging writes) ordered before the
+// async-proxy writes of the next bulk copies
+__device__ __forceinline__ void f2_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+constexpr int kFwdChunk = 16;   // records staged per round: 16 rather than 32 keeps 24 warps resident per SM
+constexpr int kFwdUnr = 4;      // coarse entries filtered per lane per pass
+
+struct FwdSmem {
+    FaceRecS rec[kFwdChunk];                   // staged records; reused as the output staging area
+    int ids[kFwdChunk + kFwdUnr * 32];         // pending block-face ids, ascending
+    __align__(16) uint32_t lmask[kFwdChunk];   // per staged record, the lanes whose pixel it covers
+    unsigned long long mbar;                   // B200R_FWD_TMA: completion barrier of the bulk copies
+    unsigned long long pad_;
+};
+static_assert(sizeof(FwdSmem) % 16 == 0, "the top-K depth lists behind FwdSmem are read with 16-byte loads");
 
 // Per-pixel depth list stride in floats: K rounded up to a multiple of 4, plus 4.  Pixel-major so that the
 // "find the new maximum" rescan reads a lane's K depths with K/4 LDS.128; stride/4 is odd for K = 8, 16, 32, 64,
 // which makes those 16-byte accesses bank-conflict free across the 8 lanes of a quarter warp.
 __host__ __device__ static inline int fwd_qz_stride(int K) { return ((K + 3) / 4) * 4 + 4; }
 
-// dynamic shared memory: FwdSmem<NW> | qz [NT][stride] f32 | qid [K][NT] i32 | plist [CHUNK][NT] u8 (VARIANT 1)
-template <int NW>
-static inline size_t fwd_smem_bytes(int K, int variant) {
-    size_t b = sizeof(FwdSmem<NW>) + (size_t)FwdCfg<NW>::NT * (fwd_qz_stride(K) + K) * 4;
-    if (variant == 1 && !(B200R_FWD_MASKLIST && FwdCfg<NW>::CHUNK <= 32)) b += (size_t)FwdCfg<NW>::CHUNK * FwdCfg<NW>::NT;
+// dynamic shared memory: FwdSmem | qz [32][stride] f32 | qid [K][32] i32
+static inline size_t fwd_smem_bytes(int K) {
+    const size_t b = sizeof(FwdSmem) + (size_t)32 * (fwd_qz_stride(K) + K) * 4;
     return (b + 15) & ~(size_t)15;
 }
 
@@ -306,74 +298,60 @@ __device__ __forceinline__ void store_pooled_8x4(const float* s_out, float* __re
     if (orow < hp && ocol < hp) pooled[(((size_t)b * 4 + ch) * hp + orow) * hp + ocol] = v;
 }
 
-__device__ __forceinline__ bool pixel_in_rect(const FaceRec* rec, int px, int row) {
-    const uint32_t rx = rec->rect_x, rr = rec->rect_r;
-    const uint32_t x0 = rx & 0xffffu, r0 = rr & 0xffffu;
-    return (uint32_t)(px - (int)x0) <= (rx >> 16) - x0 && (uint32_t)(row - (int)r0) <= (rr >> 16) - r0;
-}
-
-template <int DIST, int RGB, int VARIANT, int WX, int WY, bool EXACT>
-__global__ void __launch_bounds__(32 * WX * WY, (WX * WY >= 8) ? 2 : ((WX * WY >= 2) ? 8 : (RGB == 2 ? B200R_FWD_MINB1_SIL : B200R_FWD_MINB1)))
+template <int DIST, int RGB, bool EXACT>
+__global__ void __launch_bounds__(32, B200R_FWD_MINB1)
 k_softras_forward(const SoftRasParams P, const FaceRec* __restrict__ recs, const uint2* __restrict__ rects,
                   const int* __restrict__ coarse_cnt, const int* __restrict__ coarse_ids,
                   const float* __restrict__ textures, float* __restrict__ soft_colors,
                   float* __restrict__ aggrs_info, int* __restrict__ ids_out, int* tile_counter,
                   const int* __restrict__ tile_order, float* __restrict__ pooled) {
-    constexpr int NW = WX * WY, NT = 32 * NW, CHUNK = FwdCfg<NW>::CHUNK, UNR = FwdCfg<NW>::UNR;
-    constexpr int TW = 8 * WX, TH = 4 * WY;
+    constexpr int NT = 32, CHUNK = kFwdChunk, UNR = kFwdUnr, TW = 8, TH = 4;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    FwdSmem<NW>& S = *reinterpret_cast<FwdSmem<NW>*>(smem_raw);
+    FwdSmem& S = *reinterpret_cast<FwdSmem*>(smem_raw);
     const int qzs = fwd_qz_stride(P.K);
-    float* s_qz_all = reinterpret_cast<float*>(smem_raw + sizeof(FwdSmem<NW>));  // [NT][qzs]
-    int* s_qid = reinterpret_cast<int*>(s_qz_all + (size_t)NT * qzs);             // [K][NT]
-    unsigned char* s_plist = reinterpret_cast<unsigned char*>(s_qid + (size_t)P.K * NT);  // VARIANT 1: [CHUNK][NT]
-    float* s_qz = s_qz_all + (size_t)threadIdx.x * qzs;                           // this pixel's K depths, slot order
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float* s_qz_all = reinterpret_cast<float*>(smem_raw + sizeof(FwdSmem));   // [32][qzs]
+    int* s_qid = reinterpret_cast<int*>(s_qz_all + (size_t)NT * qzs);         // [K][32]
+    const int lane = threadIdx.x;
+    float* s_qz = s_qz_all + (size_t)lane * qzs;                              // this pixel's K depths, slot order
     const int is = P.is, nf = P.nf, K = P.K;
     const int tiles_per_image = P.fntx * P.fnty;
-    const int lx = (warp % WX) * 8 + (lane & 7), ly = (warp / WX) * 4 + (lane >> 3);
-    const int tpix = ly * (8 * WX) + lx;  // pixel index inside the tile, row-major: the index of the [K][TH][TW] id planes
+    const int lx = lane & 7, ly = lane >> 3;   // lane = row-major pixel index inside the block = index of the [K][4][8] id planes
     const float threshold = P.dist_eps * P.sigma;  // :289
     const size_t npix = (size_t)is * is;
     DivConst dc;
     dc.init(P);
     const bool consts_ok = dc.consts_ok();
     const float softmax_sum0 = expf(P.eps / P.gamma);
+    const uint32_t lt_mask = (1u << lane) - 1u;
+#if B200R_FWD_TMA
+    if (lane == 0) f2_mbar_init(&S.mbar, 1);
+    __syncwarp();
+    uint32_t parity = 0;
+#endif
 
     for (int titer = 0;; titer++) {
-        // ---- which tile
+        // ---- which block
         int t;
         if (tile_counter == nullptr) {
             if (titer > 0) break;
             t = blockIdx.y * tiles_per_image + blockIdx.x;
         } else {
-            cta_sync<NW>();  // previous tile fully written, S.s_tile free
+            __syncwarp();  // previous block fully written
             int q = 0;
-            if (NW == 1) {
-                if (lane == 0) q = atomicAdd(tile_counter, 1);
-                q = __shfl_sync(0xffffffffu, q, 0);
-            } else {
-                if (tid == 0) S.s_tile = atomicAdd(tile_counter, 1);
-                __syncthreads();
-                q = S.s_tile;
-            }
+            if (lane == 0) q = atomicAdd(tile_counter, 1);
+            q = __shfl_sync(0xffffffffu, q, 0);
             if (q >= P.queue_len) break;
-            t = __ldg(tile_order + q);  // most expensive tiles first (k_tile_order)
-            if (t < 0) continue;        // hole: partial cost tile at the image edge
+            t = __ldg(tile_order + q);  // most expensive blocks first (k_tile_order)
+            if (t < 0) continue;
         }
         const int b = t / tiles_per_image;
         const int tt = t - b * tiles_per_image;
         const int tx = tt % P.fntx, ty = tt / P.fntx;
-        const int px = tx * TW + lx, row = ty * TH + ly;
+        const int tx0 = tx * TW, tx1 = tx0 + TW - 1;   // block footprint (inclusive pixel ranges)
+        const int tr0 = ty * TH, tr1 = tr0 + TH - 1;
+        const int px = tx0 + lx, row = tr0 + ly;
         const float xp = b200r_pix_coord(px, is);
         const float yp = b200r_pix_coord(is - 1 - row, is);
-
-        // tile / warp footprints (inclusive pixel ranges)
-        const int tx0 = tx * TW, tx1 = tx0 + TW - 1;
-        const int tr0 = ty * TH, tr1 = tr0 + TH - 1;
-        const int wx0 = tx0 + (warp % WX) * 8, wx1 = wx0 + 7;
-        const int wr0 = tr0 + (warp / WX) * 4, wr1 = wr0 + 3;
 
         // ---- per-pixel state, initialised as :291-309 (background buffer is all zero, Q1)
         PixState st;
@@ -388,12 +366,12 @@ k_softras_forward(const SoftRasParams P, const FaceRec* __restrict__ recs, const
         st.q_size = 0;
         st.q_max_z = -1.f;
         st.q_max_id = -1;
-        // id slots start as -1 (the reference memsets the whole buffer, :470): the tile's ids are then written
-        // out plane by plane as 16-byte row segments straight from shared memory.  The previous tile's stores
-        // finished reading s_qid at the cta_sync at the top of this iteration.
+        // id slots start as -1 (the reference memsets the whole buffer, :470): the block's ids are then written out plane
+        // by plane as 16-byte row segments straight from shared memory.  The previous block's stores finished reading
+        // s_qid at the __syncwarp at the top of this iteration.
         const bool vec_ids = ((is & 3) == 0) && ((K & 3) == 0);
         if (vec_ids) {
-            for (int j = tid; j < K * NT / 4; j += NT) reinterpret_cast<int4*>(s_qid)[j] = make_int4(-1, -1, -1, -1);
+            for (int j = lane; j < K * NT / 4; j += NT) reinterpret_cast<int4*>(s_qid)[j] = make_int4(-1, -1, -1, -1);
         }
 
         const int cbin = (tr0 / P.coarse_px) * P.ncs + (tx0 / P.coarse_px);
@@ -403,25 +381,24 @@ k_softras_forward(const SoftRasParams P, const FaceRec* __restrict__ recs, const
         const FaceRec* brecs = recs + (size_t)b * nf;
         const float* btex = textures + (size_t)b * nf * P.T * 3;
 
-        int n_pending = 0, head = 0;  // pending ids live in S.ids[head, head + n_pending); uniform across the CTA
+        int n_pending = 0, head = 0;  // pending ids live in S.ids[head, head + n_pending); warp-uniform
         for (int base = 0; base < n_coarse; base += NT * UNR) {
-            // ---- leftover of the previous pass (< CHUNK <= NT entries) back to the front
+            // ---- leftover of the previous pass (< CHUNK entries) back to the front
             if (head > 0) {
                 int keep = 0;
-                if (tid < n_pending) keep = S.ids[head + tid];
-                cta_sync<NW>();
-                if (tid < n_pending) S.ids[tid] = keep;
+                if (lane < n_pending) keep = S.ids[head + lane];
+                __syncwarp();
+                if (lane < n_pending) S.ids[lane] = keep;
                 head = 0;
             }
-            // ---- fine filter: next UNR*NT coarse entries -> S.ids (ordered).  All id loads are
-            // issued before the dependent rectangle gathers so one pass costs two memory
-            // latencies, not 2*UNR.
+            // ---- fine filter: next UNR*32 coarse entries -> S.ids (ordered).  All id loads are issued before the
+            // dependent rectangle gathers so one pass costs two memory latencies, not 2*UNR.
             {
                 int id[UNR];
                 uint2 rc[UNR];
 #pragma unroll
                 for (int u = 0; u < UNR; u++) {
-                    const int i = base + u * NT + tid;
+                    const int i = base + u * NT + lane;
                     id[u] = (i < n_coarse) ? __ldg(clist + i) : -1;
                 }
 #pragma unroll
@@ -429,23 +406,31 @@ k_softras_forward(const SoftRasParams P, const FaceRec* __restrict__ recs, const
 #pragma unroll
                 for (int u = 0; u < UNR; u++) {
                     const bool pass = id[u] >= 0 && rect_overlaps(rc[u], tx0, tx1, tr0, tr1);
-                    int total;
-                    const int off = n_pending + block_excl_scan_flag<NW>(pass, S.s_warp, total);
-                    if (pass) S.ids[off] = id[u];
-                    n_pending += total;
+                    const unsigned bal = __ballot_sync(0xffffffffu, pass);
+                    if (pass) S.ids[n_pending + __popc(bal & lt_mask)] = id[u];
+                    n_pending += __popc(bal);
                 }
             }
             const bool last = base + NT * UNR >= n_coarse;
 
             while (n_pending >= CHUNK || (last && n_pending > 0)) {
                 const int m = min(n_pending, CHUNK);
-                cta_sync<NW>();  // S.ids complete; previous round's readers of S.rec done
-                // ---- stage m records: 10 x uint4 per face, coalesced, 5 loads in flight per thread
+                __syncwarp();  // S.ids complete; previous round's readers of S.rec done
+#if B200R_FWD_TMA
+                // ---- stage m records: one 160-byte bulk copy each, completion counted in bytes on the mbarrier
+                f2_fence_async_smem();
+                if (lane == 0) f2_mbar_expect_tx(&S.mbar, (uint32_t)m * (uint32_t)sizeof(FaceRec));
+                __syncwarp();
+                if (lane < m) f2_bulk_g2s(&S.rec[lane].r, brecs + S.ids[head + lane], (uint32_t)sizeof(FaceRec), &S.mbar);
+                f2_mbar_wait(&S.mbar, parity);
+                parity ^= 1u;
+#else
+                // ---- stage m records: 10 x uint4 per face, coalesced, 5 loads in flight per lane
                 for (int j0 = 0; j0 < m * B200R_REC_UINT4; j0 += NT * 5) {
                     uint4 v[5];
 #pragma unroll
                     for (int u = 0; u < 5; u++) {
-                        const int j = j0 + u * NT + tid;
+                        const int j = j0 + u * NT + lane;
                         if (j < m * B200R_REC_UINT4) {
                             const int f = j / B200R_REC_UINT4, q = j - f * B200R_REC_UINT4;
                             v[u] = __ldg(reinterpret_cast<const uint4*>(brecs + S.ids[head + f]) + q);
@@ -453,98 +438,48 @@ k_softras_forward(const SoftRasParams P, const FaceRec* __restrict__ recs, const
                     }
 #pragma unroll
                     for (int u = 0; u < 5; u++) {
-                        const int j = j0 + u * NT + tid;
+                        const int j = j0 + u * NT + lane;
                         if (j < m * B200R_REC_UINT4) {
                             const int f = j / B200R_REC_UINT4, q = j - f * B200R_REC_UINT4;
                             reinterpret_cast<uint4*>(&S.rec[f])[q] = v[u];
                         }
                     }
                 }
-                cta_sync<NW>();
-                // ---- warp sub-list (the whole round when the warp is the CTA)
-                int wcnt = 0;
-                if (NW > 1) {
-                    for (int j0 = 0; j0 < m; j0 += 32) {
-                        const int j = j0 + lane;
-                        bool pass = false;
-                        if (j < m) pass = rect_overlaps(make_uint2(S.rec[j].r.rect_x, S.rec[j].r.rect_r), wx0, wx1, wr0, wr1);
-                        const unsigned bal = __ballot_sync(0xffffffffu, pass);
-                        if (pass) S.wlist[warp][wcnt + __popc(bal & ((1u << lane) - 1u))] = (unsigned char)j;
-                        wcnt += __popc(bal);
+                __syncwarp();
+#endif
+                // ---- per-lane face masks by transposition: lane j turns record j's rectangle, clipped to the 8x4
+                // block, into the 32-bit set of covered lanes (a column mask replicated over the covered rows); every
+                // lane then picks its own bit out of the 16 words (4 broadcast LDS.128).  ~40 instructions per round
+                // instead of 16 x (rectangle load + two range tests).
+                uint32_t lm = 0u;
+                if (lane < m) {
+                    const uint32_t rx = S.rec[lane].r.rect_x, rr = S.rec[lane].r.rect_r;
+                    const int cx0 = max((int)(rx & 0xffffu) - tx0, 0), cx1 = min((int)(rx >> 16) - tx0, 7);
+                    const int ry0 = max((int)(rr & 0xffffu) - tr0, 0), ry1 = min((int)(rr >> 16) - tr0, 3);
+                    if (cx0 <= cx1 && ry0 <= ry1) {
+                        const uint32_t cols = (2u << cx1) - (1u << cx0);
+                        const uint32_t rows = (0xffffffffu >> (24 - 8 * ry1)) & (0xffffffffu << (8 * ry0));
+                        lm = (cols * 0x01010101u) & rows;
                     }
-                    __syncwarp();
-                } else {
-                    wcnt = m;
                 }
-
-                if (VARIANT == 0) {
-                    // ---- warp walks its list in lock-step
-                    for (int it = 0; it < wcnt; it++) {
-                        const FaceRec* rec = &S.rec[NW > 1 ? (int)S.wlist[warp][it] : it].r;
-                        if (!pixel_in_rect(rec, px, row)) continue;
-                        shade_pair<DIST, RGB, NT, EXACT>(rec, st, P, dc, xp, yp, threshold, s_qz, s_qid, tpix, btex, consts_ok);
-                    }
-                } else {
-                    // ---- each lane compacts its own list, then lanes walk private lists
-                    if constexpr (B200R_FWD_MASKLIST && CHUNK <= 32) {
-                        // the list is a bit mask over the staged records (ascending record = ascending face id)
-                        unsigned mask = 0u;
-                        if constexpr (B200R_FWD_LANEMASK && NW == 1 && (CHUNK == 16 || CHUNK == 32)) {
-                            // Transposed build: lane j turns record j's rectangle, clipped to the 8x4 block, into the
-                            // 32-bit set of covered lanes (a column mask replicated over the covered rows); every lane
-                            // then picks its own bit out of the 16 words (4 broadcast LDS.128).  ~40 instructions per
-                            // round instead of 16 x (rectangle load + two range tests).
-                            uint32_t lm = 0u;
-                            if (lane < wcnt) {
-                                const uint32_t rx = S.rec[lane].r.rect_x, rr = S.rec[lane].r.rect_r;
-                                const int cx0 = max((int)(rx & 0xffffu) - tx0, 0), cx1 = min((int)(rx >> 16) - tx0, 7);
-                                const int ry0 = max((int)(rr & 0xffffu) - tr0, 0), ry1 = min((int)(rr >> 16) - tr0, 3);
-                                if (cx0 <= cx1 && ry0 <= ry1) {
-                                    const uint32_t cols = (2u << cx1) - (1u << cx0);
-                                    const uint32_t rows = (0xffffffffu >> (24 - 8 * ry1)) & (0xffffffffu << (8 * ry0));
-                                    lm = (cols * 0x01010101u) & rows;
-                                }
-                            }
-                            if (lane < CHUNK) S.lmask[lane] = lm;
-                            __syncwarp();
+                if (lane < CHUNK) S.lmask[lane] = lm;
+                __syncwarp();
+                unsigned mask = 0u;   // bit j: staged record j covers this lane's pixel (ascending record = ascending face id)
 #pragma unroll
-                            for (int q = 0; q < CHUNK / 4; q++) {
-                                const uint4 m4 = reinterpret_cast<const uint4*>(S.lmask)[q];
-                                mask |= ((m4.x >> lane) & 1u) << (4 * q + 0);
-                                mask |= ((m4.y >> lane) & 1u) << (4 * q + 1);
-                                mask |= ((m4.z >> lane) & 1u) << (4 * q + 2);
-                                mask |= ((m4.w >> lane) & 1u) << (4 * q + 3);
-                            }
-                        } else {
-                            for (int it = 0; it < wcnt; it++) {
-                                const int j = NW > 1 ? (int)S.wlist[warp][it] : it;
-                                if (pixel_in_rect(&S.rec[j].r, px, row)) mask |= 1u << j;
-                            }
-                        }
-                        const int maxcnt = __reduce_max_sync(0xffffffffu, __popc(mask));
-                        for (int i = 0; i < maxcnt; i++) {
-                            if (mask != 0u) {
-                                const FaceRec* rec = &S.rec[__ffs(mask) - 1].r;
-                                mask &= mask - 1u;
-                                shade_pair<DIST, RGB, NT, EXACT>(rec, st, P, dc, xp, yp, threshold, s_qz, s_qid, tpix, btex, consts_ok);
-                            }
-                        }
-                    } else {
-                    int cnt = 0;
-                    for (int it = 0; it < wcnt; it++) {
-                        const int j = NW > 1 ? (int)S.wlist[warp][it] : it;
-                        if (pixel_in_rect(&S.rec[j].r, px, row)) {
-                            s_plist[cnt * NT + tid] = (unsigned char)j;
-                            cnt++;
-                        }
-                    }
-                    const int maxcnt = __reduce_max_sync(0xffffffffu, cnt);
-                    for (int i = 0; i < maxcnt; i++) {
-                        if (i < cnt) {
-                            const FaceRec* rec = &S.rec[s_plist[i * NT + tid]].r;
-                            shade_pair<DIST, RGB, NT, EXACT>(rec, st, P, dc, xp, yp, threshold, s_qz, s_qid, tpix, btex, consts_ok);
-                        }
-                    }
+                for (int q = 0; q < CHUNK / 4; q++) {
+                    const uint4 m4 = reinterpret_cast<const uint4*>(S.lmask)[q];
+                    mask |= ((m4.x >> lane) & 1u) << (4 * q + 0);
+                    mask |= ((m4.y >> lane) & 1u) << (4 * q + 1);
+                    mask |= ((m4.z >> lane) & 1u) << (4 * q + 2);
+                    mask |= ((m4.w >> lane) & 1u) << (4 * q + 3);
+                }
+                // ---- the lanes walk their masks in lock-step
+                const int maxcnt = __reduce_max_sync(0xffffffffu, __popc(mask));
+                for (int i = 0; i < maxcnt; i++) {
+                    if (mask != 0u) {
+                        const FaceRec* rec = &S.rec[__ffs(mask) - 1].r;
+                        mask &= mask - 1u;
+                        shade_pair<DIST, RGB, NT, EXACT>(rec, st, P, dc, xp, yp, threshold, s_qz, s_qid, lane, btex, consts_ok);
                     }
                 }
                 head += m;
@@ -568,21 +503,21 @@ k_softras_forward(const SoftRasParams P, const FaceRec* __restrict__ recs, const
             o0 = o1 = o2 = 0.f; g0 = g1 = 0.f;
         }
 
-        // Stage the 6 output planes of the tile in shared memory and write each plane row with
-        // 16-byte stores (TW*4 contiguous bytes per tile row).
-        cta_sync<NW>();
-        float* s_out = reinterpret_cast<float*>(S.rec);  // 6 * NT floats
-        s_out[0 * NT + tpix] = o0;
-        s_out[1 * NT + tpix] = o1;
-        s_out[2 * NT + tpix] = o2;
-        s_out[3 * NT + tpix] = out_a;
-        s_out[4 * NT + tpix] = g0;
-        s_out[5 * NT + tpix] = g1;
-        cta_sync<NW>();
-        if (NW == 1 && pooled != nullptr) store_pooled_8x4(s_out, pooled, b, tx0, tr0, is, lane);
+        // Stage the 6 output planes of the block in shared memory and write each plane row with 16-byte stores
+        // (32 contiguous bytes per block row).
+        __syncwarp();
+        float* s_out = reinterpret_cast<float*>(S.rec);  // 6 * 32 floats
+        s_out[0 * NT + lane] = o0;
+        s_out[1 * NT + lane] = o1;
+        s_out[2 * NT + lane] = o2;
+        s_out[3 * NT + lane] = out_a;
+        s_out[4 * NT + lane] = g0;
+        s_out[5 * NT + lane] = g1;
+        __syncwarp();
+        if (pooled != nullptr) store_pooled_8x4(s_out, pooled, b, tx0, tr0, is, lane);   // anti-aliasing epilogue
         if ((is & 3) == 0) {
-            constexpr int QPR = TW / 4;  // float4 per tile row
-            for (int j = tid; j < 6 * TH * QPR; j += NT) {
+            constexpr int QPR = TW / 4;  // float4 per block row
+            for (int j = lane; j < 6 * TH * QPR; j += NT) {
                 const int ch = j / (TH * QPR), r = (j % (TH * QPR)) / QPR, q = j % QPR;
                 const int orow = tr0 + r, ocol = tx0 + q * 4;
                 if (orow < is && ocol < is) {
@@ -593,7 +528,7 @@ k_softras_forward(const SoftRasParams P, const FaceRec* __restrict__ recs, const
                 }
             }
         } else {
-            for (int j = tid; j < 6 * NT; j += NT) {
+            for (int j = lane; j < 6 * NT; j += NT) {
                 const int ch = j / NT, r = (j % NT) / TW, c = j % TW;
                 const int orow = tr0 + r, ocol = tx0 + c;
                 if (orow < is && ocol < is) {
@@ -605,11 +540,11 @@ k_softras_forward(const SoftRasParams P, const FaceRec* __restrict__ recs, const
         }
         // top-K ids, slot order, -1 padded (replaces cudaMemsetAsync(out3_p, -1, ...) :470 + :453-455)
         if (vec_ids) {
-            // s_qid is [K][TH][TW]: int4 number u covers plane u / (NT/4), tile row (u % (NT/4)) / (TW/4)
-            // (every lane's own id writes were ordered before these cross-lane reads by the cta_sync above)
+            // s_qid is [K][4][8]: int4 number u covers plane u / 8, block row (u % 8) / 2 (every lane's own id writes were
+            // ordered before these cross-lane reads by the __syncwarp above)
             constexpr int QPR = TW / 4, QPP = NT / 4;
             int* bids = ids_out + (size_t)b * K * npix;
-            for (int u = tid; u < K * QPP; u += NT) {
+            for (int u = lane; u < K * QPP; u += NT) {
                 const int k = u / QPP, pq = u - k * QPP;
                 const int orow = tr0 + pq / QPR, ocol = tx0 + (pq % QPR) * 4;
                 if (orow < is && ocol < is)
@@ -618,7 +553,7 @@ k_softras_forward(const SoftRasParams P, const FaceRec* __restrict__ recs, const
         } else if (px < is && row < is) {
             int* dst = ids_out + (size_t)b * K * npix + (size_t)row * is + px;
             for (int k = 0; k < K; k++)
-                dst[(size_t)k * npix] = (k < st.q_size) ? s_qid[k * NT + tpix] : -1;
+                dst[(size_t)k * npix] = (k < st.q_size) ? s_qid[k * NT + lane] : -1;
         }
     }
 }

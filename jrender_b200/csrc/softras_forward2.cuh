@@ -37,33 +37,6 @@ namespace b200r {
 #define B200R_F2_DEFER_INSIDE 1
 #endif
 
-// ---- mbarrier / bulk-copy (TMA) helpers ------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t f2_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void f2_mbar_init(unsigned long long* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(f2_smem_u32(bar)), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void f2_mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(f2_smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void f2_bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(f2_smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(f2_smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void f2_mbar_wait(unsigned long long* bar, uint32_t parity) {
-    uint32_t done;
-    do {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(done)
-                     : "r"(f2_smem_u32(bar)), "r"(parity)
-                     : "memory");
-    } while (!done);
-}
-// generic-proxy accesses to shared memory (the previous round's reads, the output staging writes) ordered before the
-// async-proxy writes of the next bulk copies
-__device__ __forceinline__ void f2_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
 struct __align__(16) Fwd2Smem {
     FaceRecS rec[B200R_F2_R];                    // staged records (16-byte aligned: bulk-copy destination); reused as the output staging area
     __align__(16) uint32_t lmask[B200R_F2_R];    // per staged record: the lanes (pixels) inside its rectangle (read as uint4)

@@ -9,27 +9,35 @@
 using namespace b200r;
 
 namespace {
-template <int DIST, int RGB, int VARIANT, bool EXACT>
-cudaError_t launch_v(const SoftRasParams& P, const SoftRasWorkspace& W, const float* textures, float* soft_colors,
-                     float* aggrs_info, int32_t* ids, float* pooled, int persistent, cudaStream_t st) {
-    constexpr int WX = 1, WY = 1, NW = WX * WY, NT = 32 * NW;
-    const size_t smem = fwd_smem_bytes<NW>(P.K, VARIANT);
-    // attribute + occupancy are host calls: queried once per (instantiation, smem size)
-    static std::atomic<size_t> cfg_smem{0};
-    static std::atomic<int> cfg_occ{0};
-    if (cfg_smem.load() != smem) {
-        cudaError_t e = cudaFuncSetAttribute(k_softras_forward<DIST, RGB, VARIANT, WX, WY, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+constexpr int MAXDEV = 64;   // function attributes and occupancy are per DEVICE: cached per ordinal
+
+template <int DIST, int RGB, bool EXACT>
+cudaError_t launch_v1(const SoftRasParams& P, const SoftRasWorkspace& W, const float* textures, float* soft_colors,
+                      float* aggrs_info, int32_t* ids, float* pooled, int persistent, cudaStream_t st) {
+    const size_t smem = fwd_smem_bytes(P.K);
+    static std::atomic<size_t> cfg_smem[MAXDEV];
+    static std::atomic<int> cfg_occ[MAXDEV];
+    static std::atomic<int> cfg_sms[MAXDEV];
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const int slot = dev < MAXDEV ? dev : MAXDEV - 1;
+    if (cfg_smem[slot].load() != smem || dev >= MAXDEV) {
+        e = cudaFuncSetAttribute(k_softras_forward<DIST, RGB, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         // The persistent grid is sized for the occupancy the FULL shared-memory carve-out allows.  Left to the driver's
         // per-function heuristic the carve-out sometimes came out smaller: the same kernel then ran with fewer resident
         // CTAs than the grid assumed and was 25-35 % slower for the lifetime of the process (seen on C2 / C5).
-        e = cudaFuncSetAttribute(k_softras_forward<DIST, RGB, VARIANT, WX, WY, EXACT>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+        e = cudaFuncSetAttribute(k_softras_forward<DIST, RGB, EXACT>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return e;
-        int occ = 1;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_softras_forward<DIST, RGB, VARIANT, WX, WY, EXACT>, NT, smem);
+        int occ = 1, sms = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_softras_forward<DIST, RGB, EXACT>, 32, smem);
         if (e != cudaSuccess) return e;
-        cfg_occ.store(occ < 1 ? 1 : occ);
-        cfg_smem.store(smem);
+        e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return e;
+        cfg_occ[slot].store(occ < 1 ? 1 : occ);
+        cfg_sms[slot].store(sms < 1 ? 1 : sms);
+        cfg_smem[slot].store(smem);
     }
     const int tiles = P.fntx * P.fnty;
     int* counter = nullptr;
@@ -37,22 +45,21 @@ cudaError_t launch_v(const SoftRasParams& P, const SoftRasWorkspace& W, const fl
     if (persistent) {
         counter = W.counters;
         const long long total = (long long)tiles * P.B;
-        const long long slots = (long long)b200r_sm_count() * cfg_occ.load();
+        const long long slots = (long long)cfg_sms[slot].load() * cfg_occ[slot].load();
         grid = dim3((unsigned)(total < slots ? total : slots), 1);
     }
     {
         B200rProfScope prof(B200R_K_SOFTRAS_FWD, st);
-        k_softras_forward<DIST, RGB, VARIANT, WX, WY, EXACT><<<grid, NT, smem, st>>>(
+        k_softras_forward<DIST, RGB, EXACT><<<grid, 32, smem, st>>>(
             P, W.recs, W.rects, W.coarse_cnt, W.coarse_ids, textures, soft_colors, aggrs_info, ids, counter, W.tile_order, pooled);
     }
     return cudaGetLastError();
 }
 
-// two-phase kernel (softras_forward2.cuh).  Function attributes and occupancy are per DEVICE: cached per ordinal.
+// two-phase kernel (softras_forward2.cuh)
 template <int DIST, int RGB, bool EXACT>
 cudaError_t launch_v2(const SoftRasParams& P, const SoftRasWorkspace& W, const float* textures, float* soft_colors,
                       float* aggrs_info, int32_t* ids, float* pooled, int persistent, cudaStream_t st) {
-    constexpr int MAXDEV = 64;
     const size_t smem = fwd2_smem_bytes(P.K);
     static std::atomic<size_t> cfg_smem[MAXDEV];
     static std::atomic<int> cfg_occ[MAXDEV];
@@ -102,6 +109,6 @@ cudaError_t b200r_launch_forward(const SoftRasParams& P, const SoftRasWorkspace&
                                                         : launch_v2<D, R, true>(P, W, textures, soft_colors, aggrs_info, ids, pooled, persistent, st)))
         return e;
     }
-    B200R_DISPATCH_DIST_RGB((e = (D == 2 && !exact) ? launch_v<D, R, 1, (D != 2)>(P, W, textures, soft_colors, aggrs_info, ids, pooled, persistent, st) : launch_v<D, R, 1, true>(P, W, textures, soft_colors, aggrs_info, ids, pooled, persistent, st)))
+    B200R_DISPATCH_DIST_RGB((e = (D == 2 && !exact) ? launch_v1<D, R, (D != 2)>(P, W, textures, soft_colors, aggrs_info, ids, pooled, persistent, st) : launch_v1<D, R, true>(P, W, textures, soft_colors, aggrs_info, ids, pooled, persistent, st)))
     return e;
 }

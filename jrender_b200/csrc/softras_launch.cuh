@@ -6,7 +6,6 @@
 
 #include "common.cuh"
 
-int b200r_sm_count();
 // pooled: optional [B,4,is/2,is/2] 2x2 mean of soft_colors written by the forward (anti-aliasing epilogue), or nullptr
 cudaError_t b200r_launch_forward(const SoftRasParams& P, const SoftRasWorkspace& W, const float* textures, float* soft_colors,
                                  float* aggrs_info, int32_t* ids, float* pooled, int variant, int persistent, int exact, cudaStream_t st);

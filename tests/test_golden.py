@@ -22,7 +22,7 @@ from oracle import softras as osr
 from tests.conftest import ROOT
 
 ALL = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "ref_gpu_*.npz")))
-FILES = [p for p in ALL if "ref_gpu_nmr_" not in p]        # SoftRas fixtures
+FILES = [p for p in ALL if "ref_gpu_nmr_" not in p and "ref_gpu_bake_" not in p]        # SoftRas fixtures
 NMR_FILES = [p for p in ALL if "ref_gpu_nmr_" in p]        # NMR (dr_type='n3mr') fixtures
 
 
@@ -107,3 +107,13 @@ def test_nmr_oracle_matches_reference_kernels(path):
         ref_inv = z["face_inv_map"].reshape(cpu["face_inv_map"].shape)
         assert np.abs(ref_inv - cpu["face_inv_map"]).max() <= 4e-5 * np.abs(cpu["face_inv_map"]).max()
     assert np.abs(z["grad_faces"] - gf).max() <= 1e-3 * np.abs(gf).max()
+
+
+def test_bake_oracle_matches_reference_kernel_golden():
+    """oracle/bake.py against the reference's own load_textures_cuda_kernel (io/utils/load_textures.py:3-101) compiled by
+    oracle/build_ref.py and run on a B200 (oracle/make_ref_golden.py --bake-only).  The reference build contracts a*b+c."""
+    from oracle import bake as obake
+    g = np.load(os.path.join(ROOT, "tests", "golden", "ref_gpu_bake_random40_R5.npz"))
+    out = obake.bake_textures_for_softras(g["image"], g["faces_uv"], g["textures_in"], g["is_update"])
+    assert np.abs(out - g["textures"]).max() <= 1e-5
+    assert np.array_equal(out[g["is_update"] == 0], g["textures_in"][g["is_update"] == 0])
