@@ -574,7 +574,7 @@ def run_nmr(args, rank, world, local_rank):
         flush.fill_(1.0); step()
     torch.cuda.synchronize(dev); L.b200r_profile_enable(0)
     kern = {}
-    for kid, name in [(5, "k_nmr_setup"), (1, "k_coarse_bin"), (4, "k_tile_order"), (6, "k_nmr_forward"),
+    for kid, name in [(5, "k_nmr_zbuffer"), (6, "k_nmr_resolve"),
                       (10, "k_nmr_pack"), (7, "k_nmr_backward_pixel_map"), (8, "k_nmr_backward_maps")]:
         t, n = C.c_double(0), C.c_longlong(0)
         L.b200r_profile_read(kid, C.byref(t), C.byref(n))

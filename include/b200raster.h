@@ -239,8 +239,6 @@ B200R_API int b200r_surface_lighting_backward(const float* vertices, const int32
 B200R_API unsigned long long b200r_launch_count(void);
 
 /* Tuning knobs (process-wide; results are identical for every setting except softras_exact_tail):
- *   "softras_fwd_variant"    1 = lanes walk private face lists in lock-step (default), 2 = two-phase (compacted pair
- *                            list + TMA record staging; measured slower at C3 / C5, kept selectable for A/B)
  *   "softras_fwd_persistent" 0 = one CTA per tile, 1 = persistent grid + tile queue (default)
  *   "softras_exact_tail"     1 = the reference's double-precision sigmoid / alpha-product tails bit for bit;
  *                            0 (default) = the same expressions in fp32 for the default euclidean+softmax

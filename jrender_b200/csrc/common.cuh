@@ -112,14 +112,6 @@ static inline SoftRasWorkspace b200r_carve(void* state, void* base, int B, int n
     return w;
 }
 
-// Both regions in ONE block (state first): the NMR path keeps its records only for the duration of the forward.
-static inline SoftRasWorkspace b200r_carve_single(void* base, int B, int nf, int image_size) {
-    const size_t sb = b200r_carve(nullptr, nullptr, B, nf, image_size).state_bytes;
-    SoftRasWorkspace w = b200r_carve(base, (char*)base + sb, B, nf, image_size);
-    w.bytes += sb;
-    return w;
-}
-
 #ifdef __CUDACC__
 // NDC coordinate of pixel index i (x: column; y: is-1-row), evaluated in double and
 // rounded to float exactly like `(2. * xi + 1. - is) / is` (cuda/soft_rasterize.py:282-283).

@@ -9,27 +9,11 @@
 
 using namespace b200r;
 
-namespace {
-// SM count of the CURRENT device (cached per ordinal: one process may drive several GPUs)
-int nmr_sm_count() {
-    static std::atomic<int> cache[64];
-    int dev = 0;
-    cudaGetDevice(&dev);
-    const int slot = (dev >= 0 && dev < 64) ? dev : 63;
-    int n = cache[slot].load();
-    if (n == 0 || dev >= 64) {
-        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-        cache[slot].store(n);
-    }
-    return n;
-}
-}  // namespace
-
 extern "C" {
 
 size_t b200r_nmr_workspace_bytes(int batch_size, int num_faces, int image_size) {
     if (batch_size <= 0 || num_faces <= 0 || image_size <= 0) return 0;
-    return b200r_carve_single(nullptr, batch_size, num_faces, image_size).bytes;  // NmrRec (128 B) fits the 160 B slots
+    return (size_t)batch_size * image_size * image_size * sizeof(unsigned long long);   // the (depth, face id) z-buffer
 }
 
 int b200r_nmr_forward(const float* faces, const float* textures, int32_t* face_index_map, float* weight_map,
@@ -45,55 +29,33 @@ int b200r_nmr_forward(const float* faces, const float* textures, int32_t* face_i
         return b200r_fail(B200R_EINVAL, "b200r_nmr_forward: return_rgb needs textures, rgb_map, sampling maps and texture_size > 0");
     if (return_alpha && !alpha_map) return b200r_fail(B200R_EINVAL, "b200r_nmr_forward: return_alpha needs alpha_map");
     if (return_depth && !face_inv_map) return b200r_fail(B200R_EINVAL, "b200r_nmr_forward: return_depth needs face_inv_map");
-    const SoftRasWorkspace W = b200r_carve_single(workspace, B, nf, is);
-    if (workspace_bytes < W.bytes)
-        return b200r_fail(B200R_EWORKSPACE, "b200r_nmr_forward: workspace %zu < required %zu bytes", workspace_bytes, W.bytes);
+    const size_t need = b200r_nmr_workspace_bytes(B, nf, is);
+    if (workspace_bytes < need)
+        return b200r_fail(B200R_EWORKSPACE, "b200r_nmr_forward: workspace %zu < required %zu bytes", workspace_bytes, need);
     NmrParams P;
     P.B = B; P.nf = nf; P.ts = texture_size; P.is = is; P.near_ = near_; P.far_ = far_; P.eps = eps;
     for (int k = 0; k < 3; k++) P.bg[k] = background_rgb ? background_rgb[k] : 0.f;
     P.return_rgb = return_rgb ? 1 : 0; P.return_alpha = return_alpha ? 1 : 0; P.return_depth = return_depth ? 1 : 0;
-    b200r_geometry(is, &P.ntx, &P.coarse_px, &P.ncs);
     cudaStream_t st = (cudaStream_t)stream;
-    NmrRec* recs = reinterpret_cast<NmrRec*>(W.recs);
-    const int total = B * nf;
+    unsigned long long* zbuf = reinterpret_cast<unsigned long long*>(workspace);
+    cudaError_t e = cudaMemsetAsync(zbuf, 0xFF, need, st);   // every pixel: "no face yet"
+    if (e != cudaSuccess) return b200r_cuda_fail(e, "memset z-buffer");
+    const long nfaces = (long)B * nf;
     {
         B200rProfScope prof(B200R_K_NMR_SETUP, st);
-        k_nmr_setup<<<(total + 255) / 256, 256, 0, st>>>(faces, recs, W.rects, total, nf, is);
-    }
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return b200r_cuda_fail(e, "k_nmr_setup");
-    e = cudaMemsetAsync(W.counters, 0, 256 * sizeof(int), st);
-    if (e != cudaSuccess) return b200r_cuda_fail(e, "memset counters");
-    {
-        B200rProfScope prof(B200R_K_COARSE_BIN, st);
-        k_chunk_rects<<<dim3((nf + 255) / 256, B), 256, 0, st>>>(W.rects, W.chunk_rects, nf);
-        k_coarse_bin<<<dim3(P.ncs * P.ncs, B), 256, 0, st>>>(W.rects, W.chunk_rects, W.coarse_cnt, W.coarse_ids, W.tile_cost, W.counters + 64,
-                                                             nf, is, P.coarse_px, P.ncs, B200R_TILE, B200R_TILE, P.ntx, P.ntx);
+        k_nmr_zbuffer<<<(unsigned)((nfaces + 255) / 256), 256, 0, st>>>(faces, zbuf, B, nf, is, near_, far_);
     }
     e = cudaGetLastError();
-    if (e != cudaSuccess) return b200r_cuda_fail(e, "k_coarse_bin");
-    const int total_tiles = P.ntx * P.ntx * B;
+    if (e != cudaSuccess) return b200r_cuda_fail(e, "k_nmr_zbuffer");
+    const size_t npix = (size_t)B * is * is;
     {
-        B200rProfScope prof(B200R_K_TILE_ORDER, st);
-        k_tile_order<<<(total_tiles + 255) / 256, 256, 0, st>>>(W.tile_cost, W.counters + 64, W.counters + 128, W.tile_order,
-                                                                B, P.ntx, P.ntx, B200R_TILE, B200R_TILE, B200R_TILE, B200R_TILE, P.ntx, P.ntx, 1);
-    }
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return b200r_cuda_fail(e, "k_tile_order");
-    {
-        int occ = 1;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_nmr_forward, B200R_TILE_THREADS, 0);
-        if (occ < 1) occ = 1;
-        const long long slots = (long long)nmr_sm_count() * occ;
-        const unsigned grid = (unsigned)(total_tiles < slots ? total_tiles : slots);
         B200rProfScope prof(B200R_K_NMR_FWD, st);
-        k_nmr_forward<<<grid, B200R_TILE_THREADS, 0, st>>>(P, recs, W.rects, W.coarse_cnt, W.coarse_ids, faces, textures,
-                                                           face_index_map, weight_map, depth_map, rgb_map, alpha_map,
-                                                           sampling_index_map, sampling_weight_map, face_inv_map,
-                                                           W.counters, W.tile_order);
+        k_nmr_resolve<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(P, zbuf, faces, textures, face_index_map, weight_map, depth_map,
+                                                                     rgb_map, alpha_map, sampling_index_map, sampling_weight_map,
+                                                                     face_inv_map);
     }
     e = cudaGetLastError();
-    if (e != cudaSuccess) return b200r_cuda_fail(e, "k_nmr_forward");
+    if (e != cudaSuccess) return b200r_cuda_fail(e, "k_nmr_resolve");
     return 0;
 }
 

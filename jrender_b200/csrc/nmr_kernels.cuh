@@ -8,12 +8,10 @@
 //   K10 backward_textures_cuda_kernel        :659-694
 //   K11 backward_depth_map_cuda_kernel       :738-788
 //
-// B200 design: the forward is tile-centric like the SoftRas forward (same exact binning
-// infrastructure): a thread owns a pixel and keeps its z-buffer entry in registers while the
-// CTA streams the tile's faces through shared memory in ascending id -- no lock, no atomics,
-// and a deterministic tie rule (lowest face id wins equal depth; the reference's winner is
-// race-dependent).  K7 and K8 are fused: the pixel samples its winning face's texture and
-// writes every map once.  K9 keeps the reference's per-face edge walk but gives a WARP to each
+// B200 design: the forward is a face-parallel z-buffer pass (a warp per face over its bounding box, one 64-bit atomicMin
+// of (depth, face id) per covered pixel: lock-free and deterministic -- lowest face id wins equal depth; the reference's
+// winner is race-dependent) followed by a per-pixel resolve pass that fuses K7's map writes with K8: the pixel recomputes
+// its winning face's weights, samples the texture and writes every map once.  K9 keeps the reference's per-face edge walk but gives a WARP to each
 // face so that the long "out" scans (up to image_size pixels each) run 32 pixels at a time on
 // coalesced rows.  Maps keep the kernels' orientation [B, yi, xi] with yi up.
 #pragma once
@@ -23,54 +21,43 @@
 
 namespace b200r {
 
-struct __align__(16) NmrRec {   // 128 bytes
-    uint32_t rect_x;   // ix_min | ix_max << 16   (:102-103)
-    uint32_t rect_r;   // iy_min | iy_max << 16   (:104-105), yi up
-    uint32_t flags;    // bit 4+k: midrange(z_k)
-    uint32_t face_id;
-    float inv[9];      // pixel-space face_inv (:75-87), unclamped determinant
-    float v[9];        // NDC x, y and z per vertex
-    float rz[3];       // rcp_refined(z_k)
-    float pad[7];
-};
-static_assert(sizeof(NmrRec) == 128, "NmrRec must be 128 bytes");
-
 struct NmrParams {
     int B, nf, ts, is;
     float near_, far_, eps;
     float bg[3];
     int return_rgb, return_alpha, return_depth;
-    int ntx, coarse_px, ncs;
 };
 
-// K7 prologue per face (:59-105): back-face cull, pixel-space inverse, integer bounding box.
-__global__ void __launch_bounds__(256) k_nmr_setup(const float* __restrict__ faces, NmrRec* __restrict__ recs,
-                                                   uint2* __restrict__ rects, int total_faces, int nf, int is) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total_faces) return;
+// Per-face quantities of K7 (:59-105), computed identically wherever a face is touched (z-buffer pass, resolve pass):
+// back-face flag, pixel-space inverse with the UNCLAMPED determinant, integer bounding box, reciprocals of the depths.
+struct NmrFace {
+    float v[9];        // NDC x, y and z per vertex
+    float inv[9];      // pixel-space face_inv (:75-87)
+    float rz[3];       // rcp_refined(z_k)
+    uint32_t zsafe;    // bit k: midrange(z_k)
+    int ix_min, ix_max, iy_min, iy_max;   // :102-105, yi up; empty when culled
+};
+
+__device__ __forceinline__ void nmr_face_setup(const float* __restrict__ face, int is, NmrFace& r) {
     float f[9];
 #pragma unroll
-    for (int k = 0; k < 9; k++) f[k] = __ldg(faces + (size_t)i * 9 + k);
-    NmrRec r;
-    r.face_id = (uint32_t)(i % nf);
-    uint32_t flags = 0;
+    for (int k = 0; k < 9; k++) f[k] = __ldg(face + k);
 #pragma unroll
     for (int k = 0; k < 9; k++) r.v[k] = f[k];
+    r.zsafe = 0;
 #pragma unroll
     for (int k = 0; k < 3; k++) {
         r.rz[k] = rcp_refined(f[3 * k + 2]);
-        if (midrange(f[3 * k + 2])) flags |= 16u << k;
+        if (midrange(f[3 * k + 2])) r.zsafe |= 1u << k;
     }
-#pragma unroll
-    for (int k = 0; k < 7; k++) r.pad[k] = 0.f;
     float p[3][2];
 #pragma unroll
     for (int num = 0; num < 3; num++)
 #pragma unroll
         for (int dim = 0; dim < 2; dim++) p[num][dim] = 0.5f * (f[3 * num + dim] * is + is - 1);  // :70 (0.5*x exact)
-    float fi[9] = {p[1][1] - p[2][1], p[2][0] - p[1][0], p[1][0] * p[2][1] - p[2][0] * p[1][1],
-                   p[2][1] - p[0][1], p[0][0] - p[2][0], p[2][0] * p[0][1] - p[0][0] * p[2][1],
-                   p[0][1] - p[1][1], p[1][0] - p[0][0], p[0][0] * p[1][1] - p[1][0] * p[0][1]};
+    const float fi[9] = {p[1][1] - p[2][1], p[2][0] - p[1][0], p[1][0] * p[2][1] - p[2][0] * p[1][1],
+                         p[2][1] - p[0][1], p[0][0] - p[2][0], p[2][0] * p[0][1] - p[0][0] * p[2][1],
+                         p[0][1] - p[1][1], p[1][0] - p[0][0], p[0][0] * p[1][1] - p[1][0] * p[0][1]};
     const float den = (p[2][0] * (p[0][1] - p[1][1]) + p[0][0] * (p[1][1] - p[2][1]) + p[1][0] * (p[2][1] - p[0][1]));
 #pragma unroll
     for (int k = 0; k < 9; k++) r.inv[k] = fi[k] / den;
@@ -82,234 +69,193 @@ __global__ void __launch_bounds__(256) k_nmr_setup(const float* __restrict__ fac
         if (p[num][1] < y_min) y_min = p[num][1];
         if (p[num][1] > y_max) y_max = p[num][1];
     }
-    int ix_min = max(0, (int)x_min), ix_max = min(is - 1, (int)x_max);
-    int iy_min = max(0, (int)y_min), iy_max = min(is - 1, (int)y_max);
+    r.ix_min = max(0, (int)x_min); r.ix_max = min(is - 1, (int)x_max);
+    r.iy_min = max(0, (int)y_min); r.iy_max = min(is - 1, (int)y_max);
     const bool back = (f[7] - f[1]) * (f[3] - f[0]) < (f[4] - f[1]) * (f[6] - f[0]);  // :63
-    if (back || ix_min > ix_max || iy_min > iy_max) { ix_min = 1; ix_max = 0; iy_min = 1; iy_max = 0; }
-    r.rect_x = (uint32_t)ix_min | ((uint32_t)ix_max << 16);
-    r.rect_r = (uint32_t)iy_min | ((uint32_t)iy_max << 16);
-    r.flags = flags;
-    const uint4* src = reinterpret_cast<const uint4*>(&r);
-    uint4* dst = reinterpret_cast<uint4*>(recs + i);
-#pragma unroll
-    for (int k = 0; k < 8; k++) dst[k] = src[k];
-    rects[i] = make_uint2(r.rect_x, r.rect_r);
+    if (back || r.ix_min > r.ix_max || r.iy_min > r.iy_max) { r.ix_min = 1; r.ix_max = 0; r.iy_min = 1; r.iy_max = 0; }
 }
 
-#define B200R_NMR_CHUNK 128
+// K7's per-(face, pixel) body (:108-136): NDC inside test, clamped / normalised barycentric weights, depth.  Returns
+// false when the pixel is outside the face or the depth fails the near / far test; a NaN depth is rejected too (the
+// reference lets it past :136 but `zp < depth` at :146 is then false: it never wins a pixel).
+__device__ __forceinline__ bool nmr_face_pixel(const NmrFace& r, int xi, int yi, int is, float near_, float far_,
+                                               float& w0, float& w1, float& w2, float& zp) {
+    const float xp = b200r_pix_coord(xi, is), yp = b200r_pix_coord(yi, is);   // :110-111
+    const float* f = r.v;
+    if (((yp - f[1]) * (f[3] - f[0]) < (xp - f[0]) * (f[4] - f[1])) ||
+        ((yp - f[4]) * (f[6] - f[3]) < (xp - f[3]) * (f[7] - f[4])) ||
+        ((yp - f[7]) * (f[0] - f[6]) < (xp - f[6]) * (f[1] - f[7])))
+        return false;                                                          // :113-116
+    const float fxi = (float)xi, fyi = (float)yi;
+    const float* inv = r.inv;
+    w0 = inv[0] * fxi + inv[1] * fyi + inv[2];   // :121-123
+    w1 = inv[3] * fxi + inv[4] * fyi + inv[5];
+    w2 = inv[6] * fxi + inv[7] * fyi + inv[8];
+    w0 = fminf(fmaxf(w0, 0.f), 1.f);              // :128
+    w1 = fminf(fmaxf(w1, 0.f), 1.f);
+    w2 = fminf(fmaxf(w2, 0.f), 1.f);
+    const float w_sum = ((0.f + w0) + w1) + w2;  // :126-129
+    if (w_sum != 1.f) {
+        const float rr = rcp_refined(w_sum);
+        const bool safe = midrange(w_sum);
+        w0 = fast_div(w0, w_sum, rr, safe);       // :132
+        w1 = fast_div(w1, w_sum, rr, safe);
+        w2 = fast_div(w2, w_sum, rr, safe);
+    }
+    zp = 1.f / (fast_div(w0, f[2], r.rz[0], (r.zsafe & 1u) != 0) + fast_div(w1, f[5], r.rz[1], (r.zsafe & 2u) != 0) +
+                fast_div(w2, f[8], r.rz[2], (r.zsafe & 4u) != 0));   // :135
+    if (zp <= near_ || far_ <= zp) return false;                     // :136
+    return zp < far_;                                                 // NaN
+}
 
-struct NmrFwdSmem {
-    NmrRec rec[B200R_NMR_CHUNK];         // 16 KB
-    int ids[B200R_NMR_CHUNK + 256];
-    unsigned char wlist[8][B200R_NMR_CHUNK];
-    int s_warp[8];
-    int s_tile;
-};
+// float -> unsigned with the same order (negative depths are possible when `near` is negative)
+__device__ __forceinline__ uint32_t nmr_order_bits(float z) {
+    const uint32_t u = __float_as_uint(z);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
 
-// K7 + K8 + background / alpha (n3mr.py:135-148), persistent over the cost-ordered tile queue.
-__global__ void __launch_bounds__(B200R_TILE_THREADS, 3)
-k_nmr_forward(const NmrParams P, const NmrRec* __restrict__ recs, const uint2* __restrict__ rects,
-              const int* __restrict__ coarse_cnt, const int* __restrict__ coarse_ids,
-              const float* __restrict__ faces, const float* __restrict__ textures,
-              int* __restrict__ face_index_map, float* __restrict__ weight_map, float* __restrict__ depth_map,
-              float* __restrict__ rgb_map, float* __restrict__ alpha_map, int* __restrict__ sampling_index_map,
-              float* __restrict__ sampling_weight_map, float* __restrict__ face_inv_map,
-              int* tile_counter, const int* __restrict__ tile_order) {
-    __shared__ NmrFwdSmem S;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+// K7, pass 1 -- face-parallel z-buffer.  The reference gives a THREAD to every face and serialises pixels behind an
+// atomicCAS spin lock (:138-160, the winner of equal depths is whoever gets the lock first); the first version here was
+// tile-centric (every pixel of a 16x16 tile tested every face binned to the tile: ~100 bounding-box tests per pixel for
+// the 2-pixel triangles of the 39 200-face mesh, 1.1 ms + 0.3 ms of binning per 16 images).  Now every covered pixel of
+// every face does ONE 64-bit atomicMin of (depth order bits << 32 | face id) into the z-buffer: lock-free, and
+// deterministic -- lowest depth, then lowest face id, exactly the oracle's tie rule.  A thread sets its face up and walks a
+// small bounding box itself (the per-face set-up with its nine divisions is most of the work for small faces: 32 faces
+// per warp, not one); faces with a bounding box above kNmrSerialBox pixels are then taken one at a time by the whole warp,
+// lanes striding over the box (any size).
+constexpr int kNmrSerialBox = 32;
+
+__device__ __forceinline__ void nmr_zbuffer_pixel(const NmrFace& r, int xi, int yi, int is, float near_, float far_, int fn,
+                                                  unsigned long long* __restrict__ zb) {
+    float w0, w1, w2, zp;
+    if (!nmr_face_pixel(r, xi, yi, is, near_, far_, w0, w1, w2, zp)) return;
+    atomicMin(zb + (size_t)yi * is + xi, ((unsigned long long)nmr_order_bits(zp) << 32) | (unsigned)fn);
+}
+
+__global__ void __launch_bounds__(256)
+k_nmr_zbuffer(const float* __restrict__ faces, unsigned long long* __restrict__ zbuf, int B, int nf, int is, float near_, float far_) {
+    const int lane = threadIdx.x & 31;
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long total = (long)B * nf;
+    NmrFace r;
+    int npx = 0, bw = 1;
+    if (i < total) {
+        nmr_face_setup(faces + i * 9, is, r);
+        if (r.ix_min <= r.ix_max) {
+            bw = r.ix_max - r.ix_min + 1;
+            npx = bw * (r.iy_max - r.iy_min + 1);
+        }
+    }
+    const int b = (int)((i < total ? i : 0) / nf), fn = (int)((i < total ? i : 0) % nf);
+    if (npx > 0 && npx <= kNmrSerialBox) {
+        unsigned long long* zb = zbuf + (size_t)b * is * is;
+        for (int j = 0; j < npx; j++) nmr_zbuffer_pixel(r, r.ix_min + j % bw, r.iy_min + j / bw, is, near_, far_, fn, zb);
+    }
+    // large faces: the warp takes them one at a time (set-up recomputed by every lane: cheaper than 22 shuffles)
+    for (unsigned m = __ballot_sync(0xffffffffu, npx > kNmrSerialBox); m != 0u; m &= m - 1u) {
+        const int src = __ffs(m) - 1;
+        const long fi = i - lane + src;
+        NmrFace q;
+        nmr_face_setup(faces + fi * 9, is, q);
+        const int qb = (int)(fi / nf), qfn = (int)(fi % nf);
+        const int qw = q.ix_max - q.ix_min + 1, qn = qw * (q.iy_max - q.iy_min + 1);
+        unsigned long long* zb = zbuf + (size_t)qb * is * is;
+        for (int j = lane; j < qn; j += 32) nmr_zbuffer_pixel(q, q.ix_min + j % qw, q.iy_min + j / qw, is, near_, far_, qfn, zb);
+    }
+}
+
+// K7 pass 2 + K8 + background / alpha (n3mr.py:135-148) -- thread per pixel: reads the winning face id, recomputes its
+// weights and depth with the very same code the z-buffer pass ran (same bits), samples the texture and writes every map
+// once (replaces the fills / memsets of :176-184, :311-313).  ~100 bytes written per pixel: this pass runs at HBM speed.
+__global__ void __launch_bounds__(256)
+k_nmr_resolve(const NmrParams P, const unsigned long long* __restrict__ zbuf, const float* __restrict__ faces,
+              const float* __restrict__ textures, int* __restrict__ face_index_map, float* __restrict__ weight_map,
+              float* __restrict__ depth_map, float* __restrict__ rgb_map, float* __restrict__ alpha_map,
+              int* __restrict__ sampling_index_map, float* __restrict__ sampling_weight_map, float* __restrict__ face_inv_map) {
     const int is = P.is, nf = P.nf;
-    const int tiles_per_image = P.ntx * P.ntx;
-    const int total_tiles = tiles_per_image * P.B;
-    const int lx = (warp & 1) * 8 + (lane & 7), ly = (warp >> 1) * 4 + (lane >> 3);
-
-    while (true) {
-        __syncthreads();
-        if (tid == 0) S.s_tile = atomicAdd(tile_counter, 1);
-        __syncthreads();
-        const int q = S.s_tile;
-        if (q >= total_tiles) break;
-        const int t = __ldg(tile_order + q);
-        const int b = t / tiles_per_image;
-        const int tt = t - b * tiles_per_image;
-        const int tx = tt % P.ntx, ty = tt / P.ntx;
-        const int xi = tx * B200R_TILE + lx, yi = ty * B200R_TILE + ly;
-        const float xp = b200r_pix_coord(xi, is);  // :110-111
-        const float yp = b200r_pix_coord(yi, is);
-        const float fxi = (float)xi, fyi = (float)yi;
-        const int tx0 = tx * B200R_TILE, tx1 = tx0 + B200R_TILE - 1;
-        const int tr0 = ty * B200R_TILE, tr1 = tr0 + B200R_TILE - 1;
-        const int wx0 = tx0 + (warp & 1) * 8, wx1 = wx0 + 7;
-        const int wr0 = tr0 + (warp >> 1) * 4, wr1 = wr0 + 3;
-
-        float depth = P.far_;   // thrust::fill(depth_map, far) :181-182
-        int best = -1;          // thrust::fill(face_index_map, -1) :176-177
-        float bw0 = 0.f, bw1 = 0.f, bw2 = 0.f;
-
-        const int cbin = (tr0 / P.coarse_px) * P.ncs + (tx0 / P.coarse_px);
-        const int n_coarse = coarse_cnt[b * P.ncs * P.ncs + cbin];
-        const int* clist = coarse_ids + ((size_t)b * P.ncs * P.ncs + cbin) * nf;
-        const uint2* brects = rects + (size_t)b * nf;
-        const NmrRec* brecs = recs + (size_t)b * nf;
-
-        int n_pending = 0;
-        for (int base = 0; base < n_coarse; base += B200R_TILE_THREADS) {
-            {
-                const int i = base + tid;
-                int id = -1;
-                bool pass = false;
-                if (i < n_coarse) {
-                    id = __ldg(clist + i);
-                    pass = rect_overlaps(__ldg(brects + id), tx0, tx1, tr0, tr1);
-                }
-                int total;
-                const int off = n_pending + block_excl_scan_256(pass ? 1 : 0, S.s_warp, total);
-                if (pass) S.ids[off] = id;
-                n_pending += total;
+    const size_t i1 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i1 >= (size_t)P.B * is * is) return;
+    const int b = (int)(i1 / ((size_t)is * is));
+    const int rem = (int)(i1 - (size_t)b * is * is);
+    const int yi = rem / is, xi = rem - yi * is;
+    const unsigned long long key = zbuf[i1];
+    float depth = P.far_;   // thrust::fill(depth_map, far) :181-182
+    int best = -1;          // thrust::fill(face_index_map, -1) :176-177
+    float bw0 = 0.f, bw1 = 0.f, bw2 = 0.f;
+    NmrFace r;
+    if (key != ~0ull) {
+        best = (int)(unsigned)(key & 0xffffffffull);
+        nmr_face_setup(faces + ((size_t)b * nf + best) * 9, is, r);
+        nmr_face_pixel(r, xi, yi, is, P.near_, P.far_, bw0, bw1, bw2, depth);
+    }
+    face_index_map[i1] = best;
+    weight_map[i1 * 3 + 0] = bw0;
+    weight_map[i1 * 3 + 1] = bw1;
+    weight_map[i1 * 3 + 2] = bw2;
+    depth_map[i1] = depth;
+    if (P.return_alpha) alpha_map[i1] = best >= 0 ? 1.f : 0.f;   // n3mr.py:145-148
+    if (P.return_depth) {
+#pragma unroll
+        for (int k = 0; k < 9; k++) face_inv_map[i1 * 9 + k] = best >= 0 ? r.inv[k] : 0.f;   // :152-156
+    }
+    if (P.return_rgb) {
+        float px0 = P.bg[0], px1 = P.bg[1], px2 = P.bg[2];   // forward_background, n3mr.py:135-143
+        int sidx[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        float sw[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (best >= 0) {  // K8 :248-297
+            const int ts = P.ts;
+            const float* texture = textures + ((size_t)b * nf + best) * ts * ts * ts * 3;
+            const float wk[3] = {bw0, bw1, bw2};
+            float tif[3];
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                float v = wk[k] * (ts - 1) * (depth / r.v[3 * k + 2]);
+                v = fmaxf(v, 0.f);
+                v = fminf(v, ts - 1 - P.eps);
+                tif[k] = v;
             }
-            const bool last = base + B200R_TILE_THREADS >= n_coarse;
-            if (n_pending < B200R_NMR_CHUNK && !last) continue;
-            while (n_pending >= B200R_NMR_CHUNK || (last && n_pending > 0)) {
-                const int m = min(n_pending, B200R_NMR_CHUNK);
-                __syncthreads();
-                for (int j = tid; j < m * 8; j += B200R_TILE_THREADS) {
-                    const int f = j >> 3, qq = j & 7;
-                    reinterpret_cast<uint4*>(&S.rec[f])[qq] = __ldg(reinterpret_cast<const uint4*>(brecs + S.ids[f]) + qq);
+            float np0 = 0.f, np1 = 0.f, np2 = 0.f;
+#pragma unroll
+            for (int pn = 0; pn < 8; pn++) {
+                float w = 1.f;
+                int tii[3];
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    const int base_i = (int)tif[k];
+                    if (((pn >> k) & 1) == 0) { w *= 1 - (tif[k] - base_i); tii[k] = base_i; }
+                    else { w *= tif[k] - base_i; tii[k] = base_i + 1; }
                 }
-                __syncthreads();
-                const int rest = n_pending - m;
-                int keep0 = 0;
-                if (tid < rest) keep0 = S.ids[m + tid];
-                int wcnt = 0;
-                for (int j0 = 0; j0 < m; j0 += 32) {
-                    const int j = j0 + lane;
-                    bool pass = false;
-                    if (j < m) pass = rect_overlaps(make_uint2(S.rec[j].rect_x, S.rec[j].rect_r), wx0, wx1, wr0, wr1);
-                    const unsigned bal = __ballot_sync(0xffffffffu, pass);
-                    if (pass) S.wlist[warp][wcnt + __popc(bal & ((1u << lane) - 1u))] = (unsigned char)j;
-                    wcnt += __popc(bal);
+                const int isc = tii[0] * ts * ts + tii[1] * ts + tii[2];
+                // texture_size 1: ts - 1 - eps < 0 and the "+1" taps leave the face's block; the reference reads whatever
+                // follows (next faces' texels; past the tensor for the last faces).  Taps inside the tensor are read
+                // likewise, taps past it give 0.
+                const size_t tap = ((size_t)b * nf + best) * ts * ts * ts + (size_t)isc;
+                if (isc >= 0 && tap < (size_t)P.B * nf * ts * ts * ts) {
+                    np0 += w * __ldg(texture + isc * 3 + 0);
+                    np1 += w * __ldg(texture + isc * 3 + 1);
+                    np2 += w * __ldg(texture + isc * 3 + 2);
                 }
-                __syncwarp();
-                for (int it = 0; it < wcnt; it++) {
-                    const NmrRec* rec = &S.rec[S.wlist[warp][it]];
-                    {
-                        const uint32_t rx = rec->rect_x, rr = rec->rect_r;
-                        const uint32_t x0 = rx & 0xffffu, r0 = rr & 0xffffu;
-                        if ((uint32_t)(xi - (int)x0) > (rx >> 16) - x0) continue;
-                        if ((uint32_t)(yi - (int)r0) > (rr >> 16) - r0) continue;
-                    }
-                    const float* f = rec->v;
-                    // inside test in NDC (:113-116)
-                    if (((yp - f[1]) * (f[3] - f[0]) < (xp - f[0]) * (f[4] - f[1])) ||
-                        ((yp - f[4]) * (f[6] - f[3]) < (xp - f[3]) * (f[7] - f[4])) ||
-                        ((yp - f[7]) * (f[0] - f[6]) < (xp - f[6]) * (f[1] - f[7])))
-                        continue;
-                    const float* inv = rec->inv;
-                    float w0 = inv[0] * fxi + inv[1] * fyi + inv[2];   // :121-123
-                    float w1 = inv[3] * fxi + inv[4] * fyi + inv[5];
-                    float w2 = inv[6] * fxi + inv[7] * fyi + inv[8];
-                    w0 = fminf(fmaxf(w0, 0.f), 1.f);                   // :128
-                    w1 = fminf(fmaxf(w1, 0.f), 1.f);
-                    w2 = fminf(fmaxf(w2, 0.f), 1.f);
-                    const float w_sum = ((0.f + w0) + w1) + w2;       // :126-129
-                    if (w_sum != 1.f) {
-                        const float r = rcp_refined(w_sum);
-                        const bool safe = midrange(w_sum);
-                        w0 = fast_div(w0, w_sum, r, safe);            // :132
-                        w1 = fast_div(w1, w_sum, r, safe);
-                        w2 = fast_div(w2, w_sum, r, safe);
-                    }
-                    const uint32_t fl = rec->flags;
-                    const float zp = 1.f / (fast_div(w0, f[2], rec->rz[0], (fl & 16u) != 0) +
-                                            fast_div(w1, f[5], rec->rz[1], (fl & 32u) != 0) +
-                                            fast_div(w2, f[8], rec->rz[2], (fl & 64u) != 0));   // :135
-                    if (zp <= P.near_ || P.far_ <= zp) continue;       // :136
-                    if (zp < depth) {                                   // :146, ascending id => lowest id wins ties
-                        depth = zp;
-                        best = (int)rec->face_id;
-                        bw0 = w0; bw1 = w1; bw2 = w2;
-                    }
-                }
-                __syncthreads();
-                if (tid < rest) S.ids[tid] = keep0;
-                n_pending = rest;
+                sidx[pn] = isc;
+                sw[pn] = w;
             }
+            // rgb * mask + (1 - mask) * background with mask == 1
+            px0 = np0 * 1.f + 0.f * P.bg[0];
+            px1 = np1 * 1.f + 0.f * P.bg[1];
+            px2 = np2 * 1.f + 0.f * P.bg[2];
+        } else {
+            px0 = 0.f * 0.f + 1.f * P.bg[0];
+            px1 = 0.f * 0.f + 1.f * P.bg[1];
+            px2 = 0.f * 0.f + 1.f * P.bg[2];
         }
-
-        // ---- write the pixel's maps once (replaces the fills/memsets :176-184, :311-313)
-        if (xi < is && yi < is) {
-            const size_t i1 = ((size_t)b * is + yi) * is + xi;
-            face_index_map[i1] = best;
-            weight_map[i1 * 3 + 0] = bw0;
-            weight_map[i1 * 3 + 1] = bw1;
-            weight_map[i1 * 3 + 2] = bw2;
-            depth_map[i1] = depth;
-            if (P.return_alpha) alpha_map[i1] = best >= 0 ? 1.f : 0.f;   // n3mr.py:145-148
-            if (P.return_depth) {
-#pragma unroll
-                for (int k = 0; k < 9; k++)
-                    face_inv_map[i1 * 9 + k] = best >= 0 ? __ldg(&brecs[best].inv[k]) : 0.f;   // :152-156
-            }
-            if (P.return_rgb) {
-                float px0 = P.bg[0], px1 = P.bg[1], px2 = P.bg[2];   // forward_background, n3mr.py:135-143
-                int sidx[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-                float sw[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                if (best >= 0) {  // K8 :248-297
-                    const int ts = P.ts;
-                    const float* face = faces + ((size_t)b * nf + best) * 9;
-                    const float* texture = textures + ((size_t)b * nf + best) * ts * ts * ts * 3;
-                    const float wk[3] = {bw0, bw1, bw2};
-                    float tif[3];
-#pragma unroll
-                    for (int k = 0; k < 3; k++) {
-                        float v = wk[k] * (ts - 1) * (depth / __ldg(face + 3 * k + 2));
-                        v = fmaxf(v, 0.f);
-                        v = fminf(v, ts - 1 - P.eps);
-                        tif[k] = v;
-                    }
-                    float np0 = 0.f, np1 = 0.f, np2 = 0.f;
-#pragma unroll
-                    for (int pn = 0; pn < 8; pn++) {
-                        float w = 1.f;
-                        int tii[3];
-#pragma unroll
-                        for (int k = 0; k < 3; k++) {
-                            const int base_i = (int)tif[k];
-                            if (((pn >> k) & 1) == 0) { w *= 1 - (tif[k] - base_i); tii[k] = base_i; }
-                            else { w *= tif[k] - base_i; tii[k] = base_i + 1; }
-                        }
-                        const int isc = tii[0] * ts * ts + tii[1] * ts + tii[2];
-                        // texture_size 1: ts - 1 - eps < 0 and the "+1" taps leave the face's block; the
-                        // reference reads whatever follows (next faces' texels; past the tensor for the
-                        // last faces).  Taps inside the tensor are read likewise, taps past it give 0.
-                        const size_t tap = ((size_t)b * nf + best) * ts * ts * ts + (size_t)isc;
-                        if (isc >= 0 && tap < (size_t)P.B * nf * ts * ts * ts) {
-                            np0 += w * __ldg(texture + isc * 3 + 0);
-                            np1 += w * __ldg(texture + isc * 3 + 1);
-                            np2 += w * __ldg(texture + isc * 3 + 2);
-                        }
-                        sidx[pn] = isc;
-                        sw[pn] = w;
-                    }
-                    // rgb * mask + (1 - mask) * background with mask == 1
-                    px0 = np0 * 1.f + 0.f * P.bg[0];
-                    px1 = np1 * 1.f + 0.f * P.bg[1];
-                    px2 = np2 * 1.f + 0.f * P.bg[2];
-                } else {
-                    px0 = 0.f * 0.f + 1.f * P.bg[0];
-                    px1 = 0.f * 0.f + 1.f * P.bg[1];
-                    px2 = 0.f * 0.f + 1.f * P.bg[2];
-                }
-                rgb_map[i1 * 3 + 0] = px0;
-                rgb_map[i1 * 3 + 1] = px1;
-                rgb_map[i1 * 3 + 2] = px2;
-                int4* si = reinterpret_cast<int4*>(sampling_index_map + i1 * 8);
-                si[0] = make_int4(sidx[0], sidx[1], sidx[2], sidx[3]);
-                si[1] = make_int4(sidx[4], sidx[5], sidx[6], sidx[7]);
-                float4* sv = reinterpret_cast<float4*>(sampling_weight_map + i1 * 8);
-                sv[0] = make_float4(sw[0], sw[1], sw[2], sw[3]);
-                sv[1] = make_float4(sw[4], sw[5], sw[6], sw[7]);
-            }
-        }
+        rgb_map[i1 * 3 + 0] = px0;
+        rgb_map[i1 * 3 + 1] = px1;
+        rgb_map[i1 * 3 + 2] = px2;
+        int4* si = reinterpret_cast<int4*>(sampling_index_map + i1 * 8);
+        si[0] = make_int4(sidx[0], sidx[1], sidx[2], sidx[3]);
+        si[1] = make_int4(sidx[4], sidx[5], sidx[6], sidx[7]);
+        float4* sv = reinterpret_cast<float4*>(sampling_weight_map + i1 * 8);
+        sv[0] = make_float4(sw[0], sw[1], sw[2], sw[3]);
+        sv[1] = make_float4(sw[4], sw[5], sw[6], sw[7]);
     }
 }
 
@@ -393,6 +339,9 @@ __device__ __forceinline__ float rcp_approx(float x) {
 }
 
 __device__ __forceinline__ float k9_sel3(int i, float a, float b, float c) { return i == 0 ? a : (i == 1 ? b : c); }
+__device__ __forceinline__ int k9_sel6(int i, const int v[7]) {
+    return i == 0 ? v[0] : (i == 1 ? v[1] : (i == 2 ? v[2] : (i == 3 ? v[3] : (i == 4 ? v[4] : v[5]))));
+}
 
 // One line scan of K9 (:486-520 outwards / :556-601 inwards): lanes take consecutive pixels d1_from + lane, + 32, ...
 // of the packed row `prow` (k_nmr_pack) and add their  -diff_grad / dist  terms to acc0 / acc1.
@@ -404,13 +353,14 @@ __device__ __forceinline__ float k9_sel3(int i, float a, float b, float c) { ret
 // `continue` would let it), products are fused (sums of ~10^2..10^3 terms, compared at 2e-5 relative).
 // ref = (r, g, b, alpha) of the sample's in-pixel (outward scan) / out-pixel (inward scan).
 template <int MODE, bool OWNER, bool BOTH>
-__device__ __forceinline__ void k9_scan(const float* __restrict__ prow, const int* __restrict__ fim, long fim_stride,
+__device__ __forceinline__ void k9_scan(const float* __restrict__ prow, const int* __restrict__ fim, int fim_stride,
                                         int d1_from, int d1_to, int lane, int fn, float r0, float r1, float r2, float ra,
                                         float d1_cross, float k0, float k1, bool has0, bool has1, float eps,
                                         float& acc0, float& acc1) {
     constexpr int FL = K9Rec<MODE>::FL;
-    const float* __restrict__ p = prow + (long)(d1_from + lane) * FL;
-    const int* __restrict__ o = OWNER ? fim + (long)(d1_from + lane) * fim_stride : nullptr;
+    // offsets inside one image fit 32 bits (is <= 4096: is^2 * FL <= 2^27)
+    const float* __restrict__ p = prow + (d1_from + lane) * FL;
+    const int* __restrict__ o = OWNER ? fim + (d1_from + lane) * fim_stride : nullptr;
     float d1f = (float)(d1_from + lane);   // exact below 2^24
     for (int left = d1_to - d1_from - lane; left >= 0; left -= 32) {
         float diff;
@@ -426,7 +376,7 @@ __device__ __forceinline__ void k9_scan(const float* __restrict__ prow, const in
             diff = q.x - __fmaf_rn(ra, ga, __fmaf_rn(r2, q.w, __fmaf_rn(r1, q.z, r0 * q.y)));
         }
         bool mine = true;
-        if (OWNER) { mine = __ldg(o) == fn; o += 32 * fim_stride; }
+        if (OWNER) { mine = __ldg(o) == fn; o += 32 * fim_stride; }   // (pointer arithmetic in 64 bits, the product in 32)
         p += 32 * FL;
         const float d = (mine && !(diff <= 0.f)) ? diff : 0.f;   // :503 / :587 `if (diff_grad <= 0) continue`
         const float delta = d1f - d1_cross;   // (d1 - d1_cross), one rounding like the reference's
@@ -444,14 +394,43 @@ __device__ __forceinline__ void k9_scan(const float* __restrict__ prow, const in
     }
 }
 
-// K9 (backward_pixel_map_cuda_kernel, n3mr/cuda/rasterize.py:351-610): warp per (batch, face).  The six (edge, axis)
-// passes of a face run as a real loop (six inlined copies thrash the instruction cache).  Per pass the three slopes
-// of :423 / :529-533 are divided once (the reference re-divides per d0 with the same operands: same bits), the
-// per-sample quotients that only scale `dist` use the approximate reciprocal, and the two scans are the tight loops
-// of k9_scan.  d1_cross / d0_cross2 -- which pick pixels through floor / ceil -- keep the reference's exact,
-// unfused arithmetic.
+// One (edge, axis) pass of the reference's per-face loop (:386-410): the edge's vertices in (major, minor) pixel
+// coordinates, the scan direction and the range of integer major coordinates d0 the edge crosses.
+struct K9Pass {
+    float p00, p01, p10, p11, p20, p21;
+    int direction, d0_from, d0_to;
+};
+
+__device__ __forceinline__ K9Pass k9_pass(int pass, const float px[3], const float py[3], int is) {
+    const int edge_num = pass >> 1, axis = pass & 1;
+    const int pi0 = edge_num, pi1 = (edge_num == 2) ? 0 : edge_num + 1, pi2 = (edge_num == 0) ? 2 : edge_num - 1;
+    // p[num][dim] = pp[num][(dim + axis) % 2]   (:396-401)
+    const float ax0 = k9_sel3(pi0, px[0], px[1], px[2]), ay0 = k9_sel3(pi0, py[0], py[1], py[2]);
+    const float ax1 = k9_sel3(pi1, px[0], px[1], px[2]), ay1 = k9_sel3(pi1, py[0], py[1], py[2]);
+    const float ax2 = k9_sel3(pi2, px[0], px[1], px[2]), ay2 = k9_sel3(pi2, py[0], py[1], py[2]);
+    K9Pass r;
+    r.p00 = axis ? ay0 : ax0; r.p01 = axis ? ax0 : ay0;
+    r.p10 = axis ? ay1 : ax1; r.p11 = axis ? ax1 : ay1;
+    r.p20 = axis ? ay2 : ax2; r.p21 = axis ? ax2 : ay2;
+    if (axis == 0) r.direction = (r.p00 < r.p10) ? -1 : 1;   // :404-414
+    else r.direction = (r.p00 < r.p10) ? 1 : -1;
+    r.d0_from = (int)fmax((double)ceilf(fminf(r.p00, r.p10)), 0.);   // :418-419
+    r.d0_to = (int)fmin((double)fmaxf(r.p00, r.p10), is - 1.);
+    return r;
+}
+
+// K9 (backward_pixel_map_cuda_kernel, n3mr/cuda/rasterize.py:351-610): warp per (batch, face).
+//
+// A face has six (edge, axis) passes and, per pass, one SAMPLE for every integer major coordinate the edge crosses
+// (:420).  A sample's set-up -- crossing point, in / out pixel, their colours and owner, the in-scan limit, the two
+// distance scales (:421-460, :523-540; ~190 instructions and five dependent loads) -- is independent of every other
+// sample's, and for the small faces of a dense mesh it outweighed the scans themselves when the whole warp ran it once
+// per sample.  So the lanes take one sample each: the set-up of up to 32 samples runs once, in parallel, and the warp then
+// visits the samples one by one (parameters broadcast by shuffle) only for the two line scans of k9_scan, where all 32
+// lanes have pixels to work on.  d1_cross / d0_cross2 -- which pick pixels through floor / ceil -- keep the reference's
+// exact, unfused arithmetic; the per-sample quotients that only scale `dist` use the approximate reciprocal.
 #ifndef B200R_K9_MINB
-#define B200R_K9_MINB 6   // resident 256-thread CTAs per SM (40 registers; with the 32-byte records: 7.10 ms at C4 against 7.33 at 5 and 7.68 at 4 -- the scans are latency-bound)
+#define B200R_K9_MINB 5   // resident 256-thread CTAs per SM
 #endif
 template <int MODE>
 __global__ void __launch_bounds__(256, B200R_K9_MINB)
@@ -460,6 +439,7 @@ k_nmr_backward_pixel_map(const float* __restrict__ faces, const int* __restrict_
                          const float* __restrict__ ph, const float* __restrict__ pv,
                          float* __restrict__ grad_faces, int batch_size, int num_faces, int is, float eps) {
     constexpr int FL = K9Rec<MODE>::FL;
+    constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const long i = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (i >= (long)batch_size * num_faces) return;
@@ -475,81 +455,158 @@ k_nmr_backward_pixel_map(const float* __restrict__ faces, const int* __restrict_
 #pragma unroll
     for (int k = 0; k < 3; k++) { px[k] = 0.5f * (fx[k] * is + is - 1); py[k] = 0.5f * (fy[k] * is + is - 1); }
 
-    float gacc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // [vertex*2 + (0:x, 1:y)]
     const float ndc_scale = 2.f / (float)is;
-    const long img = (long)bn * is * is;
+    const size_t img = (size_t)bn * is * is;
+    // per-image bases: everything below indexes them with 32-bit offsets (is <= 4096: is^2 * FL <= 2^27)
+    const int* __restrict__ fim_img = face_index_map + img;
+    const float* __restrict__ rgb_img = (MODE & 1) ? rgb_map + img * 3 : nullptr;
+    const float* __restrict__ alpha_img = (MODE & 2) ? alpha_map + img : nullptr;
+    const float* __restrict__ ph_img = ph + img * FL;
+    const float* __restrict__ pv_img = pv + img * FL;
 
-#pragma unroll 1
-    for (int pass = 0; pass < 6; pass++) {
-        const int edge_num = pass >> 1, axis = pass & 1;
-        const int pi0 = edge_num, pi1 = (edge_num == 2) ? 0 : edge_num + 1, pi2 = (edge_num == 0) ? 2 : edge_num - 1;
-        // p[num][dim] = pp[num][(dim + axis) % 2]   (:396-401)
-        const float ax0 = k9_sel3(pi0, px[0], px[1], px[2]), ay0 = k9_sel3(pi0, py[0], py[1], py[2]);
-        const float ax1 = k9_sel3(pi1, px[0], px[1], px[2]), ay1 = k9_sel3(pi1, py[0], py[1], py[2]);
-        const float ax2 = k9_sel3(pi2, px[0], px[1], px[2]), ay2 = k9_sel3(pi2, py[0], py[1], py[2]);
-        const float p00 = axis ? ay0 : ax0, p01 = axis ? ax0 : ay0;
-        const float p10 = axis ? ay1 : ax1, p11 = axis ? ax1 : ay1;
-        const float p20 = axis ? ay2 : ax2, p21 = axis ? ax2 : ay2;
-        int direction;
-        if (axis == 0) direction = (p00 < p10) ? -1 : 1;
-        else direction = (p00 < p10) ? 1 : -1;
-        const int d0_from = (int)fmax((double)ceilf(fminf(p00, p10)), 0.);
-        const int d0_to = (int)fmin((double)fmaxf(p00, p10), is - 1.);
-        if (d0_from > d0_to) continue;
-        const float slope01 = (p11 - p01) / (p10 - p00);   // :423
-        const float slope02 = (p21 - p01) / (p20 - p00);   // :530
-        const float slope21 = (p11 - p21) / (p10 - p20);   // :533
-        const float span = p10 - p00;
-        // packed records: axis 1 scans rows of ph, axis 0 scans rows of pv; in both the record of (d0, d1) sits at
-        // (img + d0 * is + d1) * FL
-        const float* __restrict__ pk = ((axis == 0) ? pv : ph) + img * FL;
-        const long fim_stride = (axis == 0) ? is : 1;
-        float acc0 = 0.f, acc1 = 0.f;  // contributions to vertex pi0 / pi1, coordinate (1 - axis)
-        for (int d0 = d0_from; d0 <= d0_to; d0++) {
-            const float d0f = (float)d0;
-            const float d1_cross = slope01 * (d0f - p00) + p01;
-            const int d1_in = (0 < direction) ? (int)floorf(d1_cross) : (int)ceilf(d1_cross);
-            const int d1_out = d1_in + direction;
-            if (d1_in < 0 || is <= d1_in) continue;
-            if (d1_out < 0 || is <= d1_out) continue;
-            const float* __restrict__ prow = pk + (long)d0 * is * FL;
-            const bool has0 = p10 != d0f, has1 = p00 != d0f;
-            // pixel -> NDC: the reference's (float)((double)(q * delta) * 2. / is) is formed as delta * (q * (2 / is)); q by
-            // approximate reciprocal -- a few ulp on a quantity that is then offset by eps and inverted approximately
-            const float k0 = span * rcp_approx(p10 - d0f) * ndc_scale, k1 = span * rcp_approx(d0f - p00) * ndc_scale;
-            const long fim_base = (axis == 0) ? img + d0 : img + (long)d0 * is;
-            const long idx_in = fim_base + (long)d1_in * fim_stride, idx_out = fim_base + (long)d1_out * fim_stride;
-            const bool visible = __ldg(face_index_map + idx_in) == fn;
-            if (visible) {   // outwards from the edge to the image border (:461-521); reference colour = the in-pixel's
-                float r0 = 0.f, r1 = 0.f, r2 = 0.f, ra = 0.f;
-                if (MODE & 1) { r0 = __ldg(rgb_map + idx_in * 3); r1 = __ldg(rgb_map + idx_in * 3 + 1); r2 = __ldg(rgb_map + idx_in * 3 + 2); }
-                if (MODE & 2) ra = __ldg(alpha_map + idx_in);
-                const int lim = (0 < direction) ? is - 1 : 0;
-                const int d1_from = max(min(d1_out, lim), 0), d1_to = min(max(d1_out, lim), is - 1);
-                if (has0 && has1) k9_scan<MODE, false, true>(prow, nullptr, 0, d1_from, d1_to, lane, fn, r0, r1, r2, ra, d1_cross, k0, k1, true, true, eps, acc0, acc1);
-                else k9_scan<MODE, false, false>(prow, nullptr, 0, d1_from, d1_to, lane, fn, r0, r1, r2, ra, d1_cross, k0, k1, has0, has1, eps, acc0, acc1);
+    // samples of the six passes, enumerated pass-major: start[p] = first sample number of pass p
+    int start[7];
+    start[0] = 0;
+#pragma unroll
+    for (int p = 0; p < 6; p++) {
+        const K9Pass q = k9_pass(p, px, py, is);
+        start[p + 1] = start[p] + max(q.d0_to - q.d0_from + 1, 0);
+    }
+    const int total = start[6];
+
+    float gacc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // [vertex*2 + (0:x, 1:y)]
+    for (int s0 = 0; s0 < total; s0 += 32) {
+        // ---- this lane's sample: everything of :421-460 and :523-540, no scan yet
+        const int sidx = s0 + lane;
+        int pass = 0;
+#pragma unroll
+        for (int p = 1; p < 6; p++) pass += (sidx >= start[p]) ? 1 : 0;
+        bool live = sidx < total;
+        const K9Pass q = k9_pass(pass, px, py, is);
+        const int axis = pass & 1;
+        const int d0 = q.d0_from + (sidx - k9_sel6(pass, start));
+        const float d0f = (float)d0;
+        const float d1_cross = (q.p11 - q.p01) / (q.p10 - q.p00) * (d0f - q.p00) + q.p01;   // :423
+        const int d1_in = (0 < q.direction) ? (int)floorf(d1_cross) : (int)ceilf(d1_cross);
+        const int d1_out = d1_in + q.direction;
+        live = live && !(d1_in < 0 || is <= d1_in) && !(d1_out < 0 || is <= d1_out);         // :431-434
+        const bool has0 = q.p10 != d0f, has1 = q.p00 != d0f;
+        const float span = q.p10 - q.p00;
+        // pixel -> NDC: the reference's (float)((double)(q * delta) * 2. / is) is formed as delta * (q * (2 / is)); q by
+        // approximate reciprocal -- a few ulp on a quantity that is then offset by eps and inverted approximately
+        const float k0 = span * rcp_approx(q.p10 - d0f) * ndc_scale, k1 = span * rcp_approx(d0f - q.p00) * ndc_scale;
+        const int fim_stride = (axis == 0) ? is : 1;
+        const int fim_base = (axis == 0) ? d0 : d0 * is;
+        const int idx_in = fim_base + d1_in * fim_stride, idx_out = fim_base + d1_out * fim_stride;
+        int owner_in = -2;
+        float i0 = 0.f, i1 = 0.f, i2 = 0.f, ia = 0.f, o0 = 0.f, o1 = 0.f, o2 = 0.f, oa = 0.f;
+        if (live) {
+            owner_in = __ldg(fim_img + idx_in);
+            if (MODE & 1) {
+                i0 = __ldg(rgb_img + idx_in * 3); i1 = __ldg(rgb_img + idx_in * 3 + 1); i2 = __ldg(rgb_img + idx_in * 3 + 2);
+                o0 = __ldg(rgb_img + idx_out * 3); o1 = __ldg(rgb_img + idx_out * 3 + 1); o2 = __ldg(rgb_img + idx_out * 3 + 2);
             }
-            {   // inwards up to the opposite edge, pixels owned by the face (:523-602); reference colour = the out-pixel's
-                float d0_cross2;
-                if ((d0f - p00) * (d0f - p20) < 0.f) d0_cross2 = slope02 * (d0f - p00) + p01;
-                else d0_cross2 = slope21 * (d0f - p20) + p21;
-                const int lim = (0 < direction) ? (int)ceilf(d0_cross2) : (int)floorf(d0_cross2);
-                const int d1_from = max(min(d1_in, lim), 0), d1_to = min(max(d1_in, lim), is - 1);
-                if (d1_from <= d1_to) {
-                    float r0 = 0.f, r1 = 0.f, r2 = 0.f, ra = 0.f;
-                    if (MODE & 1) { r0 = __ldg(rgb_map + idx_out * 3); r1 = __ldg(rgb_map + idx_out * 3 + 1); r2 = __ldg(rgb_map + idx_out * 3 + 2); }
-                    if (MODE & 2) ra = __ldg(alpha_map + idx_out);
-                    k9_scan<MODE, true, false>(prow, face_index_map + fim_base, fim_stride, d1_from, d1_to, lane, fn, r0, r1, r2, ra,
-                                               d1_cross, k0, k1, has0, has1, eps, acc0, acc1);
+            if (MODE & 2) { ia = __ldg(alpha_img + idx_in); oa = __ldg(alpha_img + idx_out); }
+        }
+        // outward scan range (:461-473), only if the face owns the in-pixel
+        const int olim = (0 < q.direction) ? is - 1 : 0;
+        int out_from = max(min(d1_out, olim), 0), out_to = min(max(d1_out, olim), is - 1);
+        if (!(live && owner_in == fn)) { out_from = 1; out_to = 0; }
+        // inward scan range (:525-540)
+        float d0_cross2;
+        if ((d0f - q.p00) * (d0f - q.p20) < 0.f) d0_cross2 = (q.p21 - q.p01) / (q.p20 - q.p00) * (d0f - q.p00) + q.p01;
+        else d0_cross2 = (q.p11 - q.p21) / (q.p10 - q.p20) * (d0f - q.p20) + q.p21;
+        const int ilim = (0 < q.direction) ? (int)ceilf(d0_cross2) : (int)floorf(d0_cross2);
+        int in_from = max(min(d1_in, ilim), 0), in_to = min(max(d1_in, ilim), is - 1);
+        if (!live) { in_from = 1; in_to = 0; }
+        // ---- inward scans of small faces: a few pixels each, so every lane walks ITS OWN sample's pixels (:556-601) instead
+        // of the warp visiting the samples one after the other for a single partly filled trip each
+        constexpr int kSerialIn = 64;
+        if (in_from <= in_to && in_to - in_from < kSerialIn) {
+            const float* __restrict__ prow_l = ((axis == 0) ? pv_img : ph_img) + d0 * is * FL;
+            float a0 = 0.f, a1 = 0.f;
+            for (int d1 = in_from; d1 <= in_to; d1++) {
+                if (__ldg(fim_img + fim_base + d1 * fim_stride) != fn) continue;   // :573
+                float diff;
+                const float* pr = prow_l + d1 * FL;
+                if (MODE == 1) {
+                    const float4 r4 = __ldg(reinterpret_cast<const float4*>(pr));
+                    diff = r4.x - __fmaf_rn(o2, r4.w, __fmaf_rn(o1, r4.z, o0 * r4.y));
+                } else if (MODE == 2) {
+                    const float2 r2 = __ldg(reinterpret_cast<const float2*>(pr));
+                    diff = r2.x - oa * r2.y;
+                } else {
+                    const float4 r4 = __ldg(reinterpret_cast<const float4*>(pr));
+                    diff = r4.x - __fmaf_rn(oa, __ldg(pr + 4), __fmaf_rn(o2, r4.w, __fmaf_rn(o1, r4.z, o0 * r4.y)));
+                }
+                if (diff <= 0.f) continue;                                          // :587
+                const float delta = (float)d1 - d1_cross;
+                if (has0) {
+                    float dist = delta * k0;
+                    dist = (0.f < dist) ? dist + eps : dist - eps;
+                    a0 = __fmaf_rn(-diff, rcp_approx(dist), a0);
+                }
+                if (has1) {
+                    float dist = delta * k1;
+                    dist = (0.f < dist) ? dist + eps : dist - eps;
+                    a1 = __fmaf_rn(-diff, rcp_approx(dist), a1);
                 }
             }
-        }
-        const int g0 = pi0 * 2 + (1 - axis), g1 = pi1 * 2 + (1 - axis);
+            const int edge_l = pass >> 1;
+            const int gl0 = edge_l * 2 + (1 - axis), gl1 = ((edge_l == 2) ? 0 : edge_l + 1) * 2 + (1 - axis);
 #pragma unroll
-        for (int k = 0; k < 6; k++) {
-            if (k == g0) gacc[k] += acc0;
-            if (k == g1) gacc[k] += acc1;
+            for (int k = 0; k < 6; k++) {
+                if (k == gl0) gacc[k] += a0;
+                if (k == gl1) gacc[k] += a1;
+            }
+            in_from = 1; in_to = 0;   // done
         }
+        const unsigned todo = __ballot_sync(FULL, out_from <= out_to || in_from <= in_to);
+
+        // ---- the warp visits the samples that still have pixels to scan (outward scans; inward scans of large faces).
+        // Samples are numbered pass-major, so the pass of the visited samples never decreases: the two running sums are
+        // flushed into the face's six gradient slots only when the pass changes.
+        int cur_pass = -1;
+        float acc0 = 0.f, acc1 = 0.f;   // contributions to vertex pi0 / pi1 of the current pass's edge, coordinate (1 - axis)
+        auto flush = [&]() {
+            if (cur_pass < 0) return;
+            const int e_ = cur_pass >> 1, ax_ = cur_pass & 1;
+            const int g0 = e_ * 2 + (1 - ax_), g1 = ((e_ == 2) ? 0 : e_ + 1) * 2 + (1 - ax_);
+#pragma unroll
+            for (int k = 0; k < 6; k++) {
+                if (k == g0) gacc[k] += acc0;
+                if (k == g1) gacc[k] += acc1;
+            }
+            acc0 = 0.f; acc1 = 0.f;
+        };
+        for (unsigned m = todo; m != 0u; m &= m - 1u) {
+            const int src = __ffs(m) - 1;
+            const int s_pass = __shfl_sync(FULL, pass, src);
+            if (s_pass != cur_pass) { flush(); cur_pass = s_pass; }
+            const int s_d0 = __shfl_sync(FULL, d0, src);
+            const float s_cross = __shfl_sync(FULL, d1_cross, src);
+            const float s_k0 = __shfl_sync(FULL, k0, src), s_k1 = __shfl_sync(FULL, k1, src);
+            const int s_flags = __shfl_sync(FULL, (has0 ? 1 : 0) | (has1 ? 2 : 0), src);
+            const int s_of = __shfl_sync(FULL, out_from, src), s_ot = __shfl_sync(FULL, out_to, src);
+            const int s_if = __shfl_sync(FULL, in_from, src), s_it = __shfl_sync(FULL, in_to, src);
+            const int s_axis = s_pass & 1;
+            const float* __restrict__ prow = ((s_axis == 0) ? pv_img : ph_img) + s_d0 * is * FL;
+            const bool both = s_flags == 3;
+            if (s_of <= s_ot) {   // outwards from the edge to the image border; reference colour = the in-pixel's
+                const float r0 = __shfl_sync(FULL, i0, src), r1 = __shfl_sync(FULL, i1, src), r2 = __shfl_sync(FULL, i2, src);
+                const float ra = (MODE & 2) ? __shfl_sync(FULL, ia, src) : 0.f;
+                if (both) k9_scan<MODE, false, true>(prow, nullptr, 0, s_of, s_ot, lane, fn, r0, r1, r2, ra, s_cross, s_k0, s_k1, true, true, eps, acc0, acc1);
+                else k9_scan<MODE, false, false>(prow, nullptr, 0, s_of, s_ot, lane, fn, r0, r1, r2, ra, s_cross, s_k0, s_k1, (s_flags & 1) != 0, (s_flags & 2) != 0, eps, acc0, acc1);
+            }
+            if (s_if <= s_it) {   // inwards up to the opposite edge, pixels owned by the face; reference colour = the out-pixel's
+                const float r0 = __shfl_sync(FULL, o0, src), r1 = __shfl_sync(FULL, o1, src), r2 = __shfl_sync(FULL, o2, src);
+                const float ra = (MODE & 2) ? __shfl_sync(FULL, oa, src) : 0.f;
+                const int s_stride = (s_axis == 0) ? is : 1;
+                const int* __restrict__ frow = fim_img + ((s_axis == 0) ? s_d0 : s_d0 * is);
+                k9_scan<MODE, true, false>(prow, frow, s_stride, s_if, s_it, lane, fn, r0, r1, r2, ra, s_cross, s_k0, s_k1, (s_flags & 1) != 0, (s_flags & 2) != 0, eps, acc0, acc1);
+            }
+        }
+        flush();
     }
 #pragma unroll
     for (int k = 0; k < 6; k++) gacc[k] = warp_sum_f(gacc[k]);

@@ -13,7 +13,6 @@ using namespace b200r;
 
 namespace {
 
-std::atomic<int> g_fwd_variant{1};     // 0: warp-uniform face loop, 1: per-lane face lists
 std::atomic<int> g_fwd_persistent{1};  // 0: one CTA per tile, 1: persistent grid + atomic tile queue
 std::atomic<int> g_exact_tail{0};      // 1: reference's double-precision sigmoid / alpha tails bit for bit; 0: fp32 tails (<= 1 ulp)
 }  // namespace
@@ -61,7 +60,6 @@ const char* b200r_version(void) { return "b200raster 0.1 (sm_100a)"; }
 
 int b200r_set_option(const char* name, int value) {
     if (!name) return b200r_fail(B200R_EINVAL, "b200r_set_option: NULL name");
-    if (!strcmp(name, "softras_fwd_variant")) { g_fwd_variant.store(value < 0 ? 0 : (value > 2 ? 2 : value)); return 0; }
     if (!strcmp(name, "softras_fwd_persistent")) { g_fwd_persistent.store(value ? 1 : 0); return 0; }
     if (!strcmp(name, "softras_exact_tail")) { g_exact_tail.store(value ? 1 : 0); return 0; }
     return b200r_fail(B200R_EINVAL, "b200r_set_option: unknown option '%s'", name);
@@ -125,8 +123,8 @@ static int softras_forward_impl(const float* face_vertices, const float* texture
     if (e != cudaSuccess) return b200r_cuda_fail(e, "k_tile_order");
 
     {
-        const int variant = g_fwd_variant.load(), persistent = g_fwd_persistent.load(), exact = g_exact_tail.load();
-        e = b200r_launch_forward(P, W, textures, soft_colors, aggrs_info, faces_id_buffer, pooled, variant, persistent, exact, st);
+        const int persistent = g_fwd_persistent.load(), exact = g_exact_tail.load();
+        e = b200r_launch_forward(P, W, textures, soft_colors, aggrs_info, faces_id_buffer, pooled, persistent, exact, st);
     }
     if (e != cudaSuccess) return b200r_cuda_fail(e, "k_softras_forward");
     return 0;

@@ -46,13 +46,11 @@ def main():
         SoftRasterizeFunction(image_size=H)(fv, tex).backward(grad)
 
     res = {"workload": desc}
-    for variant, persistent in ((1, 1), (1, 0), (2, 1)):
-        _lib.set_option("softras_fwd_variant", variant)
+    for persistent in (1, 0):
         _lib.set_option("softras_fwd_persistent", persistent)
         for _ in range(3):
             step()
-        res["variant%d_persistent%d" % (variant, persistent)] = kernel_times(L, 10, step)
-    _lib.set_option("softras_fwd_variant", 1)
+        res["persistent%d" % persistent] = kernel_times(L, 10, step)
     _lib.set_option("softras_fwd_persistent", 1)
     print(json.dumps(res), flush=True)
 
