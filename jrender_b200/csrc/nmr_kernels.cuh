@@ -362,22 +362,36 @@ __device__ __forceinline__ void k9_scan(const float* __restrict__ prow, const in
     const float* __restrict__ p = prow + (d1_from + lane) * FL;
     const int* __restrict__ o = OWNER ? fim + (d1_from + lane) * fim_stride : nullptr;
     float d1f = (float)(d1_from + lane);   // exact below 2^24
-    for (int left = d1_to - d1_from - lane; left >= 0; left -= 32) {
-        float diff;
-        if (MODE == 1) {
-            const float4 q = __ldg(reinterpret_cast<const float4*>(p));
-            diff = q.x - __fmaf_rn(r2, q.w, __fmaf_rn(r1, q.z, r0 * q.y));
-        } else if (MODE == 2) {
-            const float2 q = __ldg(reinterpret_cast<const float2*>(p));
-            diff = q.x - ra * q.y;
-        } else {
-            const float4 q = __ldg(reinterpret_cast<const float4*>(p));
-            const float ga = __ldg(p + 4);
-            diff = q.x - __fmaf_rn(ra, ga, __fmaf_rn(r2, q.w, __fmaf_rn(r1, q.z, r0 * q.y)));
-        }
-        bool mine = true;
-        if (OWNER) { mine = __ldg(o) == fn; o += 32 * fim_stride; }   // (pointer arithmetic in 64 bits, the product in 32)
+    int left = d1_to - d1_from - lane;
+    // software pipeline: the record (and owner) of trip t + 1 is requested before trip t is evaluated -- one trip's
+    // arithmetic is far shorter than an L1 / L2 round trip, and the scan is a chain of dependent trips otherwise
+    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+    float ga = 0.f;
+    int own = fn;
+    if (left >= 0) {
+        if (MODE == 2) { const float2 t = __ldg(reinterpret_cast<const float2*>(p)); q.x = t.x; q.y = t.y; }
+        else q = __ldg(reinterpret_cast<const float4*>(p));
+        if (MODE == 3) ga = __ldg(p + 4);
+        if (OWNER) own = __ldg(o);
+    }
+    while (left >= 0) {
+        const float4 c = q;
+        const float cga = ga;
+        const int cown = own;
+        left -= 32;
         p += 32 * FL;
+        if (OWNER) o += 32 * fim_stride;   // (pointer arithmetic in 64 bits, the product in 32)
+        if (left >= 0) {
+            if (MODE == 2) { const float2 t = __ldg(reinterpret_cast<const float2*>(p)); q.x = t.x; q.y = t.y; }
+            else q = __ldg(reinterpret_cast<const float4*>(p));
+            if (MODE == 3) ga = __ldg(p + 4);
+            if (OWNER) own = __ldg(o);
+        }
+        float diff;
+        if (MODE == 1) diff = c.x - __fmaf_rn(r2, c.w, __fmaf_rn(r1, c.z, r0 * c.y));
+        else if (MODE == 2) diff = c.x - ra * c.y;
+        else diff = c.x - __fmaf_rn(ra, cga, __fmaf_rn(r2, c.w, __fmaf_rn(r1, c.z, r0 * c.y)));
+        const bool mine = !OWNER || cown == fn;
         const float d = (mine && !(diff <= 0.f)) ? diff : 0.f;   // :503 / :587 `if (diff_grad <= 0) continue`
         const float delta = d1f - d1_cross;   // (d1 - d1_cross), one rounding like the reference's
         d1f += 32.f;
@@ -430,7 +444,7 @@ __device__ __forceinline__ K9Pass k9_pass(int pass, const float px[3], const flo
 // lanes have pixels to work on.  d1_cross / d0_cross2 -- which pick pixels through floor / ceil -- keep the reference's
 // exact, unfused arithmetic; the per-sample quotients that only scale `dist` use the approximate reciprocal.
 #ifndef B200R_K9_MINB
-#define B200R_K9_MINB 5   // resident 256-thread CTAs per SM
+#define B200R_K9_MINB 6   // resident 256-thread CTAs per SM (40 registers: 4.46 ms at C4 against 4.96 at 5 and 5.02 at 4 -- the scans are latency-bound)
 #endif
 template <int MODE>
 __global__ void __launch_bounds__(256, B200R_K9_MINB)
@@ -635,10 +649,30 @@ k_nmr_backward_maps(const float* __restrict__ faces, const int* __restrict__ fac
     if (return_rgb) {  // K10 :675-692
         float* gt = grad_textures + ((size_t)bn * nf + fn) * ts * ts * ts * 3;
         const float g0 = __ldg(grad_rgb_map + i * 3 + 0), g1 = __ldg(grad_rgb_map + i * 3 + 1), g2 = __ldg(grad_rgb_map + i * 3 + 2);
+        const int4 si0 = __ldg(reinterpret_cast<const int4*>(sampling_index_map + i * 8)), si1 = __ldg(reinterpret_cast<const int4*>(sampling_index_map + i * 8) + 1);
+        const float4 sw0 = __ldg(reinterpret_cast<const float4*>(sampling_weight_map + i * 8)), sw1 = __ldg(reinterpret_cast<const float4*>(sampling_weight_map + i * 8) + 1);
+        const int sidx[8] = {si0.x, si0.y, si0.z, si0.w, si1.x, si1.y, si1.z, si1.w};
+        const float swt[8] = {sw0.x, sw0.y, sw0.z, sw0.w, sw1.x, sw1.y, sw1.z, sw1.w};
+        // texture_size 2: the eight taps are the face's eight texels, tap pn at texel (pn&1)*4 + (pn&2) + (pn>>2) (:266-279):
+        // 24 contiguous floats, added with six 16-byte atomics instead of 24 scalar ones (the kernel sits on the atomic rate)
+        bool block8 = (ts == 2) && ((reinterpret_cast<uintptr_t>(gt) & 15) == 0);
+#pragma unroll
+        for (int pn = 0; pn < 8; pn++) block8 = block8 && sidx[pn] == ((pn & 1) * 4 + (pn & 2) + (pn >> 2));
+        if (block8) {
+            float v[24];
+#pragma unroll
+            for (int pn = 0; pn < 8; pn++) {
+                const int t = (pn & 1) * 4 + (pn & 2) + (pn >> 2);
+                v[t * 3 + 0] = swt[pn] * g0; v[t * 3 + 1] = swt[pn] * g1; v[t * 3 + 2] = swt[pn] * g2;
+            }
+            float4* gt4 = reinterpret_cast<float4*>(gt);
+#pragma unroll
+            for (int k = 0; k < 6; k++) atomicAdd(gt4 + k, make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]));
+        } else
 #pragma unroll
         for (int pn = 0; pn < 8; pn++) {
-            const float w = __ldg(sampling_weight_map + i * 8 + pn);
-            const int isc = __ldg(sampling_index_map + i * 8 + pn);
+            const float w = swt[pn];
+            const int isc = sidx[pn];
             const size_t tap = ((size_t)bn * nf + fn) * ts * ts * ts + (size_t)isc;
             if (isc < 0 || tap >= (size_t)batch_size * nf * ts * ts * ts) continue;  // tap past the tensor (ts == 1, see K8)
             atomicAdd(gt + isc * 3 + 0, w * g0);
