@@ -77,7 +77,11 @@ B200R_API size_t b200r_softras_state_bytes(int batch_size, int num_faces);
  *   soft_colors    [B, 4, H, W]   out, planar RGBA, row 0 = top (y = +1)
  *   aggrs_info     [B, 2, H, W]   out: softmax -> (sum, max); hard rgb -> (depth_min, face_index_min)
  *   faces_id_buffer[B, K, H, W]   out, int32, the <=K nearest-z face ids per pixel in the
- *                                 reference's slot order, -1 padded
+ *                                 reference's slot order, -1 TERMINATED: slots [0, n) hold ids, slot n (if n < K) is
+ *                                 -1, and the slots behind it are left untouched (the reference memsets all of them
+ *                                 to -1, soft_rasterize.py:470; the backward only ever reads up to the first -1,
+ *                                 :1236-1237, and so does b200r_softras_backward).  Nothing to initialise on the caller's
+ *                                 side.
  *   faces_info     [B, nf, 27]    out, optional (may be NULL): the reference's K1 output
  *   dist_eps_logit = ln(1/dist_eps - 1) computed by the host as soft_rasterize.py:25
  * Background colour is always 0, as in the reference (the op memsets soft_colors). */

@@ -25,6 +25,8 @@
 
 #ifndef B200R_BWD_MERGE
 #define B200R_BWD_MERGE 1        // warp-side aggregation levels before the atomics: 0 off, 1 = lanes ^1 and ^8, 2 = also ^2 and ^16
+                                 // (a complete per-face reduction -- match.any groups + block-floating-point REDUX.SUM --
+                                 // was measured at 1.73 ms against 0.44 ms at C3: profiles/perf_r02.md)
 #endif
 #ifndef B200R_BWD_MINB
 // resident 256-thread CTAs per SM the backward's register allocation must allow.  Measured at C3: 2 (107 registers)
@@ -352,7 +354,7 @@ k_softras_backward_lane(const SoftRasParams P, const FaceRec* __restrict__ recs,
             }
         }
         fn = fn_next;
-        fn_next = fn_next2;
+        fn_next = (fn < 0) ? -1 : fn_next2;   // the list ends at the first -1; the slots behind it were never written
     }
 }
 

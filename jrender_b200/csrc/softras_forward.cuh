@@ -538,21 +538,32 @@ k_softras_forward(const SoftRasParams P, const FaceRec* __restrict__ recs, const
                 }
             }
         }
-        // top-K ids, slot order, -1 padded (replaces cudaMemsetAsync(out3_p, -1, ...) :470 + :453-455)
+        // top-K ids, slot order, -1 TERMINATED: a pixel's list is slots [0, q_size) followed by one -1 (unless q_size == K);
+        // the slots behind the terminator are not written at all (the reference memsets the whole buffer,
+        // cudaMemsetAsync(out3_p, -1, ...) :470 + :453-455 -- 268 MB per launch at C3, most of the forward's DRAM traffic).
+        // Granularity: an 8-pixel row segment of one id plane is one 32-byte sector, written whole (shorter lists of the
+        // segment padded with -1) up to the plane of the segment's longest list + 1, so no sector is partially written.
         if (vec_ids) {
             // s_qid is [K][4][8]: int4 number u covers plane u / 8, block row (u % 8) / 2 (every lane's own id writes were
             // ordered before these cross-lane reads by the __syncwarp above)
             constexpr int QPR = TW / 4, QPP = NT / 4;
+            static_assert(TW == 8 && NT == 32 && QPP == 8, "the row-segment maximum below assumes 8x4 blocks");
+            int seg = st.q_size;   // longest list of this lane's 8-pixel row segment
+            seg = max(seg, __shfl_xor_sync(0xffffffffu, seg, 1));
+            seg = max(seg, __shfl_xor_sync(0xffffffffu, seg, 2));
+            seg = max(seg, __shfl_xor_sync(0xffffffffu, seg, 4));
+            // this lane stores int4 (lane & 7) of planes lane / 8 + 4 i: block row (lane & 7) / 2, whose lanes are 8 * row ...
+            const int last_plane = __shfl_sync(0xffffffffu, seg, ((lane & 7) >> 1) * 8);
             int* bids = ids_out + (size_t)b * K * npix;
             for (int u = lane; u < K * QPP; u += NT) {
                 const int k = u / QPP, pq = u - k * QPP;
                 const int orow = tr0 + pq / QPR, ocol = tx0 + (pq % QPR) * 4;
-                if (orow < is && ocol < is)
+                if (orow < is && ocol < is && k <= last_plane)
                     *reinterpret_cast<int4*>(bids + (size_t)k * npix + (size_t)orow * is + ocol) = reinterpret_cast<const int4*>(s_qid)[u];
             }
         } else if (px < is && row < is) {
             int* dst = ids_out + (size_t)b * K * npix + (size_t)row * is + px;
-            for (int k = 0; k < K; k++)
+            for (int k = 0; k < K && k <= st.q_size; k++)
                 dst[(size_t)k * npix] = (k < st.q_size) ? s_qid[k * NT + lane] : -1;
         }
     }

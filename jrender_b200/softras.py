@@ -41,6 +41,14 @@ def _check_inputs(face_vertices, textures):
         raise ValueError("textures must be [batch, num_faces, T, 3], got %s" % (tuple(textures.shape),))
 
 
+def pad_face_ids(faces_id_buffer):
+    """The reference's -1 PADDED `faces_id_buffer` (soft_rasterize.py:470 memsets all of it) from the library's -1
+    TERMINATED one: a pixel's top-K list is its slots up to the first -1; the slots behind that terminator are never
+    written by the forward kernel (268 MB of stores per launch at C3) and never read by the backward.  [B,K,H,W] int32."""
+    alive = (faces_id_buffer >= 0).to(torch.uint8).cummin(dim=1).values.bool()
+    return torch.where(alive, faces_id_buffer, torch.full_like(faces_id_buffer, -1))
+
+
 class _SoftRasterizeOp(torch.autograd.Function):
     """autograd glue around b200r_softras_forward / b200r_softras_backward."""
 
@@ -84,7 +92,8 @@ class _SoftRasterizeOp(torch.autograd.Function):
         ctx.scal = scal
         ctx.st_bytes = st_bytes
         ctx.save_for_backward(fv, tx, soft_colors, aggrs_info, faces_id_buffer, state)
-        # The reference keeps these on the Function object (soft_rasterize.py:101); render2 reads
+        # The reference keeps these on the Function object (soft_rasterize.py:101; faces_id_buffer here is -1 terminated,
+        # pad_face_ids() gives the reference's fully padded form); render2 reads
         # save_vars[4] = aggrs_info (render2/render2.py:306).  Detached aliases only: a strong
         # reference to the OUTPUT tensor from here would close the cycle
         # output -> grad_fn -> ctx -> ... -> output, and ~0.9 GB per call would then wait for

@@ -25,6 +25,8 @@ def run_cuda(fv, tex, params, grad=None, device="cuda:0", want_faces_info=True):
         texture_type=params["texture_type"], max_faces_per_pixel_for_grad=params["max_faces_per_pixel_for_grad"])
     fn.return_faces_info = want_faces_info
     soft_colors, aggrs_info, ids = fn.raw(fvt, txt)
+    from jrender_b200.softras import pad_face_ids
+    ids = pad_face_ids(ids)   # the library terminates the per-pixel lists with one -1; the reference pads all K slots
     out = dict(soft_colors=soft_colors.detach().cpu().numpy(), aggrs_info=aggrs_info.cpu().numpy(),
                faces_id_buffer=ids.cpu().numpy())
     if want_faces_info:

@@ -55,7 +55,7 @@ def main():
     print(json.dumps(res), flush=True)
 
     from oracle import ref_gpu, softras as osr
-    if ref_gpu.available():
+    if ref_gpu.available() and not os.environ.get("AB_NO_REF"):
         P = osr.Params(image_size=H)
         fvd, texd = fv.detach(), tex.detach()
 
