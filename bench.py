@@ -307,6 +307,16 @@ def run_ours(args, rank, world, local_rank):
     ev_in = [torch.cuda.Event() for _ in range(2)]      # inputs of slot landed on the device
     ev_free = [torch.cuda.Event() for _ in range(2)]    # compute of the step that used the slot is done
     ev_done = [torch.cuda.Event() for _ in range(2)]
+    ev_out = [torch.cuda.Event() for _ in range(2)]     # the slot's D2H copies have read their device sources
+    keep = [None, None]   # device tensors the D2H stream still reads.  (Not Tensor.record_stream: recorded blocks make the
+                          # caching allocator poll events on every allocation and grow the pool while they are pending.)
+
+    def release(k, i):
+        """before slot k is reused (step i >= 2): the main stream waits for the slot's D2H copies, then the tensors go
+        back to the allocator (whose later main-stream users are ordered behind that wait)."""
+        if i >= 2:
+            s_main.wait_event(ev_out[k])
+        keep[k] = None
 
     def e2e_run(n):
         for i in range(n):
@@ -318,6 +328,7 @@ def run_ours(args, rank, world, local_rank):
                 d_tex[k].copy_(tex_p, non_blocking=True)
                 ev_in[k].record(s_in)
             s_main.wait_event(ev_in[k])
+            release(k, i)
             a = d_fv[k].detach().requires_grad_(True)
             t = d_tex[k].detach().requires_grad_(True)
             img = SoftRasterizeFunction(image_size=H)(a, t)
@@ -325,15 +336,17 @@ def run_ours(args, rank, world, local_rank):
             loss.backward()
             ev_free[k].record(s_main)
             ev_done[k].record(s_main)
+            keep[k] = (a.grad, t.grad, loss)
             with torch.cuda.stream(s_out):
                 s_out.wait_event(ev_done[k])
-                for g in (a.grad, t.grad, loss):
-                    g.record_stream(s_out)
                 gf_p.copy_(a.grad, non_blocking=True)
                 gt_p.copy_(t.grad, non_blocking=True)
                 loss_p[i % 64].copy_(loss.detach(), non_blocking=True)   # D2H read of the step's result
+                ev_out[k].record(s_out)
+            del a, t, img, loss
         s_out.synchronize()
         s_main.synchronize()
+        keep[0] = keep[1] = None
         return float(loss_p[(n - 1) % 64])
 
     e2e_run(3)
@@ -370,15 +383,19 @@ def run_ours(args, rank, world, local_rank):
                 d_tex[k].copy_(tex_p, non_blocking=True)
                 ev_in[k].record(s_in)
             s_main.wait_event(ev_in[k])
+            release(k, i)
             with torch.no_grad():
                 img = SoftRasterizeFunction(image_size=H)(d_fv[k], d_tex[k])
             ev_free[k].record(s_main)
+            keep[k] = img
             with torch.cuda.stream(s_out):
                 s_out.wait_event(ev_free[k])
-                img.record_stream(s_out)
                 img_p[k].copy_(img, non_blocking=True)
+                ev_out[k].record(s_out)
+            del img
         s_out.synchronize()
         s_main.synchronize()
+        keep[0] = keep[1] = None
 
     render_run(3)
     barrier()
@@ -447,6 +464,24 @@ def run_ours(args, rank, world, local_rank):
         chunks = sorted({c for c in (bpg, max(1, bpg // 2), 1) if bpg % c == 0}, reverse=True)
         overlapped = {c: make_overlapped(c) for c in chunks}
 
+        # Pipelined across steps: the gathered batch of step n is collected after step n+1's forward has been enqueued, so
+        # the gather has the backward of its own step AND the raster of the next one to hide behind (a consumer that
+        # logs / displays / post-processes the full batch; a loss on the gathered batch needs the variants above).
+        pipe_og = [OverlappedImageGather(bpg, (4, H, H), dev, chunk=bpg) for _ in range(2)]
+        pipe = {"i": 0, "pending": None}
+
+        def step_pipelined():
+            og = pipe_og[pipe["i"] & 1]
+            pipe["i"] += 1
+            fv.grad = None
+            tex.grad = None
+            im = SoftRasterizeFunction(image_size=H)(fv, tex)
+            og.push(0, im)
+            prev, pipe["pending"] = pipe["pending"], og
+            full_prev = prev.result() if prev is not None else None
+            im.backward(grad)
+            return full_prev
+
         def timed(fn, n=10):
             for _ in range(3):
                 fn()
@@ -463,12 +498,17 @@ def run_ours(args, rank, world, local_rank):
             return float(t.item())
         ref_full = step_blocking().clone()
         same = all(bool(torch.equal(ref_full, f())) for f in overlapped.values())
+        step_pipelined()
+        same = same and bool(torch.equal(ref_full, step_pipelined()))
         t_plain = timed(lambda: step())
         gather_steps = {"images_identical": same, "step_no_gather_ms": t_plain, "step_blocking_gather_ms": timed(step_blocking),
                         "step_overlapped_gather_ms": {"chunk_%d_images" % c: timed(f) for c, f in overlapped.items()},
+                        "step_pipelined_gather_ms": timed(step_pipelined),
                         "note": "each includes a 256 MiB L2 flush write per step (~0.08 ms), unlike ms_per_step; chunk = images per "
                                 "forward launch (chunk == images_per_gpu: one launch, the gather hides behind the backward; smaller "
-                                "chunks hide it behind the next chunk's raster too but pay the per-launch host cost again)"}
+                                "chunks hide it behind the next chunk's raster too but pay the per-launch host cost again); pipelined = the "
+                                "batch of step n is collected during step n+1, behind its own backward and the next raster"}
+        pipe["pending"].result()
 
     if rank != 0:
         return

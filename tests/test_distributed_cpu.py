@@ -42,9 +42,12 @@ def _worker(rank, world, port, batch, out_dir):
     assert torch.equal(full, full2)
     if batch % world == 0:   # the chunked / overlapped gather (synchronous on CPU) must give the same batch order
         from jrender_b200.distributed import OverlappedImageGather
-        g = OverlappedImageGather(images_per_rank=hi - lo, image_shape=tuple(img.shape[1:]), device="cpu")
+        g = OverlappedImageGather(images_per_rank=hi - lo, image_shape=tuple(img.shape[1:]), device="cpu", chunk=1)
         for i in range(hi - lo):
             g.push(i, img[i:i + 1])
+        assert torch.equal(g.result(), full)
+        g = OverlappedImageGather(images_per_rank=hi - lo, image_shape=tuple(img.shape[1:]), device="cpu")   # one chunk
+        g.push(0, img)
         assert torch.equal(g.result(), full)
     if rank == 0:
         np.save(os.path.join(out_dir, "gathered.npy"), full.numpy())
