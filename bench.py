@@ -318,7 +318,10 @@ def run_ours(args, rank, world, local_rank):
             s_main.wait_event(ev_out[k])
         keep[k] = None
 
+    e2e_host = {}
+
     def e2e_run(n):
+        t_enq0 = time.perf_counter()
         for i in range(n):
             k = i & 1
             with torch.cuda.stream(s_in):
@@ -344,6 +347,7 @@ def run_ours(args, rank, world, local_rank):
                 loss_p[i % 64].copy_(loss.detach(), non_blocking=True)   # D2H read of the step's result
                 ev_out[k].record(s_out)
             del a, t, img, loss
+        e2e_host["enqueue_ms"] = (time.perf_counter() - t_enq0) * 1000.0 / max(1, n)   # host time to enqueue one step
         s_out.synchronize()
         s_main.synchronize()
         keep[0] = keep[1] = None
@@ -553,7 +557,8 @@ def run_ours(args, rank, world, local_rank):
         "step_ms": {"min": float(np.min(step_ms)), "median": float(np.median(step_ms)), "max": float(np.max(step_ms))},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "what": "public API, per step: pinned host face_vertices+textures -> H2D -> forward -> on-device MSE loss -> backward -> D2H grads + loss scalar; copies of neighbouring steps overlap the kernels on two copy streams, host waits once at the end"},
+                "what": "public API, per step: pinned host face_vertices+textures -> H2D -> forward -> on-device MSE loss -> backward -> D2H grads + loss scalar; copies of neighbouring steps overlap the kernels on two copy streams, host waits once at the end",
+                "host_enqueue_ms_per_step": e2e_host.get("enqueue_ms"), "ms_per_step": float(t_e2e.item()) / e2e_steps},
         "gpu_launches": int(launches),
         "kernels": kern,
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",

@@ -408,6 +408,76 @@ __device__ __forceinline__ void k9_scan(const float* __restrict__ prow, const in
     }
 }
 
+// The outward scan (:486-520), specialised: it is 2/3 of K9's instructions and all of its load latency.
+//  * Every pixel of an outward scan lies strictly beyond the crossing point (d1_out = floor(d1_cross) + 1 or
+//    ceil(d1_cross) - 1, then away from it), so delta = d1 - d1_cross has ONE sign for the whole scan and the reference's
+//    per-pixel `dist = (0 < dist) ? dist + eps : dist - eps` (:510/:515) adds a per-scan constant: dist = fma(delta, k, +-eps)
+//    (|k| >= 2 / is, so delta * k never underflows; no cancellation, so |dist| >= eps and lanes past the end of the row --
+//    which evaluate a zero record -- add exactly 0).
+//  * `diff_grad <= 0 -> continue` (:503) is max.NaN(diff, 0): a NaN still propagates like the reference's test lets it.
+//  * delta advances by 64 per trip instead of being re-formed from the pixel number (<= 1 ulp of delta).
+//  * Two records per lane in flight, ping-pong: the load of trip t + 2 is issued as soon as trip t's record has been
+//    consumed and is only needed after trip t + 1's arithmetic -- the generic loop below re-used the record's registers
+//    and waited for every load (long_scoreboard 8.1 per issue in profiles/r02d).
+// Trip count is warp-uniform; only the loads are predicated.
+template <int MODE>
+struct K9Px { float4 q; float ga; };
+
+template <int MODE>
+__device__ __forceinline__ K9Px<MODE> k9_load_px(const float* __restrict__ p, bool on) {
+    K9Px<MODE> r;
+    r.q = make_float4(0.f, 0.f, 0.f, 0.f);
+    r.ga = 0.f;
+    if (on) {
+        if (MODE == 2) { const float2 t = __ldg(reinterpret_cast<const float2*>(p)); r.q.x = t.x; r.q.y = t.y; }
+        else r.q = __ldg(reinterpret_cast<const float4*>(p));
+        if (MODE == 3) r.ga = __ldg(p + 4);
+    }
+    return r;
+}
+
+__device__ __forceinline__ float max_nan(float a, float b) {
+    float r;
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+}
+
+template <int MODE>
+__device__ __forceinline__ void k9_term(const K9Px<MODE>& c, float r0, float r1, float r2, float ra, float delta,
+                                        float k0, float k1, float e0, float e1, float& acc0, float& acc1) {
+    float diff;
+    if (MODE == 1) diff = c.q.x - __fmaf_rn(r2, c.q.w, __fmaf_rn(r1, c.q.z, r0 * c.q.y));
+    else if (MODE == 2) diff = c.q.x - ra * c.q.y;
+    else diff = c.q.x - __fmaf_rn(ra, c.ga, __fmaf_rn(r2, c.q.w, __fmaf_rn(r1, c.q.z, r0 * c.q.y)));
+    const float d = max_nan(diff, 0.f);
+    acc0 = __fmaf_rn(-d, rcp_approx(__fmaf_rn(delta, k0, e0)), acc0);
+    acc1 = __fmaf_rn(-d, rcp_approx(__fmaf_rn(delta, k1, e1)), acc1);
+}
+
+template <int MODE>
+__device__ __forceinline__ void k9_scan_out(const float* __restrict__ prow, int d1_from, int d1_to, int lane,
+                                            float r0, float r1, float r2, float ra, float d1_cross, float k0, float k1,
+                                            float eps, float& acc0, float& acc1) {
+    constexpr int FL = K9Rec<MODE>::FL;
+    const int n = d1_to - d1_from + 1;   // pixels of the scan, warp-uniform
+    const int mine = n - lane;           // this lane has a pixel in trip t (32 pixels each) iff 32 t < mine
+    const float* __restrict__ p = prow + (d1_from + lane) * FL;
+    float delta = (float)(d1_from + lane) - d1_cross;
+    const float side = (float)d1_from - d1_cross;   // the sign every delta of this scan has
+    const float e0 = (0.f < side * k0) ? eps : -eps;
+    const float e1 = (0.f < side * k1) ? eps : -eps;
+    K9Px<MODE> a = k9_load_px<MODE>(p, mine > 0);
+    K9Px<MODE> b = k9_load_px<MODE>(p + 32 * FL, mine > 32);
+    for (int t = 64; t < n + 64; t += 64) {   // t = first pixel of the trip pair AFTER the one being evaluated
+        p += 64 * FL;
+        k9_term<MODE>(a, r0, r1, r2, ra, delta, k0, k1, e0, e1, acc0, acc1);
+        a = k9_load_px<MODE>(p, mine > t);
+        k9_term<MODE>(b, r0, r1, r2, ra, delta + 32.f, k0, k1, e0, e1, acc0, acc1);
+        b = k9_load_px<MODE>(p + 32 * FL, mine > t + 32);
+        delta += 64.f;
+    }
+}
+
 // One (edge, axis) pass of the reference's per-face loop (:386-410): the edge's vertices in (major, minor) pixel
 // coordinates, the scan direction and the range of integer major coordinates d0 the edge crosses.
 struct K9Pass {
@@ -534,7 +604,8 @@ k_nmr_backward_pixel_map(const float* __restrict__ faces, const int* __restrict_
         int in_from = max(min(d1_in, ilim), 0), in_to = min(max(d1_in, ilim), is - 1);
         if (!live) { in_from = 1; in_to = 0; }
         // ---- inward scans of small faces: a few pixels each, so every lane walks ITS OWN sample's pixels (:556-601) instead
-        // of the warp visiting the samples one after the other for a single partly filled trip each
+        // of the warp visiting the samples one after the other for a single partly filled trip each.  (Requesting a pixel's
+        // record together with its owner, instead of after the owner test, was slower: 3.30 vs 3.18 ms at C4.)
         constexpr int kSerialIn = 64;
         if (in_from <= in_to && in_to - in_from < kSerialIn) {
             const float* __restrict__ prow_l = ((axis == 0) ? pv_img : ph_img) + d0 * is * FL;
@@ -609,7 +680,7 @@ k_nmr_backward_pixel_map(const float* __restrict__ faces, const int* __restrict_
             if (s_of <= s_ot) {   // outwards from the edge to the image border; reference colour = the in-pixel's
                 const float r0 = __shfl_sync(FULL, i0, src), r1 = __shfl_sync(FULL, i1, src), r2 = __shfl_sync(FULL, i2, src);
                 const float ra = (MODE & 2) ? __shfl_sync(FULL, ia, src) : 0.f;
-                if (both) k9_scan<MODE, false, true>(prow, nullptr, 0, s_of, s_ot, lane, fn, r0, r1, r2, ra, s_cross, s_k0, s_k1, true, true, eps, acc0, acc1);
+                if (both) k9_scan_out<MODE>(prow, s_of, s_ot, lane, r0, r1, r2, ra, s_cross, s_k0, s_k1, eps, acc0, acc1);
                 else k9_scan<MODE, false, false>(prow, nullptr, 0, s_of, s_ot, lane, fn, r0, r1, r2, ra, s_cross, s_k0, s_k1, (s_flags & 1) != 0, (s_flags & 2) != 0, eps, acc0, acc1);
             }
             if (s_if <= s_it) {   // inwards up to the opposite edge, pixels owned by the face; reference colour = the out-pixel's
