@@ -66,8 +66,10 @@ B200R_API const char* b200r_last_error(void);
  *              records (what the reference keeps in `faces_info`, soft_rasterize.py:62,101) and the backward's gradient
  *              accumulator.  208 bytes per (batch, face).
  *   workspace  b200r_softras_workspace_bytes(batch, num_faces, image_size): transient scratch of the forward only (binning
- *              lists with capacity num_faces per 64-pixel bin so that nothing can overflow, tile queue); free to be
- *              released or reused once the forward has been enqueued. */
+ *              lists in a pool of 512-id chunks budgeted at 8 list entries per face -- bins that find the pool exhausted
+ *              are flagged and their blocks filter the whole face list, so nothing is ever dropped -- and the block
+ *              queue); free to be released or reused once the forward has been enqueued.  ~12 MB for 4 x 1024^2 images of
+ *              39 200 faces. */
 B200R_API size_t b200r_softras_workspace_bytes(int batch_size, int num_faces, int image_size);
 B200R_API size_t b200r_softras_state_bytes(int batch_size, int num_faces);
 
@@ -246,7 +248,9 @@ B200R_API unsigned long long b200r_launch_count(void);
  *   "softras_fwd_persistent" 0 = one CTA per tile, 1 = persistent grid + tile queue (default)
  *   "softras_exact_tail"     1 = the reference's double-precision sigmoid / alpha-product tails bit for bit;
  *                            0 (default) = the same expressions in fp32 for the default euclidean+softmax
- *                            mode (<= 1 ulp on D; all index / depth outputs are identical either way) */
+ *                            mode (<= 1 ulp on D; all index / depth outputs are identical either way)
+ *   "softras_list_pool_chunks" >= 0 caps the binning-list chunk pool (exercises the pool-exhausted path in tests);
+ *                            -1 (default) = the size b200r_softras_workspace_bytes accounts for */
 B200R_API int b200r_set_option(const char* name, int value);
 
 /* Per-kernel device timing (CUDA events recorded on the launch stream around every kernel

@@ -14,6 +14,9 @@
 #define B200R_TILE 16          // fine tile edge in pixels (one CTA of 256 threads)
 #define B200R_TILE_THREADS 256
 #define B200R_MAX_COARSE_SIDE 16
+#define B200R_LIST_CHUNK 512            // ids per chunk of the pooled coarse lists (a multiple of the forward's 128-entry filter pass)
+#define B200R_LIST_CHUNK_SHIFT 9
+#define B200R_LIST_IDS_PER_FACE 8       // pool budget: one partial chunk per bin + this many list entries per face
 
 // Per-face record, 160 bytes, written once by the setup kernel and staged through
 // shared memory by the raster kernels.  Replaces the reference's faces_info
@@ -46,7 +49,7 @@ struct SoftRasParams {
     int fntx, fnty; // forward tiles per image row / column
     int coarse_px;  // coarse bin edge in pixels (multiple of B200R_TILE)
     int ncs;        // coarse bins per image side
-    int queue_len;    // persistent scheduler: entries of tile_order (>= tiles; holes are -1)
+    int queue_len;    // persistent scheduler: entries of tile_order (one per forward block)
     int aa;           // backward: grad_soft_colors is the gradient of the 2x2-mean-pooled image [B,4,is/2,is/2] (anti-aliasing prologue)
 };
 
@@ -61,11 +64,13 @@ struct SoftRasWorkspace {
     size_t state_bytes;
     uint2* rects;        // [B*nf]  (rect_x, rect_r) copy for the binning scans
     uint2* chunk_rects;  // [B*ceil(nf/256)] union rectangle of each run of 256 consecutive faces
-    int* coarse_cnt;     // [B*ncs*ncs]
-    int* coarse_ids;     // [B*ncs*ncs][nf]
-    int* counters;       // [256] scheduler state, zeroed per launch: [0] queue head, [64..127] cost histogram, [128..191] scatter cursors
+    int* coarse_cnt;     // [B*ncs*ncs] list length; -1: the chunk pool ran out, the forward filters the whole face list for this bin
+    int* chunk_table;    // [B*ncs*ncs][chunks_per_bin] pool chunk holding the list's k-th run of B200R_LIST_CHUNK ids
+    int* coarse_pool;    // [pool_chunks][B200R_LIST_CHUNK] face ids, ascending within a list
+    int chunks_per_bin, pool_chunks;
+    int* counters;       // [256] scheduler state, zeroed per launch: [0] queue head, [1] pool cursor, [64..127] cost histogram, [128..191] scatter cursors
     int* tile_cost;      // [B*max_tiles] (pixel, face) pairs per forward tile (smallest tile 8x4)
-    int* tile_order;     // [B*max_tiles] tile ids, most expensive first
+    uint2* tile_order;   // [B*max_tiles] forward blocks, most expensive first: x = column | row << 16, y = image | (no face touches it) << 31
     size_t bytes;        // of the workspace block
 };
 
@@ -99,15 +104,28 @@ static inline SoftRasWorkspace b200r_carve(void* state, void* base, int B, int n
     off += b200r_align256((size_t)B * ((nf + 255) / 256) * sizeof(uint2));
     w.coarse_cnt = (int*)(p + off);
     off += b200r_align256((size_t)B * ncs * ncs * sizeof(int));
-    w.coarse_ids = (int*)(p + off);
-    off += b200r_align256((size_t)B * ncs * ncs * (size_t)nf * sizeof(int));
+    // Coarse lists live in a pool of fixed-size chunks handed out by an atomic cursor while k_coarse_bin scans (capacity
+    // nf per bin -- 160 MB at C3 -- would be the only overflow-proof layout without a host round trip for the totals).
+    // A bin that finds the pool empty is flagged instead (coarse_cnt = -1) and the forward filters the whole face list
+    // for its blocks: same faces, same order, only slower -- and lists that long mean every block holds most faces anyway.
+    w.chunks_per_bin = (nf + B200R_LIST_CHUNK - 1) / B200R_LIST_CHUNK;
+    {
+        const size_t budget = (size_t)B * ncs * ncs + ((size_t)B * nf * B200R_LIST_IDS_PER_FACE + B200R_LIST_CHUNK - 1) / B200R_LIST_CHUNK;
+        const size_t full = (size_t)B * ncs * ncs * w.chunks_per_bin;   // every list complete: never needs more than this
+        const size_t n = budget < full ? budget : full;
+        w.pool_chunks = (int)(n < (size_t)0x3fffff ? n : (size_t)0x3fffff);   // chunk << 9 stays inside 31 bits
+    }
+    w.chunk_table = (int*)(p + off);
+    off += b200r_align256((size_t)B * ncs * ncs * w.chunks_per_bin * sizeof(int));
+    w.coarse_pool = (int*)(p + off);
+    off += b200r_align256((size_t)w.pool_chunks * B200R_LIST_CHUNK * sizeof(int));
     w.counters = (int*)(p + off);
     off += b200r_align256(256 * sizeof(int));
     const size_t max_tiles = (size_t)ntx * ntx * 8;  // queue slots: 8 forward tiles (8x4) per 16x16 cost tile
     w.tile_cost = (int*)(p + off);
     off += b200r_align256((size_t)B * max_tiles * sizeof(int));
-    w.tile_order = (int*)(p + off);
-    off += b200r_align256((size_t)B * max_tiles * sizeof(int));
+    w.tile_order = (uint2*)(p + off);
+    off += b200r_align256((size_t)B * max_tiles * sizeof(uint2));
     w.bytes = off;
     return w;
 }

@@ -15,6 +15,7 @@ namespace {
 
 std::atomic<int> g_fwd_persistent{1};  // 0: one CTA per tile, 1: persistent grid + atomic tile queue
 std::atomic<int> g_exact_tail{0};      // 1: reference's double-precision sigmoid / alpha tails bit for bit; 0: fp32 tails (<= 1 ulp)
+std::atomic<int> g_pool_cap{-1};       // >= 0: cap on the coarse-list chunk pool (tests of the pool-exhausted path); -1: the carved size
 }  // namespace
 
 namespace {
@@ -62,6 +63,7 @@ int b200r_set_option(const char* name, int value) {
     if (!name) return b200r_fail(B200R_EINVAL, "b200r_set_option: NULL name");
     if (!strcmp(name, "softras_fwd_persistent")) { g_fwd_persistent.store(value ? 1 : 0); return 0; }
     if (!strcmp(name, "softras_exact_tail")) { g_exact_tail.store(value ? 1 : 0); return 0; }
+    if (!strcmp(name, "softras_list_pool_chunks")) { g_pool_cap.store(value < 0 ? -1 : value); return 0; }
     return b200r_fail(B200R_EINVAL, "b200r_set_option: unknown option '%s'", name);
 }
 
@@ -84,7 +86,11 @@ static int softras_forward_impl(const float* face_vertices, const float* texture
     if (rc) return rc;
     if (!face_vertices || !textures || !soft_colors || !aggrs_info || !faces_id_buffer || !workspace || !state)
         return b200r_fail(B200R_EINVAL, "b200r_softras_forward: NULL pointer argument");
-    const SoftRasWorkspace W = b200r_carve(state, workspace, B, nf, is);
+    SoftRasWorkspace W = b200r_carve(state, workspace, B, nf, is);
+    {
+        const int cap = g_pool_cap.load();
+        if (cap >= 0 && cap < W.pool_chunks) W.pool_chunks = cap;
+    }
     if (workspace_bytes < W.bytes)
         return b200r_fail(B200R_EWORKSPACE, "b200r_softras_forward: workspace %zu < required %zu bytes", workspace_bytes, W.bytes);
     if (state_bytes < W.state_bytes)
@@ -107,7 +113,8 @@ static int softras_forward_impl(const float* face_vertices, const float* texture
     {
         B200rProfScope prof(B200R_K_COARSE_BIN, st);
         k_chunk_rects<<<dim3((nf + 255) / 256, B), 256, 0, st>>>(W.rects, W.chunk_rects, nf);
-        k_coarse_bin<<<dim3(P.ncs * P.ncs, B), 256, 0, st>>>(W.rects, W.chunk_rects, W.coarse_cnt, W.coarse_ids, W.tile_cost, W.counters + 64,
+        k_coarse_bin<<<dim3(P.ncs * P.ncs, B), 256, 0, st>>>(W.rects, W.chunk_rects, W.coarse_cnt, W.chunk_table, W.coarse_pool, W.counters + 1,
+                                                             W.chunks_per_bin, W.pool_chunks, W.tile_cost, W.counters + 64,
                                                              nf, is, P.coarse_px, P.ncs, P.ftw, P.fth, P.fntx, P.fnty);
     }
     e = cudaGetLastError();

@@ -63,7 +63,7 @@ __device__ __forceinline__ void f2_mbar_wait(unsigned long long* bar, uint32_t p
 // async-proxy writes of the next bulk copies
 __device__ __forceinline__ void f2_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-constexpr int kFwdChunk = 16;   // records staged per round: 16 rather than 32 keeps 24 warps resident per SM
+constexpr int kFwdChunk = 16;   // records resident per warp: 16 rather than 32 keeps 24 warps resident per SM
 constexpr int kFwdUnr = 4;      // coarse entries filtered per lane per pass
 
 struct FwdSmem {
@@ -298,14 +298,49 @@ __device__ __forceinline__ void store_pooled_8x4(const float* s_out, float* __re
     if (orow < hp && ocol < hp) pooled[(((size_t)b * 4 + ch) * hp + orow) * hp + ocol] = v;
 }
 
+// lanes (row-major 8x4 block at pixel (tx0, tr0)) covered by a check_border rectangle rx = x0 | x1 << 16, rr = r0 | r1 << 16:
+// a column mask replicated over the covered rows; 0 when the rectangle misses the block (or is the empty rectangle (1, 0))
+__device__ __forceinline__ uint32_t rect_lane_mask(uint32_t rx, uint32_t rr, int tx0, int tr0) {
+    const int cx0 = max((int)(rx & 0xffffu) - tx0, 0), cx1 = min((int)(rx >> 16) - tx0, 7);
+    const int ry0 = max((int)(rr & 0xffffu) - tr0, 0), ry1 = min((int)(rr >> 16) - tr0, 3);
+    if (cx0 > cx1 || ry0 > ry1) return 0u;
+    const uint32_t cols = (2u << cx1) - (1u << cx0);
+    const uint32_t rows = (0xffffffffu >> (24 - 8 * ry1)) & (0xffffffffu << (8 * ry0));
+    return (cols * 0x01010101u) & rows;
+}
+
+// :425-455: a pixel's six output values from its final state.  The three colour quotients share one refined reciprocal
+// (fast_div returns the correctly rounded quotient for every input, exact_math.cuh).
+template <int RGB>
+__device__ __forceinline__ void finalize_pixel(const PixState& st, const SoftRasParams& P, float& o0, float& o1, float& o2,
+                                               float& out_a, float& g0, float& g1) {
+    if (P.alpha_func == 0) out_a = st.alpha;
+    else if (P.alpha_func == 1) out_a = st.alpha / (float)P.nf;
+    else out_a = (float)(1.0 - (double)st.alpha);
+    if (RGB == 0) {
+        o0 = st.sc0; o1 = st.sc1; o2 = st.sc2;  // stays at the (zero) background when no face was hit
+        g0 = st.depth_min; g1 = (float)st.face_index_min;
+    } else if (RGB == 1) {
+        const float r = rcp_refined(st.softmax_sum);
+        const bool safe = midrange(st.softmax_sum);
+        o0 = fast_div(st.sc0, st.softmax_sum, r, safe);
+        o1 = fast_div(st.sc1, st.softmax_sum, r, safe);
+        o2 = fast_div(st.sc2, st.softmax_sum, r, safe);
+        g0 = st.softmax_sum; g1 = st.softmax_max;
+    } else {
+        o0 = o1 = o2 = 0.f; g0 = g1 = 0.f;
+    }
+}
+
 template <int DIST, int RGB, bool EXACT>
 __global__ void __launch_bounds__(32, B200R_FWD_MINB1)
 k_softras_forward(const SoftRasParams P, const FaceRec* __restrict__ recs, const uint2* __restrict__ rects,
-                  const int* __restrict__ coarse_cnt, const int* __restrict__ coarse_ids,
-                  const float* __restrict__ textures, float* __restrict__ soft_colors,
+                  const int* __restrict__ coarse_cnt, const int* __restrict__ chunk_table,
+                  const int* __restrict__ coarse_pool, const int chunks_per_bin, const float* __restrict__ textures, float* __restrict__ soft_colors,
                   float* __restrict__ aggrs_info, int* __restrict__ ids_out, int* tile_counter,
-                  const int* __restrict__ tile_order, float* __restrict__ pooled) {
+                  const uint2* __restrict__ tile_order, float* __restrict__ pooled) {
     constexpr int NT = 32, CHUNK = kFwdChunk, UNR = kFwdUnr, TW = 8, TH = 4;
+    constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FwdSmem& S = *reinterpret_cast<FwdSmem*>(smem_raw);
     const int qzs = fwd_qz_stride(P.K);
@@ -314,7 +349,6 @@ k_softras_forward(const SoftRasParams P, const FaceRec* __restrict__ recs, const
     const int lane = threadIdx.x;
     float* s_qz = s_qz_all + (size_t)lane * qzs;                              // this pixel's K depths, slot order
     const int is = P.is, nf = P.nf, K = P.K;
-    const int tiles_per_image = P.fntx * P.fnty;
     const int lx = lane & 7, ly = lane >> 3;   // lane = row-major pixel index inside the block = index of the [K][4][8] id planes
     const float threshold = P.dist_eps * P.sigma;  // :289
     const size_t npix = (size_t)is * is;
@@ -323,6 +357,8 @@ k_softras_forward(const SoftRasParams P, const FaceRec* __restrict__ recs, const
     const bool consts_ok = dc.consts_ok();
     const float softmax_sum0 = expf(P.eps / P.gamma);
     const uint32_t lt_mask = (1u << lane) - 1u;
+    const bool vec_out = (is & 3) == 0;
+    const bool vec_ids = vec_out && ((K & 3) == 0);
 #if B200R_FWD_TMA
     if (lane == 0) f2_mbar_init(&S.mbar, 1);
     __syncwarp();
@@ -331,27 +367,27 @@ k_softras_forward(const SoftRasParams P, const FaceRec* __restrict__ recs, const
 
     for (int titer = 0;; titer++) {
         // ---- which block
-        int t;
+        int b, tx, ty;
+        bool empty = false;   // no face rectangle touches the block (k_coarse_bin's exact per-block count is 0)
         if (tile_counter == nullptr) {
             if (titer > 0) break;
-            t = blockIdx.y * tiles_per_image + blockIdx.x;
+            b = blockIdx.y;
+            tx = blockIdx.x % P.fntx;
+            ty = blockIdx.x / P.fntx;
         } else {
             __syncwarp();  // previous block fully written
             int q = 0;
             if (lane == 0) q = atomicAdd(tile_counter, 1);
-            q = __shfl_sync(0xffffffffu, q, 0);
+            q = __shfl_sync(FULL, q, 0);
             if (q >= P.queue_len) break;
-            t = __ldg(tile_order + q);  // most expensive blocks first (k_tile_order)
-            if (t < 0) continue;
+            const uint2 te = __ldg(tile_order + q);  // most expensive blocks first (k_tile_order): x | y << 16, image | empty << 31
+            tx = (int)(te.x & 0xffffu);
+            ty = (int)(te.x >> 16);
+            b = (int)(te.y & 0x7fffffffu);
+            empty = (te.y >> 31) != 0u;
         }
-        const int b = t / tiles_per_image;
-        const int tt = t - b * tiles_per_image;
-        const int tx = tt % P.fntx, ty = tt / P.fntx;
-        const int tx0 = tx * TW, tx1 = tx0 + TW - 1;   // block footprint (inclusive pixel ranges)
-        const int tr0 = ty * TH, tr1 = tr0 + TH - 1;
+        const int tx0 = tx * TW, tr0 = ty * TH;   // block origin
         const int px = tx0 + lx, row = tr0 + ly;
-        const float xp = b200r_pix_coord(px, is);
-        const float yp = b200r_pix_coord(is - 1 - row, is);
 
         // ---- per-pixel state, initialised as :291-309 (background buffer is all zero, Q1)
         PixState st;
@@ -366,17 +402,46 @@ k_softras_forward(const SoftRasParams P, const FaceRec* __restrict__ recs, const
         st.q_size = 0;
         st.q_max_z = -1.f;
         st.q_max_id = -1;
+
+        // ---- blocks no rectangle touches (78 % of the blocks at C3): every pixel leaves with its initial state.  Six constant
+        // planes and the terminator of the id lists, straight from registers.
+        if (empty && vec_ids && pooled == nullptr) {
+            float o[6];
+            finalize_pixel<RGB>(st, P, o[0], o[1], o[2], o[3], o[4], o[5]);
+            for (int j = lane; j < 6 * TH * 2; j += NT) {
+                const int ch = j >> 3, r = (j >> 1) & 3, q = j & 1;
+                const float v = ch == 0 ? o[0] : ch == 1 ? o[1] : ch == 2 ? o[2] : ch == 3 ? o[3] : ch == 4 ? o[4] : o[5];
+                const int orow = tr0 + r, ocol = tx0 + q * 4;
+                if (orow < is && ocol < is) {
+                    float* dst = (ch < 4) ? soft_colors + ((size_t)b * 4 + ch) * npix
+                                          : aggrs_info + ((size_t)b * 2 + (ch - 4)) * npix;
+                    *reinterpret_cast<float4*>(dst + (size_t)orow * is + ocol) = make_float4(v, v, v, v);
+                }
+            }
+            if (lane < TH * 2) {
+                const int orow = tr0 + (lane >> 1), ocol = tx0 + (lane & 1) * 4;
+                if (orow < is && ocol < is)
+                    *reinterpret_cast<int4*>(ids_out + (size_t)b * K * npix + (size_t)orow * is + ocol) = make_int4(-1, -1, -1, -1);
+            }
+            continue;
+        }
+
+        const float xp = b200r_pix_coord(px, is);
+        const float yp = b200r_pix_coord(is - 1 - row, is);
         // id slots start as -1 (the reference memsets the whole buffer, :470): the block's ids are then written out plane
         // by plane as 16-byte row segments straight from shared memory.  The previous block's stores finished reading
         // s_qid at the __syncwarp at the top of this iteration.
-        const bool vec_ids = ((is & 3) == 0) && ((K & 3) == 0);
         if (vec_ids) {
             for (int j = lane; j < K * NT / 4; j += NT) reinterpret_cast<int4*>(s_qid)[j] = make_int4(-1, -1, -1, -1);
         }
 
         const int cbin = (tr0 / P.coarse_px) * P.ncs + (tx0 / P.coarse_px);
-        const int n_coarse = coarse_cnt[b * P.ncs * P.ncs + cbin];
-        const int* clist = coarse_ids + ((size_t)b * P.ncs * P.ncs + cbin) * nf;
+        // the bin's face list: runs of B200R_LIST_CHUNK ids in pool chunks (k_coarse_bin); -1 = the pool ran out while this
+        // bin was listed, so its blocks filter the complete face list (identity) -- same faces, same order
+        const int cnt = empty ? 0 : coarse_cnt[b * P.ncs * P.ncs + cbin];
+        const bool unlisted = cnt < 0;
+        const int n_coarse = unlisted ? nf : cnt;
+        const int* tbl = chunk_table + ((size_t)b * P.ncs * P.ncs + cbin) * chunks_per_bin;
         const uint2* brects = rects + (size_t)b * nf;
         const FaceRec* brecs = recs + (size_t)b * nf;
         const float* btex = textures + (size_t)b * nf * P.T * 3;
@@ -396,17 +461,20 @@ k_softras_forward(const SoftRasParams P, const FaceRec* __restrict__ recs, const
             {
                 int id[UNR];
                 uint2 rc[UNR];
+                // one pass = 128 consecutive list entries starting at a multiple of 128: inside one chunk
+                const int* chunk = unlisted ? nullptr
+                                            : coarse_pool + ((size_t)__ldg(tbl + (base >> B200R_LIST_CHUNK_SHIFT)) << B200R_LIST_CHUNK_SHIFT) + (base & (B200R_LIST_CHUNK - 1));
 #pragma unroll
                 for (int u = 0; u < UNR; u++) {
                     const int i = base + u * NT + lane;
-                    id[u] = (i < n_coarse) ? __ldg(clist + i) : -1;
+                    id[u] = (i < n_coarse) ? (unlisted ? i : __ldg(chunk + u * NT + lane)) : -1;
                 }
 #pragma unroll
                 for (int u = 0; u < UNR; u++) rc[u] = (id[u] >= 0) ? __ldg(brects + id[u]) : make_uint2(1u, 1u);
 #pragma unroll
                 for (int u = 0; u < UNR; u++) {
-                    const bool pass = id[u] >= 0 && rect_overlaps(rc[u], tx0, tx1, tr0, tr1);
-                    const unsigned bal = __ballot_sync(0xffffffffu, pass);
+                    const bool pass = id[u] >= 0 && rect_overlaps(rc[u], tx0, tx0 + TW - 1, tr0, tr0 + TH - 1);
+                    const unsigned bal = __ballot_sync(FULL, pass);
                     if (pass) S.ids[n_pending + __popc(bal & lt_mask)] = id[u];
                     n_pending += __popc(bal);
                 }
@@ -448,20 +516,10 @@ k_softras_forward(const SoftRasParams P, const FaceRec* __restrict__ recs, const
                 __syncwarp();
 #endif
                 // ---- per-lane face masks by transposition: lane j turns record j's rectangle, clipped to the 8x4
-                // block, into the 32-bit set of covered lanes (a column mask replicated over the covered rows); every
-                // lane then picks its own bit out of the 16 words (4 broadcast LDS.128).  ~40 instructions per round
-                // instead of 16 x (rectangle load + two range tests).
+                // block, into the 32-bit set of covered lanes; every lane then picks its own bit out of the 16 words
+                // (4 broadcast LDS.128).
                 uint32_t lm = 0u;
-                if (lane < m) {
-                    const uint32_t rx = S.rec[lane].r.rect_x, rr = S.rec[lane].r.rect_r;
-                    const int cx0 = max((int)(rx & 0xffffu) - tx0, 0), cx1 = min((int)(rx >> 16) - tx0, 7);
-                    const int ry0 = max((int)(rr & 0xffffu) - tr0, 0), ry1 = min((int)(rr >> 16) - tr0, 3);
-                    if (cx0 <= cx1 && ry0 <= ry1) {
-                        const uint32_t cols = (2u << cx1) - (1u << cx0);
-                        const uint32_t rows = (0xffffffffu >> (24 - 8 * ry1)) & (0xffffffffu << (8 * ry0));
-                        lm = (cols * 0x01010101u) & rows;
-                    }
-                }
+                if (lane < m) lm = rect_lane_mask(S.rec[lane].r.rect_x, S.rec[lane].r.rect_r, tx0, tr0);
                 if (lane < CHUNK) S.lmask[lane] = lm;
                 __syncwarp();
                 unsigned mask = 0u;   // bit j: staged record j covers this lane's pixel (ascending record = ascending face id)
@@ -474,7 +532,7 @@ k_softras_forward(const SoftRasParams P, const FaceRec* __restrict__ recs, const
                     mask |= ((m4.w >> lane) & 1u) << (4 * q + 3);
                 }
                 // ---- the lanes walk their masks in lock-step
-                const int maxcnt = __reduce_max_sync(0xffffffffu, __popc(mask));
+                const int maxcnt = __reduce_max_sync(FULL, __popc(mask));
                 for (int i = 0; i < maxcnt; i++) {
                     if (mask != 0u) {
                         const FaceRec* rec = &S.rec[__ffs(mask) - 1].r;
@@ -488,20 +546,8 @@ k_softras_forward(const SoftRasParams P, const FaceRec* __restrict__ recs, const
         }
 
         // ---- finalise (:425-455)
-        float out_a;
-        if (P.alpha_func == 0) out_a = st.alpha;
-        else if (P.alpha_func == 1) out_a = st.alpha / (float)nf;
-        else out_a = (float)(1.0 - (double)st.alpha);
-        float o0, o1, o2, g0, g1;
-        if (RGB == 0) {
-            o0 = st.sc0; o1 = st.sc1; o2 = st.sc2;  // stays at the (zero) background when no face was hit
-            g0 = st.depth_min; g1 = (float)st.face_index_min;
-        } else if (RGB == 1) {
-            o0 = st.sc0 / st.softmax_sum; o1 = st.sc1 / st.softmax_sum; o2 = st.sc2 / st.softmax_sum;
-            g0 = st.softmax_sum; g1 = st.softmax_max;
-        } else {
-            o0 = o1 = o2 = 0.f; g0 = g1 = 0.f;
-        }
+        float o0, o1, o2, out_a, g0, g1;
+        finalize_pixel<RGB>(st, P, o0, o1, o2, out_a, g0, g1);
 
         // Stage the 6 output planes of the block in shared memory and write each plane row with 16-byte stores
         // (32 contiguous bytes per block row).
@@ -515,7 +561,7 @@ k_softras_forward(const SoftRasParams P, const FaceRec* __restrict__ recs, const
         s_out[5 * NT + lane] = g1;
         __syncwarp();
         if (pooled != nullptr) store_pooled_8x4(s_out, pooled, b, tx0, tr0, is, lane);   // anti-aliasing epilogue
-        if ((is & 3) == 0) {
+        if (vec_out) {
             constexpr int QPR = TW / 4;  // float4 per block row
             for (int j = lane; j < 6 * TH * QPR; j += NT) {
                 const int ch = j / (TH * QPR), r = (j % (TH * QPR)) / QPR, q = j % QPR;
@@ -549,11 +595,11 @@ k_softras_forward(const SoftRasParams P, const FaceRec* __restrict__ recs, const
             constexpr int QPR = TW / 4, QPP = NT / 4;
             static_assert(TW == 8 && NT == 32 && QPP == 8, "the row-segment maximum below assumes 8x4 blocks");
             int seg = st.q_size;   // longest list of this lane's 8-pixel row segment
-            seg = max(seg, __shfl_xor_sync(0xffffffffu, seg, 1));
-            seg = max(seg, __shfl_xor_sync(0xffffffffu, seg, 2));
-            seg = max(seg, __shfl_xor_sync(0xffffffffu, seg, 4));
+            seg = max(seg, __shfl_xor_sync(FULL, seg, 1));
+            seg = max(seg, __shfl_xor_sync(FULL, seg, 2));
+            seg = max(seg, __shfl_xor_sync(FULL, seg, 4));
             // this lane stores int4 (lane & 7) of planes lane / 8 + 4 i: block row (lane & 7) / 2, whose lanes are 8 * row ...
-            const int last_plane = __shfl_sync(0xffffffffu, seg, ((lane & 7) >> 1) * 8);
+            const int last_plane = __shfl_sync(FULL, seg, ((lane & 7) >> 1) * 8);
             int* bids = ids_out + (size_t)b * K * npix;
             for (int u = lane; u < K * QPP; u += NT) {
                 const int k = u / QPP, pq = u - k * QPP;

@@ -50,7 +50,7 @@ cudaError_t launch_v1(const SoftRasParams& P, const SoftRasWorkspace& W, const f
     {
         B200rProfScope prof(B200R_K_SOFTRAS_FWD, st);
         k_softras_forward<DIST, RGB, EXACT><<<grid, 32, smem, st>>>(
-            P, W.recs, W.rects, W.coarse_cnt, W.coarse_ids, textures, soft_colors, aggrs_info, ids, counter, W.tile_order, pooled);
+            P, W.recs, W.rects, W.coarse_cnt, W.chunk_table, W.coarse_pool, W.chunks_per_bin, textures, soft_colors, aggrs_info, ids, counter, W.tile_order, pooled);
     }
     return cudaGetLastError();
 }

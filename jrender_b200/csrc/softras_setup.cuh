@@ -184,8 +184,9 @@ __device__ __forceinline__ int block_excl_scan_256(int cnt, int* s_warp, int& to
 // batch element b in ascending face id and appends the overlapping ids, in order, to its
 // list.  Replaces TriangleBoundingBoxKernel + RasterizeCoarseCudaKernel
 // (cuda/soft_rasterize_coarse_to_fine.py:96-280) whose per-bin order is race-dependent and
-// whose fixed-capacity bins silently overflow; here capacity is nf per bin and the test is
-// the exact check_border rectangle.
+// whose fixed-capacity bins silently overflow; here the lists grow chunk by chunk out of a shared
+// pool (a bin that finds the pool exhausted is flagged and its blocks filter the whole face list
+// instead -- nothing is dropped) and the test is the exact check_border rectangle.
 #define B200R_COARSE_PER_THREAD 4
 #define B200R_COST_BUCKETS 64
 
@@ -227,23 +228,28 @@ static __global__ void __launch_bounds__(256) k_chunk_rects(const uint2* __restr
 }
 
 static __global__ void __launch_bounds__(256) k_coarse_bin(const uint2* __restrict__ rects, const uint2* __restrict__ chunk_rects,
-                                                    int* __restrict__ coarse_cnt,
-                                                    int* __restrict__ coarse_ids, int* __restrict__ tile_cost,
+                                                    int* __restrict__ coarse_cnt, int* __restrict__ chunk_table,
+                                                    int* __restrict__ coarse_pool, int* __restrict__ pool_cursor,
+                                                    int chunks_per_bin, int pool_chunks, int* __restrict__ tile_cost,
                                                     int* __restrict__ cost_hist, int nf, int is,
                                                     int coarse_px, int ncs, int tw, int th, int ntx, int nty) {
     __shared__ int s_warp[8];
     __shared__ int s_hist[B200R_COST_BUCKETS];
     __shared__ int s_cost[2048];  // tiles of this bin: (coarse_px/tw) * (coarse_px/th) <= 32 * 64 (8x4 tiles, 256 px bins)
+    __shared__ int s_overflow;
+    __shared__ int s_chunk[4];   // [0]: the chunk the list currently ends in; [1..3]: chunks allocated for the current pass
     const int bin = blockIdx.x, b = blockIdx.y;
     const int bx = bin % ncs, by = bin / ncs;
     const int x0 = bx * coarse_px, x1 = min(is, x0 + coarse_px) - 1;
     const int r0 = by * coarse_px, r1 = min(is, r0 + coarse_px) - 1;
     const int tpbx = coarse_px / tw, tpby = coarse_px / th;  // tiles per bin along x / y
     for (int i = threadIdx.x; i < tpbx * tpby; i += 256) s_cost[i] = 0;
+    if (threadIdx.x == 0) s_overflow = 0;
     __syncthreads();
     const uint2* rc = rects + (size_t)b * nf;
-    int* out = coarse_ids + ((size_t)b * ncs * ncs + bin) * nf;
+    int* tbl = chunk_table + ((size_t)b * ncs * ncs + bin) * chunks_per_bin;   // pool chunk of list positions [512 k, 512 k + 512)
     int n_out = 0;
+    bool overflow = false;
     const bool vec_ok = (reinterpret_cast<uintptr_t>(rc) & 15) == 0;  // (b*nf) even
     const int n_chunks = (nf + 255) / 256;
     const uint2* crc = chunk_rects + (size_t)b * n_chunks;
@@ -280,19 +286,42 @@ static __global__ void __launch_bounds__(256) k_coarse_bin(const uint2* __restri
         }
         int total;
         int off = n_out + block_excl_scan_256(__popc(mask), s_warp, total);
+        // chunks for list positions [n_out, n_out + total): the list so far ends inside chunk number have - 1
+        const int have = (n_out + B200R_LIST_CHUNK - 1) >> B200R_LIST_CHUNK_SHIFT;
+        const int need = ((n_out + total + B200R_LIST_CHUNK - 1) >> B200R_LIST_CHUNK_SHIFT) - have;
+        if (need > 0) {   // uniform for the CTA; a pass lists <= 1024 faces, i.e. need <= 3
+            if (threadIdx.x == 0) {
+                const int c0 = atomicAdd(pool_cursor, need);
+                if (c0 + need > pool_chunks) s_overflow = 1;
+                else for (int k = 0; k < need; k++) { tbl[have + k] = c0 + k; s_chunk[1 + k] = c0 + k; }
+            }
+            __syncthreads();
+            if (s_overflow) { overflow = true; break; }
+        }
 #pragma unroll
         for (int u = 0; u < B200R_COARSE_PER_THREAD; u++)
-            if (mask & (1u << u)) out[off++] = first + u;
+            if (mask & (1u << u)) {
+                const int c = s_chunk[(off >> B200R_LIST_CHUNK_SHIFT) - have + 1];   // have - 1 = the partly filled chunk
+                coarse_pool[((size_t)c << B200R_LIST_CHUNK_SHIFT) | (size_t)(off & (B200R_LIST_CHUNK - 1))] = first + u;
+                off++;
+            }
         n_out += total;
+        if (need > 0) {
+            __syncthreads();   // every writer has read s_chunk
+            if (threadIdx.x == 0) s_chunk[0] = s_chunk[need];
+        }
     }
     // cost model: faces listed per fine tile of the bin (x tile pixels), as a 2-D difference
     // array -- 4 shared-memory atomics per listed face at the corners of its tile range --
     // followed by row and column prefix sums.  (Adding the clipped area to every overlapped
     // tile costs ~12 atomics per face, and consecutive faces hit the same tiles: 32-way
     // conflicts made that pass half of the kernel.)
-    __syncthreads();  // out[] written by other threads of this CTA
-    for (int j = threadIdx.x; j < n_out; j += 256) {
-        const uint2 rr = __ldg(rc + out[j]);
+    __syncthreads();  // list written by other threads of this CTA
+    for (int j = threadIdx.x; j < (overflow ? nf : n_out); j += 256) {
+        // listed faces; after a pool overflow every face of the batch element, tested against the bin here
+        const int f = overflow ? j : coarse_pool[((size_t)tbl[j >> B200R_LIST_CHUNK_SHIFT] << B200R_LIST_CHUNK_SHIFT) | (size_t)(j & (B200R_LIST_CHUNK - 1))];
+        const uint2 rr = __ldg(rc + f);
+        if (overflow && !rect_overlaps(rr, x0, x1, r0, r1)) continue;
         const int fx0 = max((int)(rr.x & 0xffffu), x0), fx1 = min((int)(rr.x >> 16), x1);
         const int fr0 = max((int)(rr.y & 0xffffu), r0), fr1 = min((int)(rr.y >> 16), r1);
         const int ty_first = (fr0 - r0) / th, ty_end = (fr1 - r0) / th + 1;
@@ -314,7 +343,7 @@ static __global__ void __launch_bounds__(256) k_coarse_bin(const uint2* __restri
         int acc = 0;
         for (int ty = 0; ty < tpby; ty++) { acc += s_cost[ty * tpbx + tx]; s_cost[ty * tpbx + tx] = acc; }
     }
-    if (threadIdx.x == 0) coarse_cnt[b * ncs * ncs + bin] = n_out;
+    if (threadIdx.x == 0) coarse_cnt[b * ncs * ncs + bin] = overflow ? -1 : n_out;
     if (threadIdx.x < B200R_COST_BUCKETS) s_hist[threadIdx.x] = 0;
     __syncthreads();
     for (int i = threadIdx.x; i < tpbx * tpby; i += 256) {
@@ -337,7 +366,7 @@ static __global__ void __launch_bounds__(256) k_coarse_bin(const uint2* __restri
 // busy 8x4 block is long-running must not hide behind its cheap 16x16 parent).  Block-aggregated
 // reservation: one global atomic per (CTA, bucket) instead of one per tile.
 static __global__ void __launch_bounds__(256) k_tile_order(const int* __restrict__ tile_cost, const int* __restrict__ hist,
-                                                           int* __restrict__ cursor, int* __restrict__ tile_order,
+                                                           int* __restrict__ cursor, uint2* __restrict__ tile_order,
                                                            int B, int fntx, int fnty, int tw, int th, int ctw, int cth, int cntx, int cnty, int per) {
     __shared__ int s_start[B200R_COST_BUCKETS];
     __shared__ int s_cnt[B200R_COST_BUCKETS];
@@ -351,17 +380,20 @@ static __global__ void __launch_bounds__(256) k_tile_order(const int* __restrict
     const int total = B * fntx * fnty;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     int bkt = 0, lrank = 0;
+    uint2 entry = make_uint2(0u, 0u);
     if (t < total) {
         const int b = t / (fntx * fnty), tt = t % (fntx * fnty);
         const int cx = (tt % fntx) * tw / ctw, cy = (tt / fntx) * th / cth;
+        entry.x = (uint32_t)(tt % fntx) | ((uint32_t)(tt / fntx) << 16);
         bkt = cost_bucket(tile_cost[(size_t)b * cntx * cnty + cy * cntx + cx]);
         lrank = atomicAdd(&s_cnt[bkt], 1);
+        entry.y = (uint32_t)b | (bkt == 0 ? 0x80000000u : 0u);   // bucket 0 <=> no rectangle touches the block (exact count)
     }
     __syncthreads();
     if (threadIdx.x < B200R_COST_BUCKETS && s_cnt[threadIdx.x] > 0)
         s_base[threadIdx.x] = atomicAdd(&cursor[threadIdx.x], s_cnt[threadIdx.x]);
     __syncthreads();
-    if (t < total) tile_order[s_start[bkt] + s_base[bkt] + lrank] = t;
+    if (t < total) tile_order[s_start[bkt] + s_base[bkt] + lrank] = entry;
 }
 
 }  // namespace b200r

@@ -297,6 +297,41 @@ def test_scheduling_choice_gives_identical_results(cuda_device):
     assert np.abs(ref5["soft_colors"] - got5["soft_colors"]).max() <= COLOR_ATOL
 
 
+@pytest.mark.parametrize("pool_chunks", [0, 1, 3])
+def test_coarse_list_pool_exhaustion_changes_nothing(cuda_device, pool_chunks):
+    """The binning lists grow in 512-id chunks out of a shared pool.  With the pool capped (0: every non-empty bin, 1 / 3:
+    whichever bins lose the race) the flagged bins' blocks filter the complete face list instead: every output must be
+    bit-identical to the uncapped run, which itself is held to the oracle.  3280 faces at sigma 3e-5 put > 512 faces into
+    the central bins (multi-chunk lists)."""
+    from jrender_b200 import _lib
+    fv, tex = wl.make_scene(3280, batch=2)
+    P = osr.Params(image_size=200, sigma_val=3e-5)
+    g = np.random.default_rng(5).uniform(-1, 1, (2, 4, 200, 200)).astype(np.float32)
+    base = run_cuda(fv, tex, P, grad=g, want_faces_info=False)
+    try:
+        _lib.set_option("softras_list_pool_chunks", pool_chunks)
+        got = run_cuda(fv, tex, P, grad=g, want_faces_info=False)
+    finally:
+        _lib.set_option("softras_list_pool_chunks", -1)
+    for k in ("soft_colors", "aggrs_info", "faces_id_buffer"):
+        assert np.array_equal(base[k], got[k]), k
+    ref = run_oracle(fv, tex, P)
+    assert np.array_equal(ref["faces_id_buffer"], got["faces_id_buffer"])
+    assert np.abs(ref["soft_colors"] - got["soft_colors"]).max() <= COLOR_ATOL
+
+
+def test_workspace_is_small_and_lists_span_chunks(cuda_device):
+    """Workspace of the headline configuration (4 x 1024^2, 39 200 faces) stays below 16 MB (round 1: 162 MB with capacity
+    num_faces per bin), and a bin list longer than one chunk (every face of a 3280-face sphere inside one 64-pixel bin)
+    is read back correctly across chunk boundaries."""
+    from jrender_b200 import _lib
+    L = _lib.lib()
+    assert L.b200r_softras_workspace_bytes(4, 39200, 1024) < 16 * 2 ** 20
+    fv, tex = wl.make_scene(3280, batch=1, distance=40.0)   # the whole sphere projects into ~50 pixels
+    P = osr.Params(image_size=512)
+    check(fv, tex, P, grads=False)
+
+
 @pytest.mark.parametrize("mode", [dict(), dict(aggr_func_rgb="hard"), dict(texture_type="vertex"),
                                   dict(dist_func="barycentric", aggr_func_alpha="sum")])
 def test_backward_modes_agree_with_oracle(cuda_device, mode):
