@@ -1,6 +1,9 @@
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests -q -m gpu -x > gpurun_out/pytest_gpu.log 2>&1; tail -4 gpurun_out/pytest_gpu.log
+B200R_LIB=$PWD/jrender_b200/lib/libb200raster_tma2.so timeout 900 python -m pytest tests/test_softras_gpu.py tests/test_bake_gpu.py -q -m gpu -x > gpurun_out/pytest_tma2.log 2>&1; tail -3 gpurun_out/pytest_tma2.log
 for wl in c3 c2; do
-  echo "== $wl"; AB_NO_REF=1 timeout 300 python tools/ab_forward.py $wl 2>&1 | tail -1 | cut -c90-330
+ for v in "" _tma _tma2; do
+  echo "== $wl lib$v"; B200R_LIB=$PWD/jrender_b200/lib/libb200raster$v.so AB_NO_REF=1 timeout 300 python tools/ab_forward.py $wl 2>&1 | tail -1 | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); print(d['persistent1'])"
+ done
 done
-timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-reference-gpu > gpurun_out/bench_c3.json 2> gpurun_out/bench_c3.err; cut -c1-250 gpurun_out/bench_c3.json

@@ -46,6 +46,11 @@ def main():
         SoftRasterizeFunction(image_size=H)(fv, tex).backward(grad)
 
     res = {"workload": desc}
+    for opt in os.environ.get("AB_OPTIONS", "").split(","):   # e.g. AB_OPTIONS=softras_heavy_faces=0
+        if "=" in opt:
+            k, v = opt.split("=")
+            _lib.set_option(k, int(v))
+            res[k] = int(v)
     for persistent in (1, 0):
         _lib.set_option("softras_fwd_persistent", persistent)
         for _ in range(3):
