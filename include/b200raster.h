@@ -219,6 +219,15 @@ B200R_API int b200r_laplacian_loss(const float* vertices, const int32_t* neighbo
  * is_update [nf] int32, textures [nf, R*R, 3] updated in place where is_update != 0.  Device pointers. */
 B200R_API int b200r_bake_textures_softras(const float* image, const float* faces_uv, const int32_t* is_update, float* textures,
                                           int nf, int texture_res, int image_height, int image_width, void* stream);
+/* Replaces _load_textures_for_n3mr / load_textures_cuda_kernel (jrender/io/utils/load_textures.py:103-246), the bake of
+ * the NMR rasterizer's [nf, ts, ts, ts, 3] textures: texel (a, b, c) samples the image at the barycentric point
+ * (a, b, c) / (ts - 1) normalised to sum 1, through the face's wrapped UVs.  texture_wrapping: 0 REPEAT, 1 MIRRORED_REPEAT,
+ * 2 CLAMP_TO_EDGE, 3 CLAMP_TO_BORDER (writes zeros, like the reference); use_bilinear: bilinear (1) or nearest (0) fetch.
+ * texture_size >= 2 (the reference divides by texture_size - 1).  faces_uv is read-only here (the reference wraps it in
+ * place from every thread of the face, a race).  textures updated in place where is_update != 0. */
+B200R_API int b200r_bake_textures_n3mr(const float* image, const float* faces_uv, const int32_t* is_update, float* textures,
+                                       int nf, int texture_size, int image_height, int image_width, int texture_wrapping,
+                                       int use_bilinear, void* stream);
 
 /* ---- fused surface-mode lighting of the pre-raster stage -------------------------
  * Replaces Lighting.execute with light_mode='surface', no normal map, no SSS, one directional light:

@@ -289,6 +289,22 @@ extern "C" int ref_bake_textures_softras(const float* image, const float* faces,
 '''
 
 
+LAUNCH_BAKE_N3MR = r'''
+// ---- launcher: restates cuda_src of _load_textures_for_n3mr (io/utils/load_textures.py:217-246); the wrapping mode and
+// the sampling flavour are string-substituted into the header by the reference (:213-214), one translation unit each
+extern "C" int ref_bake_textures_n3mr_@W@_@B@(const float* image, float* faces, const int32_t* is_update, float* textures,
+                                              int nf, int texture_size, int image_height, int image_width) {
+    const int textures_size = nf * texture_size * texture_size * texture_size * 3;   // textures->num
+    const int threads = 1024;
+    const dim3 blocks((textures_size / 3 - 1) / threads + 1);
+    load_textures_cuda_kernel<float32><<<blocks, threads>>>(image, is_update, faces, textures, textures_size, texture_size,
+                                                            image_height, image_width);
+    cudaError_t e = cudaDeviceSynchronize();
+    return (int)(e != cudaSuccess ? e : cudaGetLastError());
+}
+'''
+
+
 def generate():
     os.makedirs(OUT, exist_ok=True)
     base = os.path.join(REFERENCE, "jrender/renderer/dr/softras/cuda")
@@ -313,6 +329,11 @@ def generate():
     files.append(("ref_nmr_k11.cu", PREAMBLE + hdr + LAUNCH_NMR_K11))
     hdr = _capture(os.path.join(REFERENCE, "jrender/io/utils/load_textures.py"), "_load_textures_for_softras", 4)
     files.append(("ref_bake.cu", PREAMBLE + hdr + LAUNCH_BAKE))
+    for wrap in range(4):
+        for bil in range(2):
+            hdr = _capture(os.path.join(REFERENCE, "jrender/io/utils/load_textures.py"), "_load_textures_for_n3mr", 4, extra=[wrap, bil])
+            files.append(("ref_bake_n3mr_%d_%d.cu" % (wrap, bil),
+                          PREAMBLE + hdr + LAUNCH_BAKE_N3MR.replace("@W@", str(wrap)).replace("@B@", str(bil))))
     paths = []
     for name, text in files:
         p = os.path.join(OUT, name)

@@ -141,6 +141,45 @@ def bake_main(out_dir):
     print(json.dumps(dict(name="bake_random40_R5", max_abs_vs_oracle=float(np.abs(ref - cpu).max()))), flush=True)
 
 
+def bake_n3mr_main(out_dir):
+    """Reference NMR texture-bake kernel (io/utils/load_textures.py:103-246 via oracle/build_ref.py, one build per
+    wrapping mode / sampling flavour) on seeded inputs -> ref_gpu_bake_n3mr_w<W>_b<B>.npz.
+
+    The reference wraps the UVs in place from every thread of a face; the fixtures stay away from the values for which
+    that race has more than one outcome: no integer UVs (REPEAT maps 0 -> 1 -> 0), and for MIRRORED_REPEAT only UVs with an
+    even integer part (the reference re-reads the value between testing mod(x, 2) < 1 and wrapping, so a value another
+    thread has already mirrored would be mirrored back)."""
+    import ctypes as C
+    import torch
+    from oracle import bake as obake
+    L = ref_gpu.lib()
+    dev = torch.device("cuda:0")
+    nf, ts, H, W = 40, 4, 37, 53
+    for wrap, bil in ((0, 1), (0, 0), (1, 1), (2, 1), (2, 0), (3, 1)):
+        rng = np.random.default_rng(11 + 2 * wrap + bil)
+        image = rng.random((H, W, 3), dtype=np.float32)
+        if wrap == 1:
+            uv = (rng.uniform(0.02, 0.98, (nf, 3, 2)) + 2.0 * rng.integers(-1, 2, (nf, 3, 2))).astype(np.float32)
+        else:
+            uv = rng.uniform(-1.4, 2.4, (nf, 3, 2)).astype(np.float32)
+            uv[np.abs(uv - np.round(uv)) < 1e-3] += np.float32(0.01)
+        upd = (rng.random(nf) > 0.2).astype(np.int32)
+        tex0 = np.full((nf, ts, ts, ts, 3), 0.5, np.float32)
+        fn = getattr(L, "ref_bake_textures_n3mr_%d_%d" % (wrap, bil))
+        fn.restype = C.c_int
+        fn.argtypes = [C.c_void_p] * 4 + [C.c_int] * 4
+        t = [torch.from_numpy(a.copy()).to(dev) for a in (image, uv, upd, tex0)]
+        rc = fn(*[C.c_void_p(x.data_ptr()) for x in t], nf, ts, H, W)
+        assert rc == 0, rc
+        ref = t[3].cpu().numpy()
+        cpu = obake.bake_textures_for_n3mr(image, uv, tex0, upd, wrap, bool(bil))
+        name = "ref_gpu_bake_n3mr_w%d_b%d" % (wrap, bil)
+        np.savez_compressed(os.path.join(out_dir, name + ".npz"), image=image, faces_uv=uv, is_update=upd, textures_in=tex0, textures=ref,
+                            texture_wrapping=wrap, use_bilinear=bil,
+                            provenance=json.dumps(dict(gpu=torch.cuda.get_device_name(0), source="jrender/io/utils/load_textures.py:103-246 via oracle/build_ref.py")))
+        print(json.dumps(dict(name=name, max_abs_vs_oracle=float(np.abs(ref - cpu).max()))), flush=True)
+
+
 def main():
     import torch
     out_dir = os.path.join("gpurun_out", "golden")
@@ -148,6 +187,7 @@ def main():
     report = []
     if "--bake-only" in sys.argv:
         bake_main(out_dir)
+        bake_n3mr_main(out_dir)
         return
     if "--nmr-only" in sys.argv:
         nmr_main(out_dir, report)

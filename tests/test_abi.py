@@ -25,7 +25,7 @@ def lib():
 def test_header_declares_entry_points():
     syms = declared_symbols()
     for s in ["b200r_softras_forward", "b200r_softras_backward", "b200r_softras_workspace_bytes", "b200r_softras_state_bytes",
-              "b200r_softras_forward_aa", "b200r_softras_backward_aa", "b200r_surface_lighting_forward", "b200r_bake_textures_softras",
+              "b200r_softras_forward_aa", "b200r_softras_backward_aa", "b200r_surface_lighting_forward", "b200r_bake_textures_softras", "b200r_bake_textures_n3mr",
               "b200r_last_error", "b200r_launch_count", "b200r_profile_read"]:
         assert s in syms
 

@@ -1,4 +1,4 @@
-"""GPU tests of the texture-bake kernel (csrc/bake_api.cu <- jrender/io/utils/load_textures.py:3-101) and of BASELINE
+"""GPU tests of the texture-bake kernels (csrc/bake_api.cu <- jrender/io/utils/load_textures.py:3-101 SoftRas, :103-246 NMR) and of BASELINE
 config C1 as the reference configures it (demo1-render.py:21-45: spot cow, 5856 faces, texture_res 5, 256^2).
 
 Tolerances: bake vs the numpy oracle 2e-6 absolute (same formulas unfused on both sides; image values in [0, 1]); vs the
@@ -38,6 +38,88 @@ def test_bake_kernel_matches_oracle_and_reference_kernel(cuda_device):
         g = np.load(p)
         got = bake_textures_for_softras(g["image"], g["faces_uv"], g["textures_in"], g["is_update"], device=cuda_device).cpu().numpy()
         assert np.abs(got - g["textures"]).max() <= 1e-5
+
+
+@pytest.mark.parametrize("wrap,bilinear", [(w, b) for w in range(4) for b in (True, False)])
+def test_n3mr_bake_kernel_matches_oracle(cuda_device, wrap, bilinear):
+    """b200r_bake_textures_n3mr (<- load_textures.py:103-246) against oracle/bake.py for every wrapping mode and both
+    sampling flavours, UVs far outside [0, 1] (odd and even integer parts, negative), 2e-6 absolute; untouched faces keep
+    their texels; texture_size 1 is refused."""
+    from jrender_b200 import _lib
+    from jrender_b200.io import bake_textures_for_n3mr
+    rng = np.random.default_rng(17 + wrap)
+    for nf, ts, H, W in ((40, 4, 37, 53), (130, 2, 8, 8), (9, 6, 64, 31)):
+        image = rng.random((H, W, 3), dtype=np.float32)
+        uv = rng.uniform(-2.3, 3.1, (nf, 3, 2)).astype(np.float32)
+        upd = (rng.random(nf) > 0.3).astype(np.int32)
+        tex0 = rng.random((nf, ts, ts, ts, 3), dtype=np.float32)
+        got = bake_textures_for_n3mr(image, uv, tex0, upd, wrap, bilinear, device=cuda_device).cpu().numpy()
+        ref = obake.bake_textures_for_n3mr(image, uv, tex0, upd, wrap, bilinear)
+        if bilinear or wrap == 3:
+            assert np.abs(got - ref).max() <= 2e-6
+        else:   # nearest: a sample point within float rounding of a texel boundary may pick the neighbour
+            bad = np.abs(got - ref).max(axis=-1) > 2e-6
+            assert bad.mean() <= 2e-3
+        assert np.array_equal(got[upd == 0], tex0[upd == 0])
+    with pytest.raises(_lib.B200RasterError):
+        bake_textures_for_n3mr(np.zeros((4, 4, 3), np.float32), np.zeros((2, 3, 2), np.float32), np.zeros((2, 1, 1, 1, 3), np.float32),
+                               np.ones(2, np.int32), 0, True, device=cuda_device)
+
+
+def test_n3mr_bake_kernel_matches_reference_kernel_golden(cuda_device):
+    """... and against the reference's own kernel run on a B200 (tests/golden/ref_gpu_bake_n3mr_*.npz), 1e-5 (its build
+    contracts a*b+c)."""
+    import glob
+    from jrender_b200.io import bake_textures_for_n3mr
+    files = sorted(glob.glob(os.path.join(G, "ref_gpu_bake_n3mr_*.npz")))
+    assert files, "golden fixtures missing"
+    for p in files:
+        g = np.load(p)
+        got = bake_textures_for_n3mr(g["image"], g["faces_uv"], g["textures_in"], g["is_update"], int(g["texture_wrapping"]),
+                                     bool(int(g["use_bilinear"])), device=cuda_device).cpu().numpy()
+        d = np.abs(got - g["textures"]).max(axis=-1)
+        if int(g["use_bilinear"]):
+            assert d.max() <= 1e-5, p
+        else:
+            assert (d > 1e-5).mean() <= 2e-3, p
+
+
+@pytest.mark.skipif(not os.path.exists(SPOT), reason="reference assets not staged (python -m tools.stage_assets where /root/reference exists)")
+def test_n3mr_loader_bakes_the_spot_texture(cuda_device):
+    """load_obj(dr_type='n3mr', load_texture=True) as demo4 would call it: [nf, ts, ts, ts, 3] textures whose baked texels
+    equal the oracle's bake of the same image / UVs."""
+    from jrender_b200 import io as jio
+    v, f, t = jio.load_obj(SPOT, load_texture=True, dr_type='n3mr', texture_res=4)
+    assert tuple(t.shape) == (5856, 4, 4, 4, 3) and tuple(f.shape) == (5856, 3)
+    faces_uv, names = jio._parse_texture_faces(SPOT)
+    image = jio._imread_rgb01(os.path.join(os.path.dirname(SPOT), "spot_texture.png"))[::-1]
+    ref = obake.bake_textures_for_n3mr(np.ascontiguousarray(image), faces_uv, np.full((5856, 4, 4, 4, 3), 0.5, np.float32),
+                                       np.ones(5856, np.int32), 0, True)
+    assert np.abs(t.numpy() - ref).max() <= 2e-6
+    assert float(t.std()) > 0.05
+
+
+@pytest.mark.skipif(not os.path.exists(SPOT), reason="reference assets not staged (python -m tools.stage_assets where /root/reference exists)")
+def test_spot_through_the_nmr_renderer_against_oracle(cuda_device):
+    """The textured cow through Renderer(dr_type='n3mr') (demo4's renderer): loader + ts^3 bake + lighting + transform +
+    N3mrRasterizer; the rasterizer's inputs are taken from the pipeline and handed to the NMR oracle, whose rgb map the
+    returned image must equal bit for bit (after the host side's transpose and vertical flip, n3mr.py:239-247)."""
+    from oracle import nmr as onmr
+    from jrender_b200.n3mr import vertices_to_faces
+    mesh = jr.Mesh.from_obj(SPOT, load_texture=True, texture_res=4, dr_type='n3mr').to(cuda_device)
+    assert tuple(mesh.textures.shape) == (1, 5856, 4, 4, 4, 3)
+    renderer = jr.Renderer(dr_type='n3mr', image_size=256, anti_aliasing=False)
+    renderer.transform.set_eyes_from_angles(2.732, 30, 40)
+    mesh.reset_()
+    img = renderer.render_mesh(mesh, mode='rgb')
+    assert tuple(img.shape) == (1, 3, 256, 256)
+    faces = vertices_to_faces(mesh.vertices, mesh.faces)
+    faces = torch.cat((faces, faces.flip(-1)), dim=1).detach().cpu().numpy()
+    tex = torch.cat((mesh.textures, mesh.textures.permute((0, 1, 4, 3, 2, 5))), dim=1).detach().cpu().numpy()
+    ref = onmr.forward(np.ascontiguousarray(faces), np.ascontiguousarray(tex), 256, 0.1, 100.0, 1e-3, (0, 0, 0), True, False, False)
+    want = np.ascontiguousarray(ref["rgb_map"].transpose(0, 3, 1, 2)[:, :, ::-1])
+    assert np.array_equal(img.detach().cpu().numpy(), want)
+    assert 0.05 < float((img.sum(1) > 0).float().mean()) < 0.6 and float(img.std()) > 0.05
 
 
 @pytest.mark.skipif(not os.path.exists(SPOT), reason="reference assets not staged (python -m tools.stage_assets where /root/reference exists)")

@@ -117,3 +117,24 @@ def test_bake_oracle_matches_reference_kernel_golden():
     out = obake.bake_textures_for_softras(g["image"], g["faces_uv"], g["textures_in"], g["is_update"])
     assert np.abs(out - g["textures"]).max() <= 1e-5
     assert np.array_equal(out[g["is_update"] == 0], g["textures_in"][g["is_update"] == 0])
+
+
+def test_n3mr_bake_oracle_matches_reference_kernel_golden():
+    """oracle/bake.py:bake_textures_for_n3mr against the reference's own kernel (io/utils/load_textures.py:103-246, one build
+    per wrapping mode / sampling flavour, oracle/build_ref.py) run on a B200 (oracle/make_ref_golden.py --bake-only).
+    Bilinear: 1e-5 (the reference build contracts a*b+c).  Nearest: the same texel except where the sample point lies
+    within that rounding of a texel boundary (<= 0.2 % of the texels)."""
+    import glob
+    from oracle import bake as obake
+    files = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "ref_gpu_bake_n3mr_*.npz")))
+    assert len(files) >= 5
+    for p in files:
+        g = np.load(p)
+        out = obake.bake_textures_for_n3mr(g["image"], g["faces_uv"], g["textures_in"], g["is_update"], int(g["texture_wrapping"]),
+                                           bool(int(g["use_bilinear"])))
+        d = np.abs(out - g["textures"]).max(axis=-1)
+        if int(g["use_bilinear"]):
+            assert d.max() <= 1e-5, p
+        else:
+            assert (d > 1e-5).mean() <= 2e-3, p
+        assert np.array_equal(out[g["is_update"] == 0], g["textures_in"][g["is_update"] == 0])
