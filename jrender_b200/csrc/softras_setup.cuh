@@ -237,7 +237,8 @@ static __global__ void __launch_bounds__(256) k_coarse_bin(const uint2* __restri
     __shared__ int s_hist[B200R_COST_BUCKETS];
     __shared__ int s_cost[2048];  // tiles of this bin: (coarse_px/tw) * (coarse_px/th) <= 32 * 64 (8x4 tiles, 256 px bins)
     __shared__ int s_overflow;
-    __shared__ int s_chunk[4];   // [0]: the chunk the list currently ends in; [1..3]: chunks allocated for the current pass
+    __shared__ int s_chunk[4];    // [0]: the chunk the list currently ends in; [1..3]: chunks allocated for the current pass
+    __shared__ int s_hits[256];   // passes of the current group of 256 that touch the bin, ascending
     const int bin = blockIdx.x, b = blockIdx.y;
     const int bx = bin % ncs, by = bin / ncs;
     const int x0 = bx * coarse_px, x1 = min(is, x0 + coarse_px) - 1;
@@ -249,89 +250,108 @@ static __global__ void __launch_bounds__(256) k_coarse_bin(const uint2* __restri
     const uint2* rc = rects + (size_t)b * nf;
     int* tbl = chunk_table + ((size_t)b * ncs * ncs + bin) * chunks_per_bin;   // pool chunk of list positions [512 k, 512 k + 512)
     int n_out = 0;
-    bool overflow = false;
+    bool overflow = false;   // the pool ran out: the list is abandoned (coarse_cnt = -1), the cost model keeps counting
     const bool vec_ok = (reinterpret_cast<uintptr_t>(rc) & 15) == 0;  // (b*nf) even
     const int n_chunks = (nf + 255) / 256;
     const uint2* crc = chunk_rects + (size_t)b * n_chunks;
-    for (int base = 0; base < nf; base += 256 * B200R_COARSE_PER_THREAD) {
-        {   // whole pass (4 runs of 256 faces) outside the bin: skip it, uniformly for the CTA
-            bool any = false;
-#pragma unroll
-            for (int u = 0; u < B200R_COARSE_PER_THREAD; u++) {
-                const int c = base / 256 + u;
-                if (c < n_chunks && rect_overlaps(__ldg(crc + c), x0, x1, r0, r1)) any = true;
-            }
-            if (!any) continue;
-        }
-        const int first = base + threadIdx.x * B200R_COARSE_PER_THREAD;
-        uint32_t mask = 0;
-        uint2 rr[B200R_COARSE_PER_THREAD];
-        if (vec_ok && first + B200R_COARSE_PER_THREAD <= nf) {
+    constexpr int PT = B200R_COARSE_PER_THREAD;
+    const int n_pass = (nf + 256 * PT - 1) / (256 * PT);   // one pass = 256 threads x 4 consecutive faces = 4 runs of 256
+
+    // the 4 rectangles a thread owns in pass `pass` (empty rectangles behind the last face)
+    auto load_pass = [&](int pass, uint2 (&rr)[PT]) {
+        const int first = pass * 256 * PT + threadIdx.x * PT;
+        if (vec_ok && first + PT <= nf) {
             const uint4 a = __ldg(reinterpret_cast<const uint4*>(rc + first));
             const uint4 c = __ldg(reinterpret_cast<const uint4*>(rc + first + 2));
             rr[0] = make_uint2(a.x, a.y); rr[1] = make_uint2(a.z, a.w);
             rr[2] = make_uint2(c.x, c.y); rr[3] = make_uint2(c.z, c.w);
-#pragma unroll
-            for (int u = 0; u < B200R_COARSE_PER_THREAD; u++)
-                if (rect_overlaps(rr[u], x0, x1, r0, r1)) mask |= 1u << u;
         } else {
 #pragma unroll
-            for (int u = 0; u < B200R_COARSE_PER_THREAD; u++) {
-                rr[u] = make_uint2(1u, 1u);  // empty
-                if (first + u < nf) {
-                    rr[u] = __ldg(rc + first + u);
-                    if (rect_overlaps(rr[u], x0, x1, r0, r1)) mask |= 1u << u;
+            for (int u = 0; u < PT; u++) rr[u] = (first + u < nf) ? __ldg(rc + first + u) : make_uint2(1u, 1u);
+        }
+    };
+
+    for (int g = 0; g < n_pass; g += 256) {
+        // ---- which of the passes g .. g + 255 touch the bin: one thread per pass tests the union rectangles of its four
+        // runs (k_chunk_rects), all at once -- consecutive faces are close on screen, so most passes miss (31 of 39 at C3)
+        // and testing them one after the other cost a dependent L2 round trip each
+        const int my_pass = g + threadIdx.x;
+        bool hit = false;
+        if (my_pass < n_pass) {
+#pragma unroll
+            for (int u = 0; u < PT; u++) {
+                const int c = my_pass * PT + u;
+                if (c < n_chunks && rect_overlaps(__ldg(crc + c), x0, x1, r0, r1)) hit = true;
+            }
+        }
+        int n_hit;
+        const int hpos = block_excl_scan_flag<8>(hit, s_warp, n_hit);
+        if (hit) s_hits[hpos] = my_pass;
+        __syncthreads();
+
+        // ---- the hitting passes in ascending order; the next pass's rectangles are in flight while this one is scanned
+        uint2 nxt[PT];
+        if (n_hit > 0) load_pass(s_hits[0], nxt);
+        for (int i = 0; i < n_hit; i++) {
+            const int first = s_hits[i] * 256 * PT + threadIdx.x * PT;
+            uint2 rr[PT];
+#pragma unroll
+            for (int u = 0; u < PT; u++) rr[u] = nxt[u];
+            if (i + 1 < n_hit) load_pass(s_hits[i + 1], nxt);
+            uint32_t mask = 0;
+#pragma unroll
+            for (int u = 0; u < PT; u++)
+                if (rect_overlaps(rr[u], x0, x1, r0, r1)) mask |= 1u << u;
+            int total;
+            int off = n_out + block_excl_scan_256(__popc(mask), s_warp, total);
+            if (!overflow) {
+                // chunks for list positions [n_out, n_out + total): the list so far ends inside chunk number have - 1
+                const int have = (n_out + B200R_LIST_CHUNK - 1) >> B200R_LIST_CHUNK_SHIFT;
+                const int need = ((n_out + total + B200R_LIST_CHUNK - 1) >> B200R_LIST_CHUNK_SHIFT) - have;
+                if (need > 0) {   // uniform for the CTA; a pass lists <= 1024 faces, i.e. need <= 3
+                    if (threadIdx.x == 0) {
+                        const int c0 = atomicAdd(pool_cursor, need);
+                        if (c0 + need > pool_chunks) s_overflow = 1;
+                        else for (int k = 0; k < need; k++) { tbl[have + k] = c0 + k; s_chunk[1 + k] = c0 + k; }
+                    }
+                    __syncthreads();
+                    overflow = s_overflow != 0;
+                }
+                if (!overflow) {
+#pragma unroll
+                    for (int u = 0; u < PT; u++)
+                        if (mask & (1u << u)) {
+                            const int c = s_chunk[(off >> B200R_LIST_CHUNK_SHIFT) - have + 1];   // have - 1 = the partly filled chunk
+                            coarse_pool[((size_t)c << B200R_LIST_CHUNK_SHIFT) | (size_t)(off & (B200R_LIST_CHUNK - 1))] = first + u;
+                            off++;
+                        }
+                    if (need > 0) {
+                        __syncthreads();   // every writer has read s_chunk
+                        if (threadIdx.x == 0) s_chunk[0] = s_chunk[need];
+                    }
                 }
             }
-        }
-        int total;
-        int off = n_out + block_excl_scan_256(__popc(mask), s_warp, total);
-        // chunks for list positions [n_out, n_out + total): the list so far ends inside chunk number have - 1
-        const int have = (n_out + B200R_LIST_CHUNK - 1) >> B200R_LIST_CHUNK_SHIFT;
-        const int need = ((n_out + total + B200R_LIST_CHUNK - 1) >> B200R_LIST_CHUNK_SHIFT) - have;
-        if (need > 0) {   // uniform for the CTA; a pass lists <= 1024 faces, i.e. need <= 3
-            if (threadIdx.x == 0) {
-                const int c0 = atomicAdd(pool_cursor, need);
-                if (c0 + need > pool_chunks) s_overflow = 1;
-                else for (int k = 0; k < need; k++) { tbl[have + k] = c0 + k; s_chunk[1 + k] = c0 + k; }
-            }
-            __syncthreads();
-            if (s_overflow) { overflow = true; break; }
-        }
+            n_out += total;
+            // ---- cost model: faces per fine tile of the bin as a 2-D difference array -- 4 shared-memory atomics per
+            // listed face at the corners of its tile range, row / column prefix sums at the end.  (Adding the clipped
+            // area to every overlapped tile costs ~12 atomics per face with 32-way conflicts.)  The rectangle is still
+            // in registers here; a separate pass over the finished list re-fetched id and rectangle of every entry.
 #pragma unroll
-        for (int u = 0; u < B200R_COARSE_PER_THREAD; u++)
-            if (mask & (1u << u)) {
-                const int c = s_chunk[(off >> B200R_LIST_CHUNK_SHIFT) - have + 1];   // have - 1 = the partly filled chunk
-                coarse_pool[((size_t)c << B200R_LIST_CHUNK_SHIFT) | (size_t)(off & (B200R_LIST_CHUNK - 1))] = first + u;
-                off++;
-            }
-        n_out += total;
-        if (need > 0) {
-            __syncthreads();   // every writer has read s_chunk
-            if (threadIdx.x == 0) s_chunk[0] = s_chunk[need];
+            for (int u = 0; u < PT; u++)
+                if (mask & (1u << u)) {
+                    const int fx0 = max((int)(rr[u].x & 0xffffu), x0), fx1 = min((int)(rr[u].x >> 16), x1);
+                    const int fr0 = max((int)(rr[u].y & 0xffffu), r0), fr1 = min((int)(rr[u].y >> 16), r1);
+                    const int ty_first = (fr0 - r0) / th, ty_end = (fr1 - r0) / th + 1;
+                    const int tx_first = (fx0 - x0) / tw, tx_end = (fx1 - x0) / tw + 1;
+                    atomicAdd(&s_cost[ty_first * tpbx + tx_first], 1);
+                    if (tx_end < tpbx) atomicAdd(&s_cost[ty_first * tpbx + tx_end], -1);
+                    if (ty_end < tpby) {
+                        atomicAdd(&s_cost[ty_end * tpbx + tx_first], -1);
+                        if (tx_end < tpbx) atomicAdd(&s_cost[ty_end * tpbx + tx_end], 1);
+                    }
+                }
         }
-    }
-    // cost model: faces listed per fine tile of the bin (x tile pixels), as a 2-D difference
-    // array -- 4 shared-memory atomics per listed face at the corners of its tile range --
-    // followed by row and column prefix sums.  (Adding the clipped area to every overlapped
-    // tile costs ~12 atomics per face, and consecutive faces hit the same tiles: 32-way
-    // conflicts made that pass half of the kernel.)
-    __syncthreads();  // list written by other threads of this CTA
-    for (int j = threadIdx.x; j < (overflow ? nf : n_out); j += 256) {
-        // listed faces; after a pool overflow every face of the batch element, tested against the bin here
-        const int f = overflow ? j : coarse_pool[((size_t)tbl[j >> B200R_LIST_CHUNK_SHIFT] << B200R_LIST_CHUNK_SHIFT) | (size_t)(j & (B200R_LIST_CHUNK - 1))];
-        const uint2 rr = __ldg(rc + f);
-        if (overflow && !rect_overlaps(rr, x0, x1, r0, r1)) continue;
-        const int fx0 = max((int)(rr.x & 0xffffu), x0), fx1 = min((int)(rr.x >> 16), x1);
-        const int fr0 = max((int)(rr.y & 0xffffu), r0), fr1 = min((int)(rr.y >> 16), r1);
-        const int ty_first = (fr0 - r0) / th, ty_end = (fr1 - r0) / th + 1;
-        const int tx_first = (fx0 - x0) / tw, tx_end = (fx1 - x0) / tw + 1;
-        atomicAdd(&s_cost[ty_first * tpbx + tx_first], 1);
-        if (tx_end < tpbx) atomicAdd(&s_cost[ty_first * tpbx + tx_end], -1);
-        if (ty_end < tpby) {
-            atomicAdd(&s_cost[ty_end * tpbx + tx_first], -1);
-            if (tx_end < tpbx) atomicAdd(&s_cost[ty_end * tpbx + tx_end], 1);
-        }
+        __syncthreads();   // s_hits is rewritten by the next group
     }
     __syncthreads();
     for (int ty = threadIdx.x; ty < tpby; ty += 256) {  // along x

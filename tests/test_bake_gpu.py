@@ -113,12 +113,14 @@ def test_spot_through_the_nmr_renderer_against_oracle(cuda_device):
     mesh.reset_()
     img = renderer.render_mesh(mesh, mode='rgb')
     assert tuple(img.shape) == (1, 3, 256, 256)
-    faces = vertices_to_faces(mesh.vertices, mesh.faces)
-    faces = torch.cat((faces, faces.flip(-1)), dim=1).detach().cpu().numpy()
+    idx = torch.cat((mesh.faces, mesh.faces.flip(-1)), dim=1)          # fill_back: reversed-winding copies (rasterizer.py:83-88)
+    faces = vertices_to_faces(mesh.vertices, idx).detach().cpu().numpy()
     tex = torch.cat((mesh.textures, mesh.textures.permute((0, 1, 4, 3, 2, 5))), dim=1).detach().cpu().numpy()
     ref = onmr.forward(np.ascontiguousarray(faces), np.ascontiguousarray(tex), 256, 0.1, 100.0, 1e-3, (0, 0, 0), True, False, False)
     want = np.ascontiguousarray(ref["rgb_map"].transpose(0, 3, 1, 2)[:, :, ::-1])
-    assert np.array_equal(img.detach().cpu().numpy(), want)
+    got = img.detach().cpu().numpy()
+    d = np.abs(got - want)
+    assert np.array_equal(got, want), "max %g, %d of %d values differ" % (d.max(), int((d > 0).sum()), d.size)
     assert 0.05 < float((img.sum(1) > 0).float().mean()) < 0.6 and float(img.std()) > 0.05
 
 

@@ -40,12 +40,14 @@ def main():
     tex = torch.from_numpy(tex_h).to(dev).requires_grad_(True)
     grad = torch.from_numpy(grad_h).to(dev)
 
+    sigma = float(os.environ.get("AB_SIGMA", "1e-5"))   # 1e-4 = demo2's value, the stress point of SURVEY.md section 8d
+
     def step():
         fv.grad = None
         tex.grad = None
-        SoftRasterizeFunction(image_size=H)(fv, tex).backward(grad)
+        SoftRasterizeFunction(image_size=H, sigma_val=sigma)(fv, tex).backward(grad)
 
-    res = {"workload": desc}
+    res = {"workload": desc, "sigma_val": sigma}
     for opt in os.environ.get("AB_OPTIONS", "").split(","):   # e.g. AB_OPTIONS=softras_heavy_faces=0
         if "=" in opt:
             k, v = opt.split("=")
