@@ -320,6 +320,22 @@ def test_coarse_list_pool_exhaustion_changes_nothing(cuda_device, pool_chunks):
     assert np.abs(ref["soft_colors"] - got["soft_colors"]).max() <= COLOR_ATOL
 
 
+def test_pool_exhaustion_at_headline_size(cuda_device):
+    """One image of the headline configuration (1024^2, 39 200 faces) with the list pool capped at 64 chunks: most of the
+    ~100 non-empty bins are flagged and their blocks filter all 39 200 faces; ids, colours and aggregates must not move."""
+    from jrender_b200 import _lib
+    fv, tex = wl.make_scene(39200, batch=1)
+    P = osr.Params(image_size=1024)
+    base = run_cuda(fv, tex, P, want_faces_info=False)
+    try:
+        _lib.set_option("softras_list_pool_chunks", 64)
+        got = run_cuda(fv, tex, P, want_faces_info=False)
+    finally:
+        _lib.set_option("softras_list_pool_chunks", -1)
+    for k in ("soft_colors", "aggrs_info", "faces_id_buffer"):
+        assert np.array_equal(base[k], got[k]), k
+
+
 def test_workspace_is_small_and_lists_span_chunks(cuda_device):
     """Workspace of the headline configuration (4 x 1024^2, 39 200 faces) stays below 16 MB (round 1: 162 MB with capacity
     num_faces per bin), and a bin list longer than one chunk (every face of a 3280-face sphere inside one 64-pixel bin)
