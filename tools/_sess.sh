@@ -1,6 +1,9 @@
 mkdir -p gpurun_out
-N=${1:-2}
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 tools/check_peer_broadcast.py > gpurun_out/peer_check.log 2>&1; grep -E "PEER|Error|error" gpurun_out/peer_check.log | head -5
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --steps 20 --warmup 5 --no-cpu-baseline --no-reference-gpu > gpurun_out/bench_c3_${N}gpu.json 2> gpurun_out/bench_c3_${N}gpu.err; grep -v "CudaIPCTypes\|OMP_NUM\|^\*\*\*" gpurun_out/bench_c3_${N}gpu.err | tail -3
-python -c "
-import json; d=json.loads(open('gpurun_out/bench_c3_${N}gpu.json').read().strip().splitlines()[-1]); print(d['value'], d['ms_per_step'], d.get('allgather_images_ms')); g=d.get('gather_in_step'); g.pop('note',None); print(json.dumps(g))"
+B200R_LIB=$PWD/jrender_b200/lib/libb200raster_tma2.so timeout 900 python -m pytest tests/test_softras_gpu.py -q -m gpu -x > gpurun_out/pytest_tma2.log 2>&1; tail -2 gpurun_out/pytest_tma2.log
+for wl in c3 c2; do
+ for v in "" _tma2 _tma2b; do
+  echo "== $wl lib$v"; B200R_LIB=$PWD/jrender_b200/lib/libb200raster$v.so AB_NO_REF=1 timeout 300 python tools/ab_forward.py $wl 2>&1 | tail -1 | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); print(d['persistent1'])"
+ done
+done
