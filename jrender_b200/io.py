@@ -148,6 +148,14 @@ def load_textures_n3mr(filename_obj, filename_mtl, texture_res, texture_wrapping
         textures[names == material_name] = color
     ts = int(texture_res)
     textures = np.ascontiguousarray(np.broadcast_to(textures[:, None, None, None, :], (faces_uv.shape[0], ts, ts, ts, 3)), dtype=np.float32)
+    if ts < 2 and texture_filenames:
+        # The reference's kernel divides by (texture_size - 1.): with Mesh.from_obj's default texture_res = 1 every sample
+        # point is 0 / 0 and the baked texels are garbage (demo4-optim_textures.py loads the cow this way and then replaces
+        # the textures).  Here the material colours are kept and the image is not sampled.
+        import warnings
+        warnings.warn("load_obj(dr_type='n3mr', texture_res=1): one texel per face cannot be sampled from the texture image "
+                      "(the reference divides by texture_res - 1); material colours kept, use texture_res >= 2 to bake")
+        return textures
     for material_name, filename_texture in texture_filenames.items():
         image = _imread_rgb01(os.path.join(os.path.dirname(filename_obj), filename_texture))[::-1, :, :]
         textures = bake_textures_for_n3mr(np.ascontiguousarray(image), faces_uv, textures, (names == material_name).astype(np.int32),

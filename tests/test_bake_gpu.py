@@ -161,3 +161,20 @@ def test_c1_spot_render_as_demo1_against_oracle(cuda_device):
     # gradient reaches the un-lit texture leaf through the fused lighting kernel
     img.backward(torch.from_numpy(g[:, :3].copy()).to(cuda_device))
     assert tex_leaf.grad is not None and float(tex_leaf.grad.abs().max()) > 0
+
+
+@pytest.mark.skipif(not os.path.exists(SPOT), reason="reference assets not staged (python -m tools.stage_assets where /root/reference exists)")
+def test_demo4_texture_optimisation_converges(cuda_device):
+    """examples/demo4_optim_textures.py (port of the reference's demo4: NMR renderer, orthogonal camera, ambient light, Adam on
+    a [1, nf, 4, 4, 4, 3] texture parameter): 60 iterations against a render of the cow's own baked texture must cut the
+    sum-of-squares loss by more than half; and the reference's own loader call (texture_res left at 1) must not fail."""
+    import warnings
+    from examples import demo4_optim_textures as d4
+    model, losses = d4.run(SPOT, None, iters=60, device=str(cuda_device))
+    assert np.isfinite(losses).all() and losses[-1] < 0.5 * losses[0], (losses[0], losses[-1])
+    g = model.textures.grad
+    assert g is not None and float(g.abs().max()) > 0
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        m = jr.Mesh.from_obj(SPOT, dr_type='n3mr', load_texture=True)   # demo4-optim_textures.py:24
+        assert tuple(m.textures.shape) == (1, 5856, 1, 1, 1, 3) and any("texture_res" in str(x.message) for x in w)
