@@ -510,7 +510,8 @@ def run_ours(args, rank, world, local_rank):
                         "step_pipelined_gather_ms": timed(step_pipelined),
                         "note": "each includes a 256 MiB L2 flush write per step (~0.08 ms), unlike ms_per_step; chunk = images per "
                                 "forward launch (chunk == images_per_gpu: one launch, the gather hides behind the backward; smaller "
-                                "chunks hide it behind the next chunk's raster too but pay the per-launch host cost again); pipelined = the "
+                                "chunks hide it behind the next chunk's raster too but every launch is bound by the serial chain of its pole "
+                                "blocks, ~0.8 ms whatever the number of images in it); pipelined = the "
                                 "batch of step n is collected during step n+1, behind its own backward and the next raster"}
         pipe["pending"].result()
 

@@ -60,7 +60,8 @@ class OverlappedImageGather:
         full = g.result()                           # [world * 4, 4, H, W]; the current stream waits for the side stream
 
     One launch for the whole batch is the fast configuration (2 GPUs: 1.44 ms per step against 1.40 without and 1.58 with
-    a blocking gather); chunk = 1 or 2 re-pays the per-launch host cost of the rasterizer and was slower (2.2 / 3.6 ms).
+    a blocking gather); chunk = 1 or 2 was slower (2.2 / 3.6 ms): a forward launch at this mesh is bound by the serial chain
+    of its heaviest blocks (~0.8 ms) however few images it holds, so splitting the batch multiplies that.
 
     Sample r * images_per_rank + i of the result is chunk i of rank r, i.e. the same order all_gather_images gives.
     Equal shards only.  On CPU tensors (gloo, tests) the calls run synchronously.  Without a process group the result
