@@ -388,9 +388,9 @@ __device__ __forceinline__ void k9_scan(const float* __restrict__ prow, const in
             if (OWNER) own = __ldg(o);
         }
         float diff;
-        if (MODE == 1) diff = c.x - __fmaf_rn(r2, c.w, __fmaf_rn(r1, c.z, r0 * c.y));
-        else if (MODE == 2) diff = c.x - ra * c.y;
-        else diff = c.x - __fmaf_rn(ra, cga, __fmaf_rn(r2, c.w, __fmaf_rn(r1, c.z, r0 * c.y)));
+        if (MODE == 1) diff = __fmaf_rn(-r2, c.w, __fmaf_rn(-r1, c.z, __fmaf_rn(-r0, c.y, c.x)));
+        else if (MODE == 2) diff = __fmaf_rn(-ra, c.y, c.x);
+        else diff = __fmaf_rn(-ra, cga, __fmaf_rn(-r2, c.w, __fmaf_rn(-r1, c.z, __fmaf_rn(-r0, c.y, c.x))));
         const bool mine = !OWNER || cown == fn;
         const float d = (mine && !(diff <= 0.f)) ? diff : 0.f;   // :503 / :587 `if (diff_grad <= 0) continue`
         const float delta = d1f - d1_cross;   // (d1 - d1_cross), one rounding like the reference's
@@ -446,9 +446,11 @@ template <int MODE>
 __device__ __forceinline__ void k9_term(const K9Px<MODE>& c, float r0, float r1, float r2, float ra, float delta,
                                         float k0, float k1, float e0, float e1, float& acc0, float& acc1) {
     float diff;
-    if (MODE == 1) diff = c.q.x - __fmaf_rn(r2, c.q.w, __fmaf_rn(r1, c.q.z, r0 * c.q.y));
-    else if (MODE == 2) diff = c.q.x - ra * c.q.y;
-    else diff = c.q.x - __fmaf_rn(ra, c.ga, __fmaf_rn(r2, c.q.w, __fmaf_rn(r1, c.q.z, r0 * c.q.y)));
+    // A - sum_k ref_k * grad_k as one fma chain off A (the negations are operand modifiers): one instruction fewer per
+    // record than forming the sum first
+    if (MODE == 1) diff = __fmaf_rn(-r2, c.q.w, __fmaf_rn(-r1, c.q.z, __fmaf_rn(-r0, c.q.y, c.q.x)));
+    else if (MODE == 2) diff = __fmaf_rn(-ra, c.q.y, c.q.x);
+    else diff = __fmaf_rn(-ra, c.ga, __fmaf_rn(-r2, c.q.w, __fmaf_rn(-r1, c.q.z, __fmaf_rn(-r0, c.q.y, c.q.x))));
     const float d = max_nan(diff, 0.f);
     acc0 = __fmaf_rn(-d, rcp_approx(__fmaf_rn(delta, k0, e0)), acc0);
     acc1 = __fmaf_rn(-d, rcp_approx(__fmaf_rn(delta, k1, e1)), acc1);
